@@ -1,0 +1,183 @@
+/*
+ * sdb200.h — C ABI of libsdb200.so, the B200-native batch demodulator that sits
+ * behind PySignalduino's SDProtocols.demodulate() hot path.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / C++ types), so it
+ * can be bound from ctypes (what pysignalduino_b200/capi.py does), cffi, or any
+ * other FFI.  Each function cites the reference interface it replaces
+ * (paths relative to the PySignalduino source tree).
+ *
+ * Threading: one handle may be used by one host thread at a time
+ * (reference: engine called through asyncio.to_thread, signalduino/controller.py:252).
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1
+
+/* ---- limits of the packed domain ------------------------------------------------ */
+#define SDB_MAX_SLOTS   8      /* P0..P7: pulse-pattern slots per message (firmware emits <= 8) */
+#define SDB_MAX_DIGITS  1024   /* digits in one D= stream (BASELINE config 3: D <= 1024)       */
+#define SDB_DIGIT_OTHER 0xE    /* any character of D that is not '0'..'9'                      */
+#define SDB_DIGIT_PAD   0xF    /* padding nibble after the last digit                          */
+#define SDB_MAX_HEX     512    /* hex characters in one MC / MN D= field                       */
+
+/* ---- return codes --------------------------------------------------------------- */
+#define SDB_OK            0
+#define SDB_E_ARG        -1    /* bad argument / malformed table blob          */
+#define SDB_E_CUDA       -2    /* CUDA runtime error, see sdb_last_error()     */
+#define SDB_E_OVERFLOW   -3    /* hit / bit arena too small: counters say how much is needed */
+#define SDB_E_NOGPU      -4    /* no CUDA device: there is NO CPU fallback     */
+
+/* ---- message kinds (SDProtocols.demodulate(msg, msg_type), sd_protocols/sd_protocols.py:60-74) */
+#define SDB_KIND_MS 0          /* demodulate_ms, sd_protocols/message_synced.py:10-243   */
+#define SDB_KIND_MU 1          /* demodulate_mu, sd_protocols/message_unsynced.py:11-296 */
+#define SDB_KIND_MC 2          /* demodulate_mc, sd_protocols/sd_protocols.py:76-111 + manchester.py:49-144 */
+#define SDB_KIND_MN 3          /* demodulate_mn, sd_protocols/sd_protocols.py:113-155    */
+
+/* ---- per-message status (replaces Python exceptions that escape demodulate()) ---- */
+#define SDB_ST_OK          0   /* returned a (possibly empty) list                                  */
+#define SDB_ST_INDEXERROR  1   /* message_unsynced.py:212 chunks[-1] on an empty capture            */
+#define SDB_ST_TYPEERROR   2   /* manchester.py:84 / :120, helpers.py:114 (MC as shipped; id 57)    */
+#define SDB_ST_VALUEERROR  3   /* message_synced.py:174 range(..., 0) with signal_width == 0        */
+
+/*
+ * One MS / MU message after host-side packing of the parser dict
+ * (input contract: message_synced.py:21-66, message_unsynced.py:22-35).
+ * 48 bytes, 16-byte aligned; algorithmic input bytes/message = 48 + ceil(dlen/2).
+ */
+typedef struct SdbPulseMsg {
+    int32_t  pat[SDB_MAX_SLOTS]; /* pulse values, slot order = insertion order of the P<d> keys (pattern_utils.py:73,83 tie-break) */
+    uint32_t doff;               /* start of this message's digit stream in the digit pool, in 16-byte units */
+    uint16_t dlen;               /* number of digits                                           */
+    uint8_t  npat;               /* valid slots 0..8                                           */
+    uint8_t  cp;                 /* MS: slot index whose id == int(CP) (message_synced.py:59-66), 0xFF if none */
+    uint32_t pat_ids;            /* nibble s = decimal id (0..9) that slot s is addressed by in D */
+    uint8_t  flags;              /* SDB_MSG_* */
+    uint8_t  rsv[3];
+} SdbPulseMsg;
+
+#define SDB_MSG_VALID 0x01       /* passed the host-side input gates; a message without it yields [] */
+
+/*
+ * One MC / MN message (sd_protocols.py:79-88: protocol_id, data, clock, bit_length).
+ * 16 bytes.
+ */
+typedef struct SdbHexMsg {
+    uint32_t doff;               /* start of the hex nibbles in the digit pool, in 16-byte units */
+    uint16_t hlen;               /* number of hex characters                                     */
+    uint16_t proto;              /* index of protocol_id in protocol-table order, 0xFFFF = unknown/missing */
+    int32_t  clock;              /* MC: C=                                                       */
+    int16_t  bitlen;             /* MC: L= (clamped to int16)                                    */
+    uint8_t  flags;              /* SDB_MSG_VALID | SDB_HEX_* */
+    uint8_t  rsv;
+} SdbHexMsg;
+
+#define SDB_HEX_TOGGLE_POLARITY 0x02  /* messagetype 'Mc' or firmware "V 3.2." (manchester.py:94-96)          */
+
+/* Per-message result slot, 8 bytes. hits of message m = hits[hit_off .. hit_off+nhits) in reference order. */
+typedef struct SdbMsgOut {
+    uint32_t hit_off;
+    uint16_t nhits;
+    uint8_t  status;             /* SDB_ST_* */
+    uint8_t  rsv;
+} SdbMsgOut;
+
+/* One decoded message ("hit"), 16 bytes.  payload bits live in the bit arena. */
+typedef struct SdbHit {
+    uint32_t msg;                /* index of the message in the batch                                   */
+    uint32_t bits_off;           /* first 32-bit word of this hit in the bit arena                      */
+    uint16_t proto;              /* index in protocol-table order (JSON order, sd_protocols.py:49-52)   */
+    uint16_t nbits;              /* meta.bit_length (message_synced.py:237 / message_unsynced.py:286)   */
+    uint16_t aux;                /* MS/MU: match ordinal within (msg, proto); MC/MN: decoder-specific   */
+    uint8_t  flags;              /* SDB_HIT_* */
+    uint8_t  rsv;
+} SdbHit;
+
+#define SDB_HIT_HAS_F   0x01     /* a second plane of nbits follows: 1 = symbol is 'F' (float)           */
+#define SDB_HIT_LIST    0x02     /* MC TFA: element of the duplicate list (manchester.py:705-717)        */
+#define SDB_HIT_FIELDS  0x04     /* MN: bits hold decoder fields, host renders "OK 9 ..." / "OK 24 ..."  */
+
+/* Device-side counters written by every demod call (16 bytes). */
+typedef struct SdbCounters {
+    uint32_t hits;               /* hit records needed (may exceed capacity -> SDB_E_OVERFLOW)           */
+    uint32_t words;              /* bit-arena words needed                                               */
+    uint32_t raised;             /* messages whose status != SDB_ST_OK                                   */
+    uint32_t rsv;
+} SdbCounters;
+
+typedef struct SdbHandle SdbHandle;
+
+/* Library / device ------------------------------------------------------------- */
+int         sdb_abi_version(void);
+const char *sdb_last_error(const SdbHandle *h);   /* h may be NULL for creation errors */
+
+/*
+ * Create an engine on CUDA device `device` from a compiled protocol table blob
+ * (pysignalduino_b200/table.py; replaces SDProtocols.__init__/_load_protocols,
+ * sd_protocols/sd_protocols.py:25-41).  Fails with SDB_E_NOGPU when no device exists.
+ */
+int  sdb_create(const void *blob, size_t blob_len, int device, SdbHandle **out);
+void sdb_destroy(SdbHandle *h);
+
+/*
+ * Device-resident batch demodulation of MS or MU messages: all pointers are DEVICE
+ * pointers, the call only enqueues work on `stream` (a cudaStream_t passed as void*).
+ * Replaces SDProtocols.demodulate(msg, "MS"|"MU") for n messages
+ * (sd_protocols.py:64-71 -> message_synced.py:10 / message_unsynced.py:11).
+ */
+int sdb_demod_pulse_device(SdbHandle *h, int kind,
+                           const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                           SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                           uint32_t *d_bits, uint32_t bits_cap,
+                           SdbCounters *d_counters, void *stream);
+
+/* Same for MC / MN (sd_protocols.py:76-155, manchester.py, helpers.py:223-716).
+ * mc_repaired: 0 = as shipped (TypeError, SURVEY §8c "strict"), 1 = the two documented one-line repairs. */
+int sdb_demod_hex_device(SdbHandle *h, int kind, int mc_repaired,
+                         const SdbHexMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                         SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                         uint32_t *d_bits, uint32_t bits_cap,
+                         SdbCounters *d_counters, void *stream);
+
+/*
+ * Host-buffer convenience call (what SDProtocols.demodulate()/demodulate_batch() use):
+ * copies the packed batch to the device, runs the kernels, copies results back and
+ * synchronises.  All pointers are HOST pointers.  `msgs` is SdbPulseMsg[] for MS/MU and
+ * SdbHexMsg[] for MC/MN.  On SDB_E_OVERFLOW `counters` holds the required capacities.
+ */
+int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
+                   const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                   SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                   uint32_t *bits, uint32_t bits_cap, SdbCounters *counters);
+
+/*
+ * Host-side result formatting (the payload string of every hit:
+ * preamble + hex/bits + postamble, message_synced.py:224-231, message_unsynced.py:254-274,
+ * manchester.py:131-132).  Writes NUL-free strings into `pool`; str_off has nhits+1 entries.
+ * Returns SDB_E_OVERFLOW (and the needed size in *pool_used) when pool_cap is too small.
+ */
+int sdb_format_hits(const SdbHandle *h, int kind,
+                    const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
+                    char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used);
+
+/*
+ * Unit-op entry points: run ONE device function on ONE input (a 1-warp launch).  They back
+ * the scalar helper methods of the drop-in class so that the reference's own unit tests
+ * (tests/test_postdemodulation.py, tests/test_manchester_protocols.py, tests/test_helpers.py)
+ * exercise the device code.  bits are one byte per bit (0/1).
+ */
+int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_t n_in,
+                       uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

@@ -1,0 +1,43 @@
+"""Import the REAL reference (build container only: /root/reference is absent on the GPU box).
+
+Used by oracle/validate_vs_reference.py and tests/golden/make_golden.py to pin the C oracle
+and to generate the committed golden fixtures.  Never imported by the product or by
+anything that runs on the GPU box.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+from typing import Any, Dict, List, Tuple
+
+REFERENCE_ROOT = Path("/root/reference")
+
+
+def available() -> bool:
+    return (REFERENCE_ROOT / "sd_protocols" / "sd_protocols.py").exists()
+
+
+def reference_class():
+    if not available():
+        raise RuntimeError("reference tree not present (expected only in the build container)")
+    if str(REFERENCE_ROOT) not in sys.path:
+        sys.path.insert(0, str(REFERENCE_ROOT))
+    from sd_protocols import SDProtocols  # type: ignore
+
+    return SDProtocols
+
+
+def canonical(results: List[Dict[str, Any]]) -> List[Tuple[str, str, int]]:
+    out = []
+    for r in results:
+        meta = r.get("meta") or {}
+        out.append((str(r["protocol_id"]), str(r["payload"]), int(meta.get("bit_length", -1))))
+    return out
+
+
+def ref_demodulate(proto, msg: Dict[str, Any], msg_type: str):
+    """-> (status, [(protocol_id, payload, bit_length)...]) with exceptions mapped to their type name."""
+    try:
+        return ("ok", canonical(proto.demodulate(dict(msg), msg_type)))
+    except Exception as e:  # noqa: BLE001 - the exception type IS the result
+        return (type(e).__name__, [])

@@ -1,0 +1,303 @@
+"""Host-side packing of parser dicts into the fixed-width batch arrays of the C ABI.
+
+Replaces the per-message input handling at the top of the reference demodulators:
+  * MS gates and P# parsing  — sd_protocols/message_synced.py:21-66
+  * MU gate and P# parsing   — sd_protocols/message_unsynced.py:22-35
+  * MC / MN argument pickup  — sd_protocols/sd_protocols.py:79-88, :115-129
+
+Layout (include/sdb200.h): ``SdbPulseMsg`` 48 B/message + a nibble-packed digit pool whose
+per-message streams start on 16-byte boundaries and are padded with 0xF nibbles.
+
+Inputs the packed domain cannot represent (non-integer pulse values, pattern ids >= 10,
+more than 8 pattern slots, D longer than SDB_MAX_DIGITS) raise :class:`DomainError`;
+they are never silently decoded differently from the reference.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+MAX_SLOTS = 8
+MAX_DIGITS = 1024
+MAX_HEX = 512
+DIGIT_OTHER = 0xE
+DIGIT_PAD = 0xF
+
+KIND_MS, KIND_MU, KIND_MC, KIND_MN = 0, 1, 2, 3
+KIND_BY_NAME = {"MS": KIND_MS, "MU": KIND_MU, "MC": KIND_MC, "MN": KIND_MN}
+
+MSG_VALID = 0x01
+HEX_TOGGLE_POLARITY = 0x02
+
+PULSE_DTYPE = np.dtype(
+    [
+        ("pat", "<i4", (MAX_SLOTS,)),
+        ("doff", "<u4"),
+        ("dlen", "<u2"),
+        ("npat", "u1"),
+        ("cp", "u1"),
+        ("pat_ids", "<u4"),
+        ("flags", "u1"),
+        ("rsv", "u1", (3,)),
+    ]
+)
+assert PULSE_DTYPE.itemsize == 48
+
+HEX_DTYPE = np.dtype(
+    [
+        ("doff", "<u4"),
+        ("hlen", "<u2"),
+        ("proto", "<u2"),
+        ("clock", "<i4"),
+        ("bitlen", "<i2"),
+        ("flags", "u1"),
+        ("rsv", "u1"),
+    ]
+)
+assert HEX_DTYPE.itemsize == 16
+
+MSGOUT_DTYPE = np.dtype([("hit_off", "<u4"), ("nhits", "<u2"), ("status", "u1"), ("rsv", "u1")])
+HIT_DTYPE = np.dtype(
+    [
+        ("msg", "<u4"),
+        ("bits_off", "<u4"),
+        ("proto", "<u2"),
+        ("nbits", "<u2"),
+        ("aux", "<u2"),
+        ("flags", "u1"),
+        ("rsv", "u1"),
+    ]
+)
+COUNTERS_DTYPE = np.dtype([("hits", "<u4"), ("words", "<u4"), ("raised", "<u4"), ("rsv", "<u4")])
+assert MSGOUT_DTYPE.itemsize == 8 and HIT_DTYPE.itemsize == 16 and COUNTERS_DTYPE.itemsize == 16
+
+
+class DomainError(ValueError):
+    """The message cannot be represented in the packed batch format."""
+
+
+_DIGIT_LUT = np.full(256, DIGIT_OTHER, dtype=np.uint8)
+_DIGIT_LUT[ord("0") : ord("9") + 1] = np.arange(10, dtype=np.uint8)
+
+_HEX_LUT = np.full(256, 0xFF, dtype=np.uint8)
+_HEX_LUT[ord("0") : ord("9") + 1] = np.arange(10, dtype=np.uint8)
+_HEX_LUT[ord("A") : ord("F") + 1] = np.arange(10, 16, dtype=np.uint8)
+_HEX_LUT[ord("a") : ord("f") + 1] = np.arange(10, 16, dtype=np.uint8)
+
+
+def parse_patterns(msg_data: Dict[str, Any]) -> Dict[str, float]:
+    """``P<d>`` keys -> ``{str(int(d)): float(value)}`` in dict insertion order.
+
+    message_synced.py:50-57 / message_unsynced.py:28-35: a later duplicate id overwrites the
+    value but keeps the first position; a value ``float()`` rejects is skipped.
+    """
+    patterns: Dict[str, float] = {}
+    for key, val in msg_data.items():
+        if key.startswith("P") and key[1:].isdigit():
+            try:
+                pidx = str(int(key[1:]))
+                patterns[pidx] = float(val)
+            except ValueError:
+                pass
+    return patterns
+
+
+def _ms_gates(msg_data: Dict[str, Any]) -> bool:
+    """message_synced.py:21-47 — D, CP, SP (and R when present) must be digit strings."""
+    raw_data = msg_data.get("data", "")
+    if not raw_data or not raw_data.isdigit():
+        return False
+    cp = msg_data.get("CP", "")
+    if not cp or not cp.isdigit():
+        return False
+    sp = msg_data.get("SP", "")
+    if not sp or not sp.isdigit():
+        return False
+    if "R" in msg_data:
+        if not msg_data.get("R", "").isdigit():
+            return False
+    return True
+
+
+class PulseBatch:
+    """Packed MS or MU batch plus the host-only fields needed to format results."""
+
+    __slots__ = ("kind", "msgs", "digits", "rssi", "clock", "n")
+
+    def __init__(self, kind: int, msgs: np.ndarray, digits: np.ndarray, rssi: List[Any], clock: np.ndarray):
+        self.kind = kind
+        self.msgs = msgs
+        self.digits = digits
+        self.rssi = rssi      # msg_data.get('R') per message (meta.rssi is the raw value)
+        self.clock = clock    # MS: abs(P[CP]) per message (meta.clock); unused for MU
+        self.n = len(msgs)
+
+    def algorithmic_input_bytes(self) -> int:
+        """48 B header + ceil(dlen/2) digit bytes per message."""
+        return int(48 * self.n + ((self.msgs["dlen"].astype(np.int64) + 1) // 2).sum())
+
+
+def pack_digit_streams(streams: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """Nibble-pack digit arrays (values 0..15) into a pool; returns (pool, doff in 16-byte units)."""
+    n = len(streams)
+    lens = np.fromiter((len(s) for s in streams), dtype=np.int64, count=n)
+    padded = (lens + 31) // 32 * 32            # 32 nibbles = 16 bytes
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(padded, out=offs[1:])
+    nib = np.full(int(offs[-1]) + 64, DIGIT_PAD, dtype=np.uint8)   # +32 B tail so device windows may over-read
+    for i, s in enumerate(streams):
+        if len(s):
+            nib[offs[i] : offs[i] + len(s)] = s
+    pool = (nib[0::2] | (nib[1::2] << 4)).astype(np.uint8)
+    return pool, (offs[:-1] // 32).astype(np.uint32)
+
+
+def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
+    """Pack MS (kind 0) or MU (kind 1) parser dicts."""
+    n = len(msgs)
+    rec = np.zeros(n, dtype=PULSE_DTYPE)
+    rec["cp"] = 0xFF
+    streams: List[np.ndarray] = []
+    rssi: List[Any] = []
+    clock = np.zeros(n, dtype=np.float64)
+    empty = np.zeros(0, dtype=np.uint8)
+    for i, m in enumerate(msgs):
+        rssi.append(m.get("R"))
+        data = m.get("data", "")
+        if kind == KIND_MS:
+            valid = _ms_gates(m)
+        else:
+            valid = bool(data)                     # message_unsynced.py:22-25
+        if not valid:
+            streams.append(empty)
+            continue
+        if not isinstance(data, str):
+            raise DomainError(f"message {i}: 'data' must be a str")
+        if len(data) > MAX_DIGITS:
+            raise DomainError(f"message {i}: D has {len(data)} digits (max {MAX_DIGITS})")
+        patterns = parse_patterns(m)
+        if len(patterns) > MAX_SLOTS:
+            raise DomainError(f"message {i}: {len(patterns)} pattern slots (max {MAX_SLOTS})")
+        ids = 0
+        for s, (pidx, val) in enumerate(patterns.items()):
+            if len(pidx) != 1:
+                raise DomainError(f"message {i}: pattern id {pidx!r} is not a single digit")
+            if val != val or val in (float("inf"), float("-inf")) or val != int(val) or abs(val) > 2147483647:
+                raise DomainError(f"message {i}: pattern value {val!r} is not an int32")
+            rec["pat"][i, s] = int(val)
+            ids |= int(pidx) << (4 * s)
+        rec["pat_ids"][i] = ids
+        rec["npat"][i] = len(patterns)
+        rec["flags"][i] = MSG_VALID
+        if kind == KIND_MS:
+            cp_key = str(int(m.get("CP", "")))     # message_synced.py:33,59
+            if cp_key in patterns:
+                rec["cp"][i] = list(patterns).index(cp_key)
+                clock[i] = abs(patterns[cp_key])
+        raw = data.encode("ascii", "replace")      # one byte per character
+        streams.append(_DIGIT_LUT[np.frombuffer(raw, dtype=np.uint8)])
+        rec["dlen"][i] = len(raw)
+    pool, doff = pack_digit_streams(streams)
+    rec["doff"] = doff
+    return PulseBatch(kind, rec, pool, rssi, clock)
+
+
+def unpack_pulse(batch: PulseBatch, i: int) -> Dict[str, Any]:
+    """Inverse of :func:`pack_pulse` for one message (used by corpus tools and tests).
+
+    Returns a parser-style dict that packs back to the same record.  SP is synthesised
+    (the reference validates but never uses it, message_synced.py:35-39).
+    """
+    r = batch.msgs[i]
+    d: Dict[str, Any] = {}
+    if not (r["flags"] & MSG_VALID):
+        return {"data": ""}
+    for s in range(int(r["npat"])):
+        d[f"P{(int(r['pat_ids']) >> (4 * s)) & 0xF}"] = str(int(r["pat"][s]))
+    base = int(r["doff"]) * 16
+    dl = int(r["dlen"])
+    by = batch.digits[base : base + (dl + 1) // 2]
+    nib = np.empty(len(by) * 2, dtype=np.uint8)
+    nib[0::2] = by & 0xF
+    nib[1::2] = by >> 4
+    d["data"] = "".join("0123456789??????"[v] for v in nib[:dl])
+    if batch.kind == KIND_MS:
+        cp = int(r["cp"])
+        d["CP"] = str((int(r["pat_ids"]) >> (4 * cp)) & 0xF) if cp != 0xFF else "9"
+        d["SP"] = "0"
+    if batch.rssi[i] is not None:
+        d["R"] = batch.rssi[i]
+    return d
+
+
+class HexBatch:
+    """Packed MC or MN batch."""
+
+    __slots__ = ("kind", "msgs", "digits", "n", "protocol_ids", "data")
+
+    def __init__(self, kind, msgs, digits, protocol_ids, data):
+        self.kind = kind
+        self.msgs = msgs
+        self.digits = digits
+        self.protocol_ids = protocol_ids
+        self.data = data
+        self.n = len(msgs)
+
+    def algorithmic_input_bytes(self) -> int:
+        return int(16 * self.n + ((self.msgs["hlen"].astype(np.int64) + 1) // 2).sum())
+
+
+def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, int],
+             toggle_polarity: bool = False) -> HexBatch:
+    """Pack MC (kind 2) or MN (kind 3) dicts: protocol_id, data (hex), clock, bit_length.
+
+    D must be upper-case hex (what the firmware emits): the reference's polarity inversion is an
+    upper-case-only ``str.translate`` (manchester.py:36) and several MN converters echo the input
+    verbatim, neither of which a 4-bit nibble can express -> DomainError for lower-case letters.
+    """
+    n = len(msgs)
+    rec = np.zeros(n, dtype=HEX_DTYPE)
+    rec["proto"] = 0xFFFF
+    streams: List[np.ndarray] = []
+    pids: List[Any] = []
+    datas: List[Any] = []
+    empty = np.zeros(0, dtype=np.uint8)
+    for i, m in enumerate(msgs):
+        pid = m.get("protocol_id")
+        pids.append(pid)
+        data = m.get("data", "") if kind == KIND_MC else m.get("data")
+        datas.append(data)
+        ok = pid in proto_index if isinstance(pid, str) else False
+        if kind == KIND_MN and "protocol_id" not in m:
+            ok = False
+        if not ok:
+            streams.append(empty)
+            continue
+        rec["proto"][i] = proto_index[pid]
+        rec["flags"][i] = MSG_VALID | (HEX_TOGGLE_POLARITY if toggle_polarity else 0)
+        if data is None:
+            data = ""
+        if not isinstance(data, str):
+            raise DomainError(f"message {i}: 'data' must be a str")
+        raw = data.encode("ascii", "replace")
+        if len(raw) > MAX_HEX:
+            raise DomainError(f"message {i}: D has {len(raw)} hex characters (max {MAX_HEX})")
+        b = np.frombuffer(raw, dtype=np.uint8)
+        nib = _HEX_LUT[b]
+        if (nib == 0xFF).any():
+            raise DomainError(f"message {i}: D is not a hex string")
+        if ((b >= ord("a")) & (b <= ord("f"))).any():
+            raise DomainError(f"message {i}: D must be upper-case hex (what the firmware emits)")
+        streams.append(nib)
+        rec["hlen"][i] = len(raw)
+        if kind == KIND_MC:
+            clock = m.get("clock", 0)
+            bitlen = m.get("bit_length", 0)
+            if not isinstance(clock, int) or not isinstance(bitlen, int):
+                raise DomainError(f"message {i}: clock / bit_length must be int")
+            rec["clock"][i] = max(-(2**31), min(2**31 - 1, clock))
+            rec["bitlen"][i] = max(-32768, min(32767, bitlen))
+    pool, doff = pack_digit_streams(streams)
+    rec["doff"] = doff
+    return HexBatch(kind, rec, pool, pids, datas)
