@@ -1,0 +1,188 @@
+"""ctypes binding of libsdb200.so (include/sdb200.h) — the only way the package reaches the GPU.
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if that or
+``sdb_create`` fails (no CUDA device) the error propagates to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import pack
+from .table import CompiledTable
+
+LIB_PATH = Path(__file__).resolve().parent / "libsdb200.so"
+
+SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU = 0, -1, -2, -3, -4
+ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR = 0, 1, 2, 3
+STATUS_EXC = {ST_INDEXERROR: IndexError, ST_TYPEERROR: TypeError, ST_VALUEERROR: ValueError}
+STATUS_NAMES = {ST_OK: "ok", ST_INDEXERROR: "IndexError", ST_TYPEERROR: "TypeError", ST_VALUEERROR: "ValueError"}
+
+HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
+
+EXPORTS = [
+    "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
+    "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
+    "sdb_format_hits", "sdb_unit_postdemod",
+]
+
+
+class SdbError(RuntimeError):
+    pass
+
+
+class NoGpuError(SdbError):
+    """No CUDA device: the demodulator has no CPU path."""
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        from .build_ext import build
+
+        build()
+    L = C.CDLL(str(LIB_PATH))
+    L.sdb_abi_version.restype = C.c_int
+    L.sdb_last_error.restype = C.c_char_p
+    L.sdb_last_error.argtypes = [C.c_void_p]
+    L.sdb_create.restype = C.c_int
+    L.sdb_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.sdb_destroy.restype = None
+    L.sdb_destroy.argtypes = [C.c_void_p]
+    dev_args = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.sdb_demod_pulse_device.restype = C.c_int
+    L.sdb_demod_pulse_device.argtypes = dev_args
+    L.sdb_demod_hex_device.restype = C.c_int
+    L.sdb_demod_hex_device.argtypes = [C.c_void_p, C.c_int, C.c_int] + dev_args[2:]
+    L.sdb_demod_host.restype = C.c_int
+    L.sdb_demod_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                 C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.sdb_format_hits.restype = C.c_int
+    L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.POINTER(C.c_size_t)]
+    L.sdb_unit_postdemod.restype = C.c_int
+    L.sdb_unit_postdemod.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    if L.sdb_abi_version() != 1:
+        raise SdbError("libsdb200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+class Result:
+    """Raw result arrays of one batch call."""
+
+    __slots__ = ("kind", "out", "hits", "bits", "counters")
+
+    def __init__(self, kind, out, hits, bits, counters):
+        self.kind, self.out, self.hits, self.bits, self.counters = kind, out, hits, bits, counters
+
+
+class Engine:
+    """One sdb handle = one compiled protocol table resident on one GPU."""
+
+    def __init__(self, table: CompiledTable, device: int = 0):
+        self.lib = load_library()
+        self.table = table
+        self.device = device
+        h = C.c_void_p()
+        blob = table.blob
+        rc = self.lib.sdb_create(blob, len(blob), device, C.byref(h))
+        if rc != SDB_OK:
+            msg = (self.lib.sdb_last_error(None) or b"").decode()
+            raise (NoGpuError if rc == SDB_E_NOGPU else SdbError)(f"sdb_create failed ({rc}): {msg}")
+        self.h = h
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.sdb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc: int, what: str) -> SdbError:
+        return SdbError(f"{what} failed ({rc}): {(self.lib.sdb_last_error(self.h) or b'').decode()}")
+
+    # ---- host-buffer call ------------------------------------------------------------------
+    def demod_host(self, batch, mc_repaired: bool = False, hits_cap: int = 0, bits_cap: int = 0) -> Result:
+        n = batch.n
+        kind = batch.kind
+        msgs = np.ascontiguousarray(batch.msgs)
+        digits = np.ascontiguousarray(batch.digits)
+        out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
+        hits_cap = hits_cap or max(1024, 4 * n)
+        bits_cap = bits_cap or max(4096, 16 * n)
+        ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
+        while True:
+            hits = np.empty(hits_cap, dtype=pack.HIT_DTYPE)
+            bits = np.empty(bits_cap, dtype=np.uint32)
+            rc = self.lib.sdb_demod_host(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
+                                         digits.nbytes, n, out.ctypes.data, hits.ctypes.data, hits_cap,
+                                         bits.ctypes.data, bits_cap, ctr.ctypes.data)
+            if rc == SDB_E_OVERFLOW:
+                hits_cap = max(hits_cap, int(ctr["hits"][0]) + 16)
+                bits_cap = max(bits_cap, int(ctr["words"][0]) + 16)
+                continue
+            if rc != SDB_OK:
+                raise self._err(rc, "sdb_demod_host")
+            nh, nw = int(ctr["hits"][0]), int(ctr["words"][0])
+            return Result(kind, out, hits[:nh], bits[:nw], ctr[0])
+
+    # ---- device-pointer call (pointers are ints, e.g. torch tensor.data_ptr()) ---------------
+    def demod_pulse_device(self, kind: int, d_msgs: int, d_digits: int, n: int, d_out: int, d_hits: int, hits_cap: int,
+                           d_bits: int, bits_cap: int, d_ctr: int, stream: int = 0) -> None:
+        rc = self.lib.sdb_demod_pulse_device(self.h, kind, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits,
+                                             bits_cap, d_ctr, stream)
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_demod_pulse_device")
+
+    def demod_hex_device(self, kind: int, mc_repaired: bool, d_msgs: int, d_digits: int, n: int, d_out: int,
+                         d_hits: int, hits_cap: int, d_bits: int, bits_cap: int, d_ctr: int, stream: int = 0) -> None:
+        rc = self.lib.sdb_demod_hex_device(self.h, kind, 1 if mc_repaired else 0, d_msgs, d_digits, n, d_out, d_hits,
+                                           hits_cap, d_bits, bits_cap, d_ctr, stream)
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_demod_hex_device")
+
+    # ---- formatting ------------------------------------------------------------------------
+    def format_hits(self, kind: int, hits: np.ndarray, bits: np.ndarray) -> Tuple[bytes, np.ndarray]:
+        """Payload strings of all hits: (pool bytes, offsets[nhits+1])."""
+        nh = len(hits)
+        hits = np.ascontiguousarray(hits)
+        bits = np.ascontiguousarray(bits)
+        off = np.zeros(nh + 1, dtype=np.uint64)
+        cap = max(64, 40 * nh)
+        while True:
+            pool = np.empty(cap, dtype=np.uint8)
+            used = C.c_size_t(0)
+            rc = self.lib.sdb_format_hits(self.h, kind, hits.ctypes.data, nh, bits.ctypes.data if len(bits) else None,
+                                          pool.ctypes.data, cap, off.ctypes.data, C.byref(used))
+            if rc == SDB_E_OVERFLOW:
+                cap = used.value + 16
+                continue
+            if rc != SDB_OK:
+                raise self._err(rc, "sdb_format_hits")
+            return pool[: used.value].tobytes(), off
+
+    # ---- unit ops --------------------------------------------------------------------------
+    def unit_postdemod(self, method: int, bits_in) -> Tuple[int, List[int]]:
+        a = np.ascontiguousarray(np.asarray(list(bits_in), dtype=np.uint8))
+        out = np.zeros(len(a) + 64, dtype=np.uint8)
+        n_out, rcode = C.c_uint32(0), C.c_int(0)
+        rc = self.lib.sdb_unit_postdemod(self.h, method, a.ctypes.data if len(a) else None, len(a), out.ctypes.data,
+                                         len(out), C.byref(n_out), C.byref(rcode))
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_unit_postdemod")
+        return rcode.value, [int(x) for x in out[: n_out.value]]

@@ -1,0 +1,327 @@
+/*
+ * sdb_capi.cu — the extern "C" boundary of libsdb200.so (declared in include/sdb200.h).
+ *
+ * Host logic only: table upload, buffer management, kernel launches, host<->device copies and
+ * result formatting.  There is NO CPU decode path in this library: without a CUDA device
+ * sdb_create() fails with SDB_E_NOGPU.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdb200.h"
+#include "sdb_pulse.h"
+#include "sdb_table.h"
+
+struct SdbHandle {
+    int device = 0;
+    int sm_count = 0;
+    int grid_ms = 0, grid_mu = 0, grid_hex = 0;
+    std::vector<uint8_t> blob;          /* host copy (formatting needs preamble / flags) */
+    uint8_t *d_blob = nullptr;
+    SdbDevTable tab{};
+    std::string err;
+    /* buffers of the host-pointer convenience path (grown on demand) */
+    void *d_msgs = nullptr;   size_t cap_msgs = 0;
+    uint8_t *d_digits = nullptr; size_t cap_digits = 0;
+    SdbMsgOut *d_out = nullptr;  size_t cap_out = 0;
+    SdbHit *d_hits = nullptr;    size_t cap_hits = 0;
+    uint32_t *d_bits = nullptr;  size_t cap_bits = 0;
+    SdbCounters *d_ctr = nullptr;
+    uint8_t *d_unit = nullptr;          /* unit-op scratch */
+    cudaStream_t stream = nullptr;
+};
+
+static thread_local std::string g_create_err;
+
+static int set_err(SdbHandle *h, int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+    std::string s = what;
+    if (ce != cudaSuccess) { s += ": "; s += cudaGetErrorString(ce); }
+    if (h) h->err = s; else g_create_err = s;
+    return code;
+}
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return set_err(h, SDB_E_CUDA, #call, _e); } while (0)
+
+extern "C" int sdb_abi_version(void) { return SDB_ABI_VERSION; }
+
+extern "C" const char *sdb_last_error(const SdbHandle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHandle **out)
+{
+    SdbHandle *h = nullptr;
+    if (!blob || !out || blob_len < sizeof(SdbTblHeader)) return set_err(nullptr, SDB_E_ARG, "sdb_create: bad arguments");
+    const SdbTblHeader *hd = static_cast<const SdbTblHeader *>(blob);
+    if (hd->magic != SDB_TBL_MAGIC || hd->version != SDB_TBL_VERSION || hd->total != blob_len)
+        return set_err(nullptr, SDB_E_ARG, "sdb_create: not a protocol table blob of this version");
+    if (hd->n_clk > SDB_MAX_CLK) return set_err(nullptr, SDB_E_ARG, "sdb_create: too many distinct clocks");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return set_err(nullptr, SDB_E_NOGPU, "sdb_create: no CUDA device (there is no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return set_err(nullptr, SDB_E_ARG, "sdb_create: bad device index");
+    h = new SdbHandle();
+    h->device = device;
+    auto fail = [&](int code) { std::string e = h->err; sdb_destroy(h); g_create_err = e; return code; };
+#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_err(h, SDB_E_CUDA, #call, _e); return fail(SDB_E_CUDA); } } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    h->blob.assign(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + blob_len);
+    CKC(cudaMalloc(&h->d_blob, blob_len));
+    CKC(cudaMemcpy(h->d_blob, blob, blob_len, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&h->d_ctr, sizeof(SdbCounters)));
+    CKC(cudaMalloc(&h->d_unit, 16384));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const uint8_t *b = h->d_blob;
+    h->tab.ms = reinterpret_cast<const SdbPulseProto *>(b + hd->off_ms);
+    h->tab.mu = reinterpret_cast<const SdbPulseProto *>(b + hd->off_mu);
+    h->tab.ms_pf = reinterpret_cast<const SdbPrefilter *>(b + hd->off_ms_pf);
+    h->tab.mu_pf = reinterpret_cast<const SdbPrefilter *>(b + hd->off_mu_pf);
+    h->tab.clk = reinterpret_cast<const double *>(b + hd->off_clk);
+    h->tab.rank = reinterpret_cast<const uint16_t *>(b + hd->off_rank);
+    h->tab.mm = reinterpret_cast<const SdbMmItem *>(b + hd->off_mm);
+    h->tab.hex = reinterpret_cast<const SdbHexProto *>(b + hd->off_hex);
+    h->tab.n_ms = hd->n_ms; h->tab.n_mu = hd->n_mu; h->tab.n_clk = hd->n_clk; h->tab.nproto = hd->nproto;
+    /* persistent grids: every SM filled with as many CTAs as fit */
+    h->grid_ms = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MS);
+    h->grid_mu = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MU);
+    h->grid_hex = h->sm_count * 8;
+#undef CKC
+    *out = h;
+    return SDB_OK;
+}
+
+extern "C" void sdb_destroy(SdbHandle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit);
+    cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
+                                      const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                                      SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                                      uint32_t *d_bits, uint32_t bits_cap,
+                                      SdbCounters *d_counters, void *stream)
+{
+    if (!h) return SDB_E_ARG;
+    if (kind != SDB_KIND_MS && kind != SDB_KIND_MU) return set_err(h, SDB_E_ARG, "sdb_demod_pulse_device: kind must be MS or MU");
+    if (n && (!d_msgs || !d_digits || !d_out || !d_counters)) return set_err(h, SDB_E_ARG, "sdb_demod_pulse_device: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
+    int grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
+    uint32_t need = (n + (SDB_PULSE_THREADS / 32) - 1) / (SDB_PULSE_THREADS / 32);
+    if (need < (uint32_t)grid) grid = (int)(need ? need : 1);
+    int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid, st);
+    if (rc != 0) return set_err(h, SDB_E_CUDA, "pulse kernel launch", static_cast<cudaError_t>(rc));
+    return SDB_OK;
+}
+
+extern "C" int sdb_demod_hex_device(SdbHandle *h, int kind, int mc_repaired,
+                                    const SdbHexMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                                    SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                                    uint32_t *d_bits, uint32_t bits_cap,
+                                    SdbCounters *d_counters, void *stream)
+{
+    if (!h) return SDB_E_ARG;
+    if (kind != SDB_KIND_MC && kind != SDB_KIND_MN) return set_err(h, SDB_E_ARG, "sdb_demod_hex_device: kind must be MC or MN");
+    if (n && (!d_msgs || !d_digits || !d_out || !d_counters)) return set_err(h, SDB_E_ARG, "sdb_demod_hex_device: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
+    int grid = h->grid_hex;
+    uint32_t need = (n + SDB_HEX_THREADS - 1) / SDB_HEX_THREADS;
+    if (need < (uint32_t)grid) grid = (int)(need ? need : 1);
+    int rc = sdb::launch_hex(kind, mc_repaired, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid, st);
+    if (rc != 0) return set_err(h, SDB_E_CUDA, "hex kernel launch", static_cast<cudaError_t>(rc));
+    return SDB_OK;
+}
+
+template <typename T>
+static int grow(SdbHandle *h, T *&p, size_t &cap, size_t need_bytes)
+{
+    if (need_bytes <= cap) return SDB_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need_bytes + need_bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want);
+    if (e != cudaSuccess) return set_err(h, SDB_E_CUDA, "cudaMalloc", e);
+    cap = want;
+    return SDB_OK;
+}
+
+extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
+                              const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                              SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                              uint32_t *bits, uint32_t bits_cap, SdbCounters *counters)
+{
+    if (!h) return SDB_E_ARG;
+    if (!counters || (n && (!msgs || !digits || !out))) return set_err(h, SDB_E_ARG, "sdb_demod_host: null pointer");
+    const bool pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
+    if (!pulse && kind != SDB_KIND_MC && kind != SDB_KIND_MN) return set_err(h, SDB_E_ARG, "sdb_demod_host: bad kind");
+    CK(cudaSetDevice(h->device));
+    memset(counters, 0, sizeof *counters);
+    if (n == 0) return SDB_OK;
+    const size_t rec = pulse ? sizeof(SdbPulseMsg) : sizeof(SdbHexMsg);
+    int rc;
+    if ((rc = grow(h, reinterpret_cast<uint8_t *&>(h->d_msgs), h->cap_msgs, rec * n))) return rc;
+    if ((rc = grow(h, h->d_digits, h->cap_digits, digits_len + 64))) return rc;
+    if ((rc = grow(h, h->d_out, h->cap_out, sizeof(SdbMsgOut) * (size_t)n))) return rc;
+    if ((rc = grow(h, h->d_hits, h->cap_hits, sizeof(SdbHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
+    if ((rc = grow(h, h->d_bits, h->cap_bits, sizeof(uint32_t) * (size_t)(bits_cap ? bits_cap : 1)))) return rc;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->d_msgs, msgs, rec * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_digits, digits, digits_len, cudaMemcpyHostToDevice, st));
+    if (pulse)
+        rc = sdb_demod_pulse_device(h, kind, static_cast<const SdbPulseMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
+                                    h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+    else
+        rc = sdb_demod_hex_device(h, kind, mc_repaired, static_cast<const SdbHexMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
+                                  h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+    if (rc != SDB_OK) return rc;
+    CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
+    if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
+    if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SDB_OK;
+}
+
+/* ---- host-side formatting --------------------------------------------------------------- */
+static inline int hbit(const uint32_t *w, uint32_t i) { return (w[i >> 5] >> (i & 31)) & 1; }
+
+extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
+                               const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
+                               char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
+{
+    if (!h || !str_off || !pool_used) return SDB_E_ARG;
+    const SdbTblHeader *hd = reinterpret_cast<const SdbTblHeader *>(h->blob.data());
+    const bool pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
+    /* table-order index -> pulse row (for preamble / flags) */
+    std::vector<const SdbPulseProto *> row(hd->nproto, nullptr);
+    if (pulse) {
+        const SdbPulseProto *tab = reinterpret_cast<const SdbPulseProto *>(h->blob.data() + (kind == SDB_KIND_MS ? hd->off_ms : hd->off_mu));
+        uint32_t cnt = kind == SDB_KIND_MS ? hd->n_ms : hd->n_mu;
+        for (uint32_t i = 0; i < cnt; i++) row[tab[i].proto] = &tab[i];
+    }
+    size_t used = 0;
+    auto put = [&](char c) { if (used < pool_cap) pool[used] = c; used++; };
+    auto put_str = [&](const char *s) { while (*s) put(*s++); };
+    auto put_hex = [&](const uint32_t *w, uint32_t nb, bool strip) {
+        uint32_t nd = (nb + 3) >> 2;                      /* right-aligned nibbles, helpers.py:28-64 */
+        for (uint32_t j = 0; j < nd; j++) {
+            int b0 = (int)nb - 4 * (int)(nd - j), v = 0;
+            for (int k = 0; k < 4; k++) { int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
+            if (strip && v == 0) continue;
+            strip = false;
+            put("0123456789ABCDEF"[v]);
+        }
+    };
+    if (!pulse) {
+        /* MC: preamble + hex, or preamble + repr(list) for TFA (manchester.py:131-132, :713-717)
+         * MN: the converter's own string (helpers.py:223-716), no preamble (sd_protocols.py:151-155) */
+        const SdbHexProto *hx = reinterpret_cast<const SdbHexProto *>(h->blob.data() + hd->off_hex);
+        char num[64];
+        for (uint32_t i = 0; i < nhits; i++) {
+            str_off[i] = used;
+            const SdbHit &ht = hits[i];
+            if (ht.proto >= hd->nproto) return SDB_E_ARG;
+            const SdbHexProto &p = hx[ht.proto];
+            const uint32_t *w = bits + ht.bits_off;
+            if (kind == SDB_KIND_MC) {
+                if (ht.flags & SDB_HIT_LIST) {
+                    if (ht.aux != 0) continue;           /* the first element of a list carries the whole string */
+                    for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
+                    put('[');
+                    for (uint32_t e = i; e < nhits && hits[e].msg == ht.msg && (hits[e].flags & SDB_HIT_LIST) && hits[e].aux == e - i; e++) {
+                        if (e > i) { put(','); put(' '); }
+                        put('\'');
+                        put_hex(bits + hits[e].bits_off, hits[e].nbits, false);
+                        put('\'');
+                    }
+                    put(']');
+                } else {
+                    for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
+                    put_hex(w, ht.nbits, false);
+                }
+            } else if (ht.flags & SDB_HIT_FIELDS) {
+                if (p.method == SDB_M_PCA301) {
+                    snprintf(num, sizeof num, "OK 24 %u %u %u %u %u %u %u %u %u %u %04X", w[0], w[1], w[2], w[3], w[4],
+                             w[5], w[6], w[7], w[8], w[9], w[10]);
+                    put_str(num);
+                } else {
+                    snprintf(num, sizeof num, "OK 9 %u %u %u %u %u", w[0], w[1], w[2], w[3], w[4]);
+                    put_str(num);
+                }
+            } else {
+                if (p.method == SDB_M_KOPP) put_str("kr");
+                put_hex(w, ht.nbits, false);
+            }
+        }
+        str_off[nhits] = used;
+        *pool_used = used;
+        return used > pool_cap ? SDB_E_OVERFLOW : SDB_OK;
+    }
+    for (uint32_t i = 0; i < nhits; i++) {
+        str_off[i] = used;
+        const SdbHit &ht = hits[i];
+        const uint32_t *w = bits + ht.bits_off;
+        const uint32_t nb = ht.nbits, nwv = (nb + 31) >> 5;
+        const SdbPulseProto *pp = pulse && ht.proto < hd->nproto ? row[ht.proto] : nullptr;
+        if (pulse && !pp) return SDB_E_ARG;
+        if (pp) for (int k = 0; k < pp->pre_len; k++) put(pp->preamble[k]);
+        const bool has_f = (ht.flags & SDB_HIT_HAS_F) != 0;
+        if (pp && (pp->flags & SDB_PF_DISPATCH_BIN)) {
+            for (uint32_t b = 0; b < nb; b++) put(has_f && hbit(w + nwv, b) ? 'F' : (char)('0' + hbit(w, b)));
+        } else if (has_f) {
+            put('N'); put('o'); put('n'); put('e');       /* f"{None}" (message_unsynced.py:267,274) */
+        } else {
+            uint32_t nd = (nb + 3) >> 2;
+            bool strip = pp && (pp->flags & SDB_PF_REMOVE_ZERO);
+            for (uint32_t j = 0; j < nd; j++) {
+                int b0 = (int)nb - 4 * (int)(nd - j), v = 0;
+                for (int k = 0; k < 4; k++) { int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
+                if (strip && v == 0) continue;
+                strip = false;
+                put("0123456789ABCDEF"[v]);
+            }
+        }
+        if (pp) for (int k = 0; k < pp->post_len; k++) put(pp->postamble[k]);
+    }
+    str_off[nhits] = used;
+    *pool_used = used;
+    return used > pool_cap ? SDB_E_OVERFLOW : SDB_OK;
+}
+
+/* ---- unit ops ----------------------------------------------------------------------------- */
+extern "C" int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_t n_in,
+                                  uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode)
+{
+    if (!h || !n_out || !rcode || (n_in && !bits_in)) return SDB_E_ARG;
+    if (n_in > 2048 || out_cap > 4096) return set_err(h, SDB_E_ARG, "sdb_unit_postdemod: input too long");
+    CK(cudaSetDevice(h->device));
+    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 4096;
+    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 12288);
+    if (n_in) CK(cudaMemcpyAsync(d_in, bits_in, n_in, cudaMemcpyHostToDevice, h->stream));
+    int rc = sdb::launch_unit_postdemod(method, d_in, n_in, d_out, out_cap, d_res, h->stream);
+    if (rc != 0) return set_err(h, rc < 0 ? SDB_E_ARG : SDB_E_CUDA, "unit postdemod launch", rc > 0 ? static_cast<cudaError_t>(rc) : cudaSuccess);
+    int32_t res[2];
+    CK(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *rcode = res[0];
+    uint32_t no = res[1] > 0 ? (uint32_t)res[1] : 0;
+    *n_out = no;
+    if (no > out_cap) no = out_cap;
+    if (no && bits_out) { CK(cudaMemcpy(bits_out, d_out, no, cudaMemcpyDeviceToHost)); }
+    return SDB_OK;
+}

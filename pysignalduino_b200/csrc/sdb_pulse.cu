@@ -1,0 +1,827 @@
+/*
+ * sdb_pulse.cu — MS / MU batch demodulation kernel for sm_100a.
+ *
+ * Replaces, for a whole batch of packed messages,
+ *   demodulate_ms      sd_protocols/message_synced.py:10-243
+ *   demodulate_mu      sd_protocols/message_unsynced.py:11-296
+ *   pattern_exists     sd_protocols/pattern_utils.py:34-136
+ *   length_in_range / bin_str_2_hex_str   sd_protocols/helpers.py:28-64, :124-166
+ *   postDemo_*         sd_protocols/postdemodulation.py (sdb_postdemod.cuh)
+ *
+ * Work decomposition: ONE WARP PER MESSAGE, persistent warps striding over the batch.
+ *   phase 0  the warp stages the message in shared memory: nibble-packed digits (coalesced
+ *            128-bit loads), digit / digram first- and last-occurrence tables (so that
+ *            "target in D" becomes a table lookup), and for MU the tenths table
+ *            T[clock][slot] = 10*round(P/clock, 1) for the distinct protocol clocks.
+ *   phase 1  one LANE per protocol: integer interval tests decide which protocols can resolve
+ *            all mandatory templates at all; survivors come back as a ballot mask.
+ *   phase 2  one WARP per surviving (message x protocol) task, in protocol-table order:
+ *            exact pattern_exists (lane = (distinct value, slot), gap ranks, mixed-radix
+ *            product enumeration), symbol / start bitmaps by __ballot_sync over digit
+ *            windows, run-length via shifted-AND doubling, bit emission by ballots,
+ *            post-demodulation, padding, modulematch, hit staging.
+ * Hits of one message are staged in shared memory and published with one atomicAdd, so
+ * they are contiguous and already in reference order (protocol order, then match order).
+ *
+ * Float parity: the only float64 work is x = P/clock and CPython's round(x, 1), done with
+ * correctly-rounded division and an FMA residual; every tolerance /
+ * gap comparison is an integer compare against tables the host derived by running the
+ * reference's own float expressions.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdb200.h"
+#include "sdb_table.h"
+#include "sdb_postdemod.cuh"
+#include "sdb_pulse.h"
+
+namespace sdb {
+
+#define FULL 0xffffffffu
+#define DIG_WORDS (SDB_MAX_DIGITS / 8 + 4)
+#define BIT_WORDS (SDB_MAX_DIGITS / 32 + 4)
+#define ST_HITS 8
+#define ST_WORDS 48
+#define NONE32 0xffffffffu
+
+struct __align__(16) WarpSm {
+    uint32_t dig[DIG_WORDS];          /* nibble-packed digits, 0xF beyond dlen               */
+    uint32_t first2[100], last2[100]; /* digram ab: first position / last position + 1       */
+    uint32_t first1[12], last1[12];   /* digit a                                             */
+    int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
+    int32_t  pat[8];
+    uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
+    uint32_t fpl[BIT_WORDS];          /* 'F' plane                                           */
+    uint32_t tmp[BIT_WORDS];          /* post-demodulation output                            */
+    SdbHit   st_hits[ST_HITS];        /* staged hits of the current message                  */
+    uint32_t st_bits[ST_WORDS];
+    int32_t  pd_rc, pd_no;
+};
+
+/* ---- small helpers ------------------------------------------------------------------- */
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+/* 8 digits starting at position p (nibble-packed, low nibble first) */
+__device__ __forceinline__ uint32_t win32(const uint32_t *dig, int p)
+{
+    int wi = p >> 3, sh = (p & 7) * 4;
+    return __funnelshift_r(dig[wi], dig[wi + 1], sh);
+}
+/* 16 digits starting at position p */
+__device__ __forceinline__ uint64_t win64(const uint32_t *dig, int p)
+{
+    int wi = p >> 3, sh = (p & 7) * 4;
+    uint32_t a = dig[wi], b = dig[wi + 1], c = dig[wi + 2];
+    return ((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
+}
+__device__ __forceinline__ uint64_t nibmask64(int n) { return n >= 16 ? ~0ull : ((1ull << (4 * n)) - 1); }
+__device__ __forceinline__ uint32_t nibmask32(int n) { return n >= 8 ? ~0u : ((1u << (4 * n)) - 1); }
+
+/* 10 * round(p / c, 1) as an integer: CPython float.__round__(x, 1) on x = p / c (float64). */
+__device__ __forceinline__ int tenths(int p, double c)
+{
+    double x = __ddiv_rn((double)p, c);
+    double y = __dmul_rn(x, 10.0);
+    double e = __fma_rn(x, 10.0, -y);          /* 10x = y + e exactly */
+    double r = rint(y);                        /* ties-to-even on y */
+    double d = __dsub_rn(y, r);
+    if (d == 0.5 || d == -0.5) {               /* y sits on a tie: the exact value decides */
+        double fl = floor(y);
+        if (e > 0.0) r = fl + 1.0;
+        else if (e < 0.0) r = fl;
+    }
+    if (r > 32000.0) r = 32000.0;              /* far outside every accept interval */
+    if (r < -32000.0) r = -32000.0;
+    return (int)r;
+}
+
+/* X >> nb for a 1024-bit value spread little-endian over the warp (lane r = bits 32r..32r+31) */
+__device__ __forceinline__ uint32_t shr_dist(uint32_t mine, int nb)
+{
+    int lane = lane_id();
+    int ws = nb >> 5, bs = nb & 31;
+    uint32_t a = __shfl_down_sync(FULL, mine, ws & 31);
+    uint32_t b = __shfl_down_sync(FULL, mine, (ws + 1) & 31);
+    if (lane + ws > 31) a = 0;
+    if (lane + ws + 1 > 31) b = 0;
+    return __funnelshift_r(a, b, bs);
+}
+
+/* first set bit at position >= pos of a distributed 1024-bit value, -1 if none */
+__device__ __forceinline__ int first_set_from(uint32_t mine, int pos)
+{
+    int base = lane_id() * 32;
+    uint32_t w = mine;
+    if (base + 31 < pos) w = 0;
+    else if (base < pos) w &= FULL << (pos - base);
+    uint32_t nz = __ballot_sync(FULL, w != 0);
+    if (!nz) return -1;
+    int fl = __ffs(nz) - 1;
+    uint32_t wv = __shfl_sync(FULL, w, fl);
+    return fl * 32 + __ffs(wv) - 1;
+}
+
+/* ---- warp-cooperative substring search: first p >= from with D[p:p+L] == tgt, else -1 ------- */
+__device__ __forceinline__ int warp_find(const uint32_t *dig, int dlen, uint64_t tgt, int L, int from)
+{
+    uint64_t m = nibmask64(L);
+    for (int base = from; base + L <= dlen; base += 32) {
+        int p = base + lane_id();
+        bool hit = (p + L <= dlen) && ((win64(dig, p) & m) == tgt);
+        uint32_t bal = __ballot_sync(FULL, hit);
+        if (bal) return base + __ffs(bal) - 1;
+    }
+    return -1;
+}
+
+/*
+ * pattern_exists (pattern_utils.py:34-136) for one template, warp-cooperative.
+ *   t_slot : this lane's tenths value for slot (lane & 7)
+ *   from   : the searched text is D[from:]
+ * On success tgt = the id string (nibble-packed) and, when want_pos, pos = its first occurrence.
+ */
+__device__ bool resolve_key(const SdbKeyTpl *__restrict__ k, const uint16_t *__restrict__ rank,
+                            int t_slot, int npat, uint32_t pat_ids, const WarpSm &sm, int dlen, int from,
+                            uint64_t &tgt, int &pos, bool want_pos)
+{
+    const int lane = lane_id();
+    const int L = k->len, K = k->nuniq;
+    const int v = lane >> 3, j = lane & 7;
+    /* candidates of distinct value v: slots whose tenths lie in [lo, hi] (:73-76) */
+    bool in = false;
+    int key = 0x7fffffff;
+    if (v < K && j < npat) {
+        int lo = k->lo[v], hi = k->hi[v];
+        if (t_slot >= lo && t_slot <= hi) {
+            in = true;
+            key = ((int)__ldg(&rank[k->rank_off[v] + (t_slot - lo)]) << 3) | j;   /* gap rank, then slot order (:83 stable sort) */
+        }
+    }
+    uint32_t bal = __ballot_sync(FULL, in);
+    int cnt[SDB_MAX_UNIQ];
+#pragma unroll
+    for (int u = 0; u < SDB_MAX_UNIQ; u++) cnt[u] = __popc((bal >> (8 * u)) & 0xff);
+#pragma unroll
+    for (int u = 0; u < SDB_MAX_UNIQ; u++) if (u < K && cnt[u] == 0) return false;   /* :78-80 */
+    /* position of this slot in its sorted candidate list */
+    int ord = 0;
+#pragma unroll
+    for (int o = 1; o < 8; o++) {
+        int other = __shfl_sync(FULL, key, (lane & ~7) | ((j + o) & 7));
+        ord += other < key;
+    }
+    uint32_t list = in ? ((uint32_t)j << (4 * ord)) : 0u;
+    list |= __shfl_xor_sync(FULL, list, 1);
+    list |= __shfl_xor_sync(FULL, list, 2);
+    list |= __shfl_xor_sync(FULL, list, 4);
+    uint32_t lists[SDB_MAX_UNIQ];
+#pragma unroll
+    for (int u = 0; u < SDB_MAX_UNIQ; u++) lists[u] = __shfl_sync(FULL, list, 8 * u);
+    int total = 1;
+#pragma unroll
+    for (int u = 0; u < SDB_MAX_UNIQ; u++) if (u < K) total *= cnt[u];
+    /* total <= 8^4 = 4096 < 10000: the explosion guard (:97-101) can never fire with <= 8 slots */
+    const uint32_t uidx = k->uidx;
+    for (int base = 0; base < total; base += 32) {                  /* :111 product order, last list fastest */
+        int c = base + lane;
+        bool ok = c < total;
+        int slot[SDB_MAX_UNIQ] = {0, 0, 0, 0};
+        int rem = ok ? c : 0;
+#pragma unroll
+        for (int u = SDB_MAX_UNIQ - 1; u >= 0; u--) {
+            if (u < K) {
+                int ch = rem % cnt[u];
+                rem /= cnt[u];
+                slot[u] = (lists[u] >> (4 * ch)) & 0xF;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < SDB_MAX_UNIQ; a++)
+#pragma unroll
+            for (int b = a + 1; b < SDB_MAX_UNIQ; b++)
+                if (b < K && slot[a] == slot[b]) ok = false;        /* :114 one id for two values */
+        uint64_t tg = 0;
+        int prev = 0;
+        for (int i = 0; i < L; i++) {                               /* :118-127 */
+            int u = (uidx >> (2 * i)) & 3;
+            int s = u == 0 ? slot[0] : (u == 1 ? slot[1] : (u == 2 ? slot[2] : slot[3]));
+            int d = (pat_ids >> (4 * s)) & 0xF;
+            tg |= (uint64_t)d << (4 * i);
+            if (ok) {
+                if (L == 1) ok = sm.last1[d] > (uint32_t)from;
+                else if (i > 0) ok = sm.last2[prev * 10 + d] > (uint32_t)(from + i - 1);   /* digram filter (exact for L == 2) */
+            }
+            prev = d;
+        }
+        uint32_t good = __ballot_sync(FULL, ok);
+        while (good) {                                              /* :133 first combination present in D wins */
+            int w = __ffs(good) - 1;
+            good &= good - 1;
+            uint32_t tlo = __shfl_sync(FULL, (uint32_t)tg, w);
+            uint32_t thi = __shfl_sync(FULL, (uint32_t)(tg >> 32), w);
+            uint64_t cand = ((uint64_t)thi << 32) | tlo;
+            if (L <= 2) {
+                tgt = cand;
+                if (want_pos) {
+                    int d0 = (int)(cand & 0xF), d1 = (int)((cand >> 4) & 0xF);
+                    pos = (L == 1) ? (int)sm.first1[d0] : (int)sm.first2[d0 * 10 + d1];   /* want_pos callers search from 0 */
+                }
+                return true;
+            }
+            int p = warp_find(sm.dig, dlen, cand, L, from);
+            if (p >= 0) { tgt = cand; pos = p; return true; }
+        }
+    }
+    return false;
+}
+
+/* ---- payload characters (for modulematch, message_unsynced.py:254-280) ------------------- */
+struct Payload {
+    const SdbPulseProto *pp;
+    const uint32_t *val, *fpl;
+    int nb;          /* bits after padding */
+    int ndig;        /* hex digits ceil(nb/4) */
+    int lz;          /* leading '0' digits removed by remove_zero */
+    int body;        /* length of the middle part */
+    bool has_f, bin;
+};
+__device__ __forceinline__ int hex_digit(const uint32_t *val, int nb, int ndig, int j)
+{
+    /* right-aligned nibbles (helpers.py:28-64): digit j covers bits nb-4(ndig-j) .. +3 */
+    int b0 = nb - 4 * (ndig - j), v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int bi = b0 + k; v = (v << 1) | (bi >= 0 ? gbit(val, bi) : 0); }
+    return v;
+}
+__device__ int payload_char(const Payload &P, int i)
+{
+    const SdbPulseProto *pp = P.pp;
+    if (i < pp->pre_len) return (unsigned char)pp->preamble[i];
+    i -= pp->pre_len;
+    if (i < P.body) {
+        if (P.bin) return gbit(P.fpl, i) ? 'F' : ('0' + gbit(P.val, i));
+        if (P.has_f) return "None"[i];
+        int d = hex_digit(P.val, P.nb, P.ndig, i + P.lz);
+        return d < 10 ? '0' + d : 'A' + d - 10;
+    }
+    i -= P.body;
+    if (i < pp->post_len) return (unsigned char)pp->postamble[i];
+    return -1;
+}
+__device__ bool modulematch(const Payload &P, const SdbMmItem *__restrict__ items)
+{
+    const SdbPulseProto *pp = P.pp;
+    if (pp->flags & SDB_PF_MM_NEVER) return false;
+    if (pp->mm_off == 0xFFFF) return true;
+    const int total = pp->pre_len + P.body + pp->post_len;
+    const bool end = (pp->flags & SDB_PF_MM_END) != 0;
+    int pos = pp->pre_len;
+    const int n = pp->mm_nitems;
+    for (int it = 0; it < n; it++) {
+        const SdbMmItem *m = &items[pp->mm_off + it];
+        int mn = m->min, mx = m->max;
+        int cnt = 0;
+        int lim = (end && it == n - 1) ? mx : mn;
+        while (cnt < lim && pos < total) {
+            int c = payload_char(P, pos);
+            if (c < 0 || c >= 128 || !((m->mask[c >> 5] >> (c & 31)) & 1)) break;
+            pos++; cnt++;
+        }
+        if (cnt < mn) return false;
+    }
+    if (end && pos != total) return false;
+    return true;
+}
+
+/* ---- hit sink: shared-memory staging, or direct global writes on the rare second pass ------ */
+struct Sink {
+    uint32_t nh, nw;       /* hits / words produced so far for this message */
+    bool direct;           /* second pass: write at hbase/wbase in global memory */
+    bool overflow;         /* staging too small */
+    uint32_t hbase, wbase;
+};
+
+struct KArgs {
+    SdbDevTable tab;
+    const SdbPulseMsg *msgs;
+    const uint8_t *digits;
+    uint32_t n;
+    SdbMsgOut *out;
+    SdbHit *hits;  uint32_t hits_cap;
+    uint32_t *bits; uint32_t bits_cap;
+    SdbCounters *ctr;
+};
+
+__device__ void emit_hit(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
+                         int nb, bool has_f, int ordinal)
+{
+    const int lane = lane_id();
+    const int nwv = (nb + 31) >> 5;
+    const int nw = has_f ? 2 * nwv : nwv;
+    SdbHit h;
+    h.msg = msg; h.proto = pp->proto; h.nbits = (uint16_t)nb; h.aux = (uint16_t)ordinal;
+    h.flags = has_f ? SDB_HIT_HAS_F : 0; h.rsv = 0;
+    if (!S.direct) {
+        if (S.nh < ST_HITS && S.nw + nw <= ST_WORDS && !S.overflow) {
+            h.bits_off = S.nw;
+            if (lane == 0) sm.st_hits[S.nh] = h;
+            for (int i = lane; i < nw; i += 32) sm.st_bits[S.nw + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+        } else S.overflow = true;
+    } else {
+        h.bits_off = S.wbase + S.nw;
+        if (S.hbase + S.nh < A.hits_cap && S.wbase + S.nw + nw <= A.bits_cap) {
+            if (lane == 0) A.hits[S.hbase + S.nh] = h;
+            for (int i = lane; i < nw; i += 32) A.bits[S.wbase + S.nw + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+        }
+    }
+    S.nh++; S.nw += nw;
+    __syncwarp();
+}
+
+/* Shared tail of an MS / MU match: the bits are in sm.val / sm.fpl (nb of them).
+ * Returns SDB_ST_* (non-OK aborts the message). */
+template <bool MS>
+__device__ int finish_match(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
+                            int nb, int ordinal)
+{
+    const int lane = lane_id();
+    const int flags = pp->flags;
+    __syncwarp();
+    uint32_t fany = 0;
+    for (int i = lane; i < ((nb + 31) >> 5); i += 32) fany |= sm.fpl[i];
+    bool has_f = __any_sync(FULL, fany != 0);
+
+    if (MS) {
+        /* length_in_range (helpers.py:124-166), message_synced.py:194 */
+        if (pp->lir_min != -1 && nb < pp->lir_min) return SDB_ST_OK;
+        if ((flags & SDB_PF_HAS_LIR_MAX) && nb > pp->lir_max) return SDB_ST_OK;
+    }
+    const int pad = pp->padbits;
+    auto do_pad = [&]() {
+        int nn = (nb + pad - 1) / pad * pad;      /* appended bits are '0' */
+        if (nn != nb) {
+            __syncwarp();
+            for (int w = lane; w < BIT_WORDS; w += 32) {
+                int lo = w * 32;
+                if (lo + 32 > nb) {
+                    uint32_t keep = nb > lo ? (FULL >> (32 - (nb - lo))) : 0u;
+                    sm.val[w] &= keep; sm.fpl[w] &= keep;
+                }
+            }
+            nb = nn;
+            __syncwarp();
+        }
+    };
+    if (MS) do_pad();                             /* message_synced.py:198-200: pad BEFORE postDemod */
+
+    if (pp->postdemod) {
+        if (has_f) {
+            if (MS) return SDB_ST_VALUEERROR;     /* message_synced.py:209 int('F') escapes */
+            /* MU: ValueError swallowed (message_unsynced.py:249), bits kept */
+        } else {
+            if (lane == 0) {
+                int no = 0;
+                for (int w = 0; w < BIT_WORDS; w++) sm.tmp[w] = 0;
+                sm.pd_rc = postdemod(pp->postdemod, sm.val, nb, sm.tmp, &no);
+                sm.pd_no = no;
+            }
+            __syncwarp();
+            int rc = sm.pd_rc, no = sm.pd_no;
+            if (rc == -2) {
+                if (MS) return SDB_ST_VALUEERROR;
+            } else {
+                if (rc < 1) return SDB_ST_OK;
+                if (!MS || no > 0) {              /* MS keeps the old bits when ret_bits is empty (:218) */
+                    for (int w = lane; w < BIT_WORDS; w += 32) sm.val[w] = sm.tmp[w];
+                    nb = no;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (!MS) do_pad();                            /* message_unsynced.py:257-259: pad AFTER postDemod */
+
+    if (MS) {
+        if (has_f) return SDB_ST_OK;              /* bin_str_2_hex_str -> None (:224-226) */
+    } else {
+        Payload P;
+        P.pp = pp; P.val = sm.val; P.fpl = sm.fpl; P.nb = nb; P.ndig = (nb + 3) >> 2;
+        P.has_f = has_f; P.bin = (flags & SDB_PF_DISPATCH_BIN) != 0; P.lz = 0;
+        if (P.bin) P.body = nb;
+        else if (has_f) P.body = 4;
+        else {
+            if (flags & SDB_PF_REMOVE_ZERO) {     /* lstrip('0') :268-269 */
+                int z = 0;
+                while (z < P.ndig && hex_digit(sm.val, nb, P.ndig, z) == 0) z++;
+                P.lz = z;
+            }
+            P.body = P.ndig - P.lz;
+        }
+        if (!modulematch(P, A.tab.mm)) return SDB_ST_OK;   /* :277-280 */
+    }
+    emit_hit(A, sm, S, msg, pp, nb, has_f, ordinal);
+    return SDB_ST_OK;
+}
+
+/* ---- one (message x MU protocol) task: message_unsynced.py:59-290 --------------------------- */
+__device__ int decode_mu(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
+                         int dlen, int npat, uint32_t pat_ids)
+{
+    const int lane = lane_id();
+    const int t_slot = sm.T[pp->clk_idx][lane & 7];
+    const uint16_t *rank = A.tab.rank;
+    const int w = pp->width;
+    const int flags = pp->flags;
+
+    /* start (:67-88) */
+    int s0 = 0, Ls = pp->key[0].len;
+    uint64_t start_t = 0;
+    if (Ls) {
+        if (!resolve_key(&pp->key[0], rank, t_slot, npat, pat_ids, sm, dlen, 0, start_t, s0, true)) return SDB_ST_OK;
+    }
+    /* one / zero / float on D' = D[s0:] (:99-141) */
+    uint64_t t1 = 0, t0 = 0, tf = 0;
+    int dummy;
+    if (!resolve_key(&pp->key[1], rank, t_slot, npat, pat_ids, sm, dlen, s0, t1, dummy, false)) return SDB_ST_OK;
+    bool has0 = pp->key[2].len != 0, hasf = false;
+    if (has0 && !resolve_key(&pp->key[2], rank, t_slot, npat, pat_ids, sm, dlen, s0, t0, dummy, false)) return SDB_ST_OK;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], rank, t_slot, npat, pat_ids, sm, dlen, s0, tf, dummy, false);
+
+    const uint32_t wm = nibmask32(w);
+    const uint32_t c1 = (uint32_t)t1, c0 = (uint32_t)t0, cf = (uint32_t)tf;
+    const uint64_t lm = nibmask64(Ls);
+    const bool use_tail = (flags & SDB_PF_RECONSTRUCT) && w > 1;   /* w == 1: the tail key is '' and matches nothing extra */
+    const uint32_t em = nibmask32(w - 1);
+
+    /* symbol bitmap B and start bitmap Sm over positions of D (only p >= s0 matter) */
+    uint32_t myB = 0, myS = 0;
+    const int nr = (dlen + 31) >> 5;              /* an empty START at p == dlen needs MIN == 0, which the table compiler rejects */
+    for (int r = 0; r < nr; r++) {
+        int p = r * 32 + lane;
+        uint32_t x = win32(sm.dig, p) & wm;
+        bool sym = (p + w <= dlen) && (x == c1 || (has0 && x == c0) || (hasf && x == cf));
+        bool st = Ls == 0 ? (p < dlen) : ((p + Ls <= dlen) && ((win64(sm.dig, p) & lm) == start_t));
+        uint32_t bw = __ballot_sync(FULL, sym), sw = __ballot_sync(FULL, st && p >= s0);
+        if (lane == r) { myB = bw; myS = sw; }
+    }
+    /* R[p] = B[p] & B[p+w] & ... (MIN terms), by binary doubling */
+    const int MIN = pp->regex_min;
+    uint32_t R = FULL, Acc = myB;
+    int rl = 0, al = 1;
+    for (int m = MIN; m > 0; m >>= 1) {
+        if (m & 1) { R &= rl ? shr_dist(Acc, rl * w) : Acc; rl += al; }
+        if (m > 1) { Acc &= shr_dist(Acc, al * w); al <<= 1; }
+    }
+    const uint32_t myC = myS & (Ls ? shr_dist(R, Ls) : R);
+
+    /* re.finditer (:192): leftmost match from pos, then continue at its end */
+    int pos = s0, ordinal = 0;
+    for (;;) {
+        int i = first_set_from(myC, pos);
+        if (i < 0) break;
+        int p = i + Ls;
+        /* greedy run: first position q >= p, q = p (mod w), that is not a symbol */
+        uint32_t cls = w == 1 ? FULL : (w == 2 ? 0x55555555u << (p & 1) : 0x11111111u << (p & 3));
+        int ns = first_set_from(~myB & cls, p);
+        int n = ns >= 0 ? (ns - p) / w : (SDB_MAX_DIGITS - p + w - 1) / w;
+        int end = p + n * w;
+        int tail = -1;                             /* 0/1/2 = bit '1'/'0'/'F' of the reconstructed chunk */
+        if (use_tail) {
+            uint32_t x = win32(sm.dig, end) & em;  /* beyond dlen the 0xF padding never matches */
+            if (x == (c1 & em)) tail = 0;
+            else if (has0 && x == (c0 & em)) tail = 1;
+            else if (hasf && x == (cf & em)) tail = 2;
+            if (tail >= 0) end += w - 1;
+        }
+        pos = end > i ? end : i + 1;
+        int nch = n + (tail >= 0 ? 1 : 0);
+        if (nch == 0) return SDB_ST_INDEXERROR;   /* :212 chunks[-1] on an empty capture */
+        if (pp->mu_len_max >= 0 && nch > pp->mu_len_max) continue;   /* :217 */
+        /* chunks -> bits (:220-228): later keys overwrite earlier ones on identical strings */
+        __syncwarp();
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            int c = b0 + lane;
+            bool isf = false, one = false;
+            if (c < n) {
+                uint32_t x = win32(sm.dig, p + c * w) & wm;
+                if (hasf && x == cf) isf = true;
+                else if (has0 && x == c0) one = false;
+                else one = true;
+            }
+            uint32_t vw = __ballot_sync(FULL, one), fw = __ballot_sync(FULL, isf);
+            if (lane == 0) { sm.val[b0 >> 5] = vw; sm.fpl[b0 >> 5] = fw; }
+        }
+        __syncwarp();
+        for (int wq = lane; wq < BIT_WORDS; wq += 32)
+            if (wq >= ((n + 31) >> 5)) { sm.val[wq] = 0; sm.fpl[wq] = 0; }
+        __syncwarp();
+        if (lane == 0) {
+            if (tail == 0) sm.val[n >> 5] |= 1u << (n & 31);
+            else if (tail == 2) sm.fpl[n >> 5] |= 1u << (n & 31);
+        }
+        int st = finish_match<false>(A, sm, S, msg, pp, nch, ordinal);
+        if (st != SDB_ST_OK) return st;
+        ordinal++;
+    }
+    return SDB_ST_OK;
+}
+
+/* ---- one (message x MS protocol) task: message_synced.py:90-241 ----------------------------- */
+__device__ int decode_ms(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
+                         int dlen, int npat, uint32_t pat_ids, int t_slot)
+{
+    const int lane = lane_id();
+    const uint16_t *rank = A.tab.rank;
+    const int w = pp->width;
+    const int flags = pp->flags;
+    uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
+    int spos = 0, dummy;
+    const int Lsy = pp->key[0].len;
+    /* sync, then length_min against the digits left after it (:140-156) */
+    if (!resolve_key(&pp->key[0], rank, t_slot, npat, pat_ids, sm, dlen, 0, ts, spos, true)) return SDB_ST_OK;
+    const int ms = spos + Lsy;
+    if ((int)pp->regex_min * w > dlen - ms) return SDB_ST_OK;   /* length_min > (len - start) / width */
+    if (!resolve_key(&pp->key[1], rank, t_slot, npat, pat_ids, sm, dlen, 0, t1, dummy, false)) return SDB_ST_OK;
+    bool has0 = pp->key[2].len != 0, hasf = false;
+    if (has0 && !resolve_key(&pp->key[2], rank, t_slot, npat, pat_ids, sm, dlen, 0, t0, dummy, false)) return SDB_ST_OK;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], rank, t_slot, npat, pat_ids, sm, dlen, 0, tf, dummy, false);
+
+    const uint32_t wm = nibmask32(w), em = nibmask32(w - 1), sm_ = nibmask32(Lsy);
+    const uint32_t c1 = (uint32_t)t1, c0 = (uint32_t)t0, cf = (uint32_t)tf, cs = (uint32_t)ts;
+    const bool recon = (flags & SDB_PF_RECONSTRUCT) != 0;
+
+    /* chunk loop (:174-189): class per chunk = '1' / '0' / 'F' / skip (sync string) / stop */
+    __syncwarp();
+    for (int i = lane; i < BIT_WORDS; i += 32) { sm.val[i] = 0; sm.fpl[i] = 0; }
+    __syncwarp();
+    int nb = 0;
+    const int nchunks = (dlen - ms + w - 1) / w;
+    for (int b0 = 0; b0 < nchunks; b0 += 32) {
+        int c = b0 + lane;
+        int cls = 4;                               /* 0 '1', 1 '0', 2 'F', 3 skip, 4 stop, 5 none */
+        if (c < nchunks) {
+            int q = ms + c * w;
+            int cl = min(w, dlen - q);
+            uint32_t x = win32(sm.dig, q);
+            if (cl == w) {
+                uint32_t xs = x & wm;
+                if (hasf && xs == cf) cls = 2;
+                else if (has0 && xs == c0) cls = 1;
+                else if (xs == c1) cls = 0;
+                else if (Lsy == w && xs == cs) cls = 3;
+                else if (recon) {
+                    uint32_t xe = x & em;          /* chunk[:-1] (:182) against the first-wins end table */
+                    if (xe == (c1 & em)) cls = 0;
+                    else if (has0 && xe == (c0 & em)) cls = 1;
+                    else if (hasf && xe == (cf & em)) cls = 2;
+                }
+            } else {                               /* short last chunk */
+                if (cl == Lsy && (x & sm_) == cs) cls = 3;
+                else if (recon && cl == w - 1) {
+                    uint32_t xe = x & em;
+                    if (xe == (c1 & em)) cls = 0;
+                    else if (has0 && xe == (c0 & em)) cls = 1;
+                    else if (hasf && xe == (cf & em)) cls = 2;
+                }
+            }
+        } else cls = 5;
+        uint32_t stop = __ballot_sync(FULL, cls == 4);
+        uint32_t live = stop ? ((1u << (__ffs(stop) - 1)) - 1) : FULL;      /* chunks before the first stop */
+        uint32_t emitm = __ballot_sync(FULL, cls <= 2) & live;
+        uint32_t onem = __ballot_sync(FULL, cls == 0) & live;
+        uint32_t fm = __ballot_sync(FULL, cls == 2) & live;
+        if (emitm) {
+            bool mine = (emitm >> lane) & 1;
+            if (mine) {
+                int idx = nb + __popc(emitm & ((1u << lane) - 1));
+                if ((onem >> lane) & 1) atomicOr(&sm.val[idx >> 5], 1u << (idx & 31));
+                if ((fm >> lane) & 1) atomicOr(&sm.fpl[idx >> 5], 1u << (idx & 31));
+            }
+            nb += __popc(emitm);
+        }
+        if (stop) break;
+    }
+    if (nb == 0) return SDB_ST_OK;                 /* :191 */
+    return finish_match<true>(A, sm, S, msg, pp, nb, 0);
+}
+
+/* ---- phase 0: stage one message ---------------------------------------------------------- */
+__device__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen)
+{
+    const int lane = lane_id();
+    const uint4 *src = reinterpret_cast<const uint4 *>(A.digits + (size_t)m->doff * 16);
+    const int nq = (dlen + 31) >> 5;               /* 16-byte units */
+    if (lane < nq) {
+        uint4 v = __ldg(&src[lane]);
+        reinterpret_cast<uint4 *>(sm.dig)[lane] = v;
+    }
+    if (lane < 4) sm.dig[4 * nq + lane] = FULL;    /* windows may read 3 words past the last digit */
+    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; }
+    if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
+    if (lane < 8) sm.pat[lane] = m->pat[lane];
+    __syncwarp();
+    /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
+    for (int base = 0; base < dlen; base += 32) {
+        int p = base + lane;
+        uint32_t x = win32(sm.dig, p);
+        int a = x & 0xF, b = (x >> 4) & 0xF;
+        bool va = p < dlen && a <= 9;
+        bool vb = va && (p + 1 < dlen) && b <= 9;
+        uint32_t ga = __match_any_sync(FULL, va ? a : 16 + lane);
+        uint32_t gb = __match_any_sync(FULL, vb ? a * 10 + b : 128 + lane);
+        if (va) {
+            if (lane == __ffs(ga) - 1 && sm.first1[a] == NONE32) sm.first1[a] = p;
+            if (lane == 31 - __clz(ga)) sm.last1[a] = p + 1;
+        }
+        if (vb) {
+            int code = a * 10 + b;
+            if (lane == __ffs(gb) - 1 && sm.first2[code] == NONE32) sm.first2[code] = p;
+            if (lane == 31 - __clz(gb)) sm.last2[code] = p + 1;
+        }
+        __syncwarp();
+    }
+}
+
+/* phase 1: does protocol row `pf` have >= 1 candidate slot for every mandatory distinct value? */
+__device__ __forceinline__ bool prefilter_ok(const SdbPrefilter *__restrict__ pf, const int t[8])
+{
+    const int nreq = pf->nreq;
+    bool ok = true;
+    for (int r = 0; r < nreq && ok; r++) {
+        int lo = pf->lo[r], hi = pf->hi[r];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) any |= (t[j] >= lo) & (t[j] <= hi);
+        ok = any;
+    }
+    return ok;
+}
+
+template <bool MS>
+__device__ int run_message(const KArgs &A, WarpSm &sm, Sink &S, uint32_t mi, const SdbPulseMsg *m)
+{
+    const int lane = lane_id();
+    const int dlen = m->dlen, npat = m->npat;
+    const uint32_t pat_ids = m->pat_ids;
+    int status = SDB_ST_OK;
+    if (MS) {
+        const int cp = m->cp;
+        if (cp == 0xFF) return SDB_ST_OK;                        /* message_synced.py:60-62 */
+        const int pc = sm.pat[cp];
+        if (pc == 0) return SDB_ST_OK;                           /* :65-66 */
+        const double clock_abs = fabs((double)pc);
+        int t[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[j] = j < npat ? tenths(sm.pat[j], clock_abs) : -32768;   /* :70-72 */
+        int t_slot = t[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) if ((lane & 7) == j) t_slot = t[j];
+        const uint32_t n = A.tab.n_ms;
+        for (uint32_t q0 = 0; q0 < n; q0 += 32) {
+            uint32_t q = q0 + lane;
+            bool alive = false;
+            if (q < n) {
+                double pclk = A.tab.ms[q].clock;                  /* :83-88 */
+                bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
+                alive = !gate && prefilter_ok(&A.tab.ms_pf[q], t);
+            }
+            uint32_t surv = __ballot_sync(FULL, alive);
+            while (surv) {
+                int b = __ffs(surv) - 1;
+                surv &= surv - 1;
+                status = decode_ms(A, sm, S, mi, &A.tab.ms[q0 + b], dlen, npat, pat_ids, t_slot);
+                if (status != SDB_ST_OK) return status;
+            }
+        }
+    } else {
+        /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
+        const int ncl = A.tab.n_clk;
+        for (int idx = lane; idx < ncl * 8; idx += 32) {
+            int c = idx >> 3, j = idx & 7;
+            sm.T[c][j] = (int16_t)(j < npat ? tenths(sm.pat[j], __ldg(&A.tab.clk[c])) : -32768);
+        }
+        __syncwarp();
+        const uint32_t n = A.tab.n_mu;
+        for (uint32_t q0 = 0; q0 < n; q0 += 32) {
+            uint32_t q = q0 + lane;
+            bool alive = false;
+            if (q < n) {
+                const SdbPrefilter *pf = &A.tab.mu_pf[q];
+                const int4 row = *reinterpret_cast<const int4 *>(&sm.T[pf->clk_idx][0]);
+                int t[8];
+                t[0] = (int16_t)(row.x & 0xffff); t[1] = row.x >> 16;
+                t[2] = (int16_t)(row.y & 0xffff); t[3] = row.y >> 16;
+                t[4] = (int16_t)(row.z & 0xffff); t[5] = row.z >> 16;
+                t[6] = (int16_t)(row.w & 0xffff); t[7] = row.w >> 16;
+                alive = prefilter_ok(pf, t);
+            }
+            uint32_t surv = __ballot_sync(FULL, alive);
+            while (surv) {
+                int b = __ffs(surv) - 1;
+                surv &= surv - 1;
+                status = decode_mu(A, sm, S, mi, &A.tab.mu[q0 + b], dlen, npat, pat_ids);
+                if (status != SDB_ST_OK) return status;
+            }
+        }
+    }
+    return status;
+}
+
+template <bool MS>
+__global__ void __launch_bounds__(SDB_PULSE_THREADS) pulse_kernel(KArgs A)
+{
+    __shared__ WarpSm smem[SDB_PULSE_THREADS / 32];
+    WarpSm &sm = smem[threadIdx.x >> 5];
+    const int lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+        const SdbPulseMsg *m = &A.msgs[mi];
+        SdbMsgOut mo;
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        const int dlen = m->dlen;
+        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
+            stage_message(A, sm, m, dlen);
+            Sink S;
+            S.nh = 0; S.nw = 0; S.direct = false; S.overflow = false; S.hbase = 0; S.wbase = 0;
+            int status = run_message<MS>(A, sm, S, mi, m);
+            __syncwarp();
+            if (status != SDB_ST_OK) {
+                mo.status = (uint8_t)status;                     /* exception: earlier hits are lost */
+                if (lane == 0) atomicAdd(&A.ctr->raised, 1u);
+            } else if (S.nh) {
+                uint32_t hb = 0, wb = 0;
+                if (lane == 0) {
+                    hb = atomicAdd(&A.ctr->hits, S.nh);
+                    wb = atomicAdd(&A.ctr->words, S.nw);
+                }
+                hb = __shfl_sync(FULL, hb, 0);
+                wb = __shfl_sync(FULL, wb, 0);
+                mo.hit_off = hb; mo.nhits = (uint16_t)S.nh;
+                if (!S.overflow) {
+                    if (hb + S.nh <= A.hits_cap && wb + S.nw <= A.bits_cap) {
+                        for (uint32_t i = lane; i < S.nh; i += 32) {
+                            SdbHit h = sm.st_hits[i];
+                            h.bits_off += wb;
+                            A.hits[hb + i] = h;
+                        }
+                        for (uint32_t i = lane; i < S.nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
+                    }
+                } else {
+                    /* rare: more output than the staging area holds -> decode again, writing in place */
+                    Sink D;
+                    D.nh = 0; D.nw = 0; D.direct = true; D.overflow = false; D.hbase = hb; D.wbase = wb;
+                    run_message<MS>(A, sm, D, mi, m);
+                }
+            }
+        }
+        if (lane == 0) A.out[mi] = mo;
+        __syncwarp();
+    }
+}
+
+int pulse_blocks_per_sm(int kind)
+{
+    int nb = 0;
+    if (kind == SDB_KIND_MS) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pulse_kernel<true>, SDB_PULSE_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pulse_kernel<false>, SDB_PULSE_THREADS, 0);
+    return nb > 0 ? nb : 1;
+}
+
+/* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
+__global__ void unit_postdemod_kernel(int method, const uint8_t *in, uint32_t n_in, uint8_t *out, uint32_t out_cap, int32_t *res)
+{
+    __shared__ uint32_t a[BIT_WORDS * 2], b[BIT_WORDS * 2];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BIT_WORDS * 2; i++) { a[i] = 0; b[i] = 0; }
+        for (uint32_t i = 0; i < n_in; i++) sbit(a, (int)i, in[i] & 1);
+        int no = 0;
+        int rc = postdemod(method, a, (int)n_in, b, &no);
+        res[0] = rc; res[1] = no;
+        for (int i = 0; i < no && (uint32_t)i < out_cap; i++) out[i] = (uint8_t)gbit(b, i);
+    }
+}
+int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_t *d_out, uint32_t out_cap,
+                          int32_t *d_res, cudaStream_t stream)
+{
+    if (n_in > (uint32_t)(BIT_WORDS * 32)) return -1;
+    unit_postdemod_kernel<<<1, 32, 0, stream>>>(method, d_in, n_in, d_out, out_cap, d_res);
+    return (int)cudaGetLastError();
+}
+
+int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                 SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
+                 SdbCounters *d_ctr, int grid, cudaStream_t stream)
+{
+    KArgs A;
+    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.out = d_out;
+    A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
+    if (n == 0) return 0;
+    if (kind == SDB_KIND_MS) pulse_kernel<true><<<grid, SDB_PULSE_THREADS, 0, stream>>>(A);
+    else pulse_kernel<false><<<grid, SDB_PULSE_THREADS, 0, stream>>>(A);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sdb

@@ -1,0 +1,25 @@
+/* sdb_pulse.h — host-callable launchers of the device kernels (internal to libsdb200.so). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sdb200.h"
+#include "sdb_table.h"
+
+#define SDB_PULSE_THREADS 256   /* 8 warps = 8 messages in flight per CTA */
+#define SDB_HEX_THREADS   128
+
+namespace sdb {
+
+int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                 SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
+                 SdbCounters *d_ctr, int grid, cudaStream_t stream);
+int pulse_blocks_per_sm(int kind);
+
+int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMsg *d_msgs, const uint8_t *d_digits,
+               uint32_t n, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
+               SdbCounters *d_ctr, int grid, cudaStream_t stream);
+
+int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_t *d_out, uint32_t out_cap,
+                          int32_t *d_res /* [rc, n_out] */, cudaStream_t stream);
+
+}  // namespace sdb

@@ -1,0 +1,332 @@
+"""Drop-in ``SDProtocols`` backed by the B200 batch demodulator.
+
+Mirrors the public surface of the reference class (sd_protocols/sd_protocols.py:13-170): same
+method names, same argument meaning, same returned dicts and the same exceptions.  The scalar
+``demodulate(msg_data, msg_type)`` is a batch of one; ``demodulate_batch`` is the call the GPU
+path exists for.  Every decode decision is taken on the device (libsdb200.so); this module only
+packs inputs (pack.py), compiles the protocol table (table.py) and formats strings / dicts.
+"""
+from __future__ import annotations
+
+import copy
+import json
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import pack
+from .capi import (HIT_LIST, ST_OK, STATUS_EXC, STATUS_NAMES, Engine, Result)
+from .protocol_data import load_protocol_table
+from .table import PD_IDS, compile_table
+
+
+class SDProtocols:
+    """Protocol handling class: same API as the reference, demodulation on the GPU.
+
+    Extra keyword arguments (not in the reference):
+      device       CUDA device index of this instance's engine (default 0)
+      mc_repaired  False = MC path exactly as shipped (raises TypeError, SURVEY §8c "strict");
+                   True  = with the two documented one-line repairs of manchester.py:83/:120.
+    """
+
+    def __init__(self, device: int = 0, mc_repaired: bool = False):
+        self._protocols = self._load_protocols()
+        self._log_callback: Optional[Callable[[str, int], None]] = None
+        self.set_defaults()
+        self._device = device
+        self.mc_repaired = mc_repaired
+        self._engine: Optional[Engine] = None
+        self._engine_key: Optional[int] = None
+
+    # ------------------------------------------------------------------ table / property API
+    def _load_protocols(self) -> Dict[str, Any]:
+        """sd_protocols.py:30-41"""
+        return load_protocol_table()
+
+    def protocol_exists(self, pid: str) -> bool:
+        return pid in self._protocols
+
+    def get_protocol_list(self) -> dict:
+        return self._protocols
+
+    def get_keys(self, filter_key: str = None) -> list:
+        if filter_key:
+            return [pid for pid, props in self._protocols.items() if filter_key in props]
+        return list(self._protocols.keys())
+
+    def check_property(self, pid: str, value_name: str, default=None):
+        return self._protocols.get(pid, {}).get(value_name, default)
+
+    def get_property(self, pid: str, value_name: str):
+        return self._protocols.get(pid, {}).get(value_name)
+
+    def set_defaults(self):
+        """sd_protocols.py:157-160"""
+        for pid, proto in self._protocols.items():
+            proto.setdefault("active", True)
+            proto.setdefault("name", f"Protocol_{pid}")
+
+    def register_log_callback(self, callback):
+        if callable(callback):
+            self._log_callback = callback
+
+    def _logging(self, message: str, level: int = 3):
+        if self._log_callback:
+            self._log_callback(message, level)
+
+    # ------------------------------------------------------------------ engine management
+    def _table_key(self) -> int:
+        return hash(json.dumps(self._protocols, sort_keys=False, default=str))
+
+    def engine(self) -> Engine:
+        """The device engine for the CURRENT protocol dict (recompiled when the dict was mutated)."""
+        key = self._table_key()
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(compile_table(self._protocols), self._device)
+            self._engine_key = key
+        return self._engine
+
+    # ------------------------------------------------------------------ batch API (new)
+    def demodulate_packed(self, batch) -> Result:
+        """Run a packed batch (pack.PulseBatch / pack.HexBatch) and return the raw result arrays."""
+        return self.engine().demod_host(batch, mc_repaired=self.mc_repaired)
+
+    def pack(self, msgs: Sequence[Dict[str, Any]], msg_type: str):
+        kind = pack.KIND_BY_NAME[msg_type]
+        if kind in (pack.KIND_MS, pack.KIND_MU):
+            return pack.pack_pulse(msgs, kind)
+        eng = self.engine()
+        index = {pid: i for i, pid in enumerate(eng.table.ids)}
+        return pack.pack_hex(msgs, kind, index)
+
+    def demodulate_batch(self, msgs: Sequence[Dict[str, Any]], msg_type: str) -> Tuple[List[str], List[List[Dict[str, Any]]]]:
+        """Demodulate many messages of one type.
+
+        Returns (statuses, results): statuses[i] is "ok" or the name of the exception the reference
+        raises for message i ("IndexError", "TypeError", "ValueError"); results[i] is the list the
+        reference's demodulate() returns (empty when it raises).
+        """
+        if msg_type not in pack.KIND_BY_NAME:
+            self._logging(f"Unknown message type {msg_type}", 3)
+            return ["ok"] * len(msgs), [[] for _ in msgs]
+        batch = self.pack(msgs, msg_type)
+        res = self.demodulate_packed(batch)
+        return self.format_results(batch, res, msgs)
+
+    def format_results(self, batch, res: Result, msgs: Optional[Sequence[Dict[str, Any]]] = None):
+        eng = self.engine()
+        ids = eng.table.ids
+        kind = batch.kind
+        pool, off = eng.format_hits(kind, res.hits, res.bits)
+        text = pool.decode("latin-1")
+        statuses = [STATUS_NAMES[int(s)] for s in res.out["status"]]
+        results: List[List[Dict[str, Any]]] = []
+        hits = res.hits
+        clk_cache: Dict[int, float] = {}
+        for m in range(batch.n):
+            o = res.out[m]
+            lst: List[Dict[str, Any]] = []
+            h0 = int(o["hit_off"])
+            for i in range(h0, h0 + int(o["nhits"])):
+                h = hits[i]
+                if (int(h["flags"]) & HIT_LIST) and int(h["aux"]) != 0:
+                    continue
+                pi = int(h["proto"])
+                payload = text[int(off[i]) : int(off[i + 1])]
+                if kind in (pack.KIND_MS, pack.KIND_MU):
+                    if kind == pack.KIND_MS:
+                        clock = float(batch.clock[m])                      # message_synced.py:239
+                    else:
+                        if pi not in clk_cache:
+                            clk_cache[pi] = float(self.check_property(ids[pi], "clockabs", 1))
+                        clock = clk_cache[pi]                              # message_unsynced.py:288
+                    lst.append({"protocol_id": ids[pi], "payload": payload,
+                                "meta": {"bit_length": int(h["nbits"]), "rssi": batch.rssi[m], "clock": clock}})
+                elif kind == pack.KIND_MC:
+                    pid = batch.protocol_ids[m]
+                    lst.append({"protocol_id": str(pid), "payload": payload,
+                                "meta": {"protocol_id": pid, "rssi": None, "freq_afc": None}})   # manchester.py:136-140
+                else:
+                    meta = {"is_raw": False} if int(h["aux"]) in (18, 19, 20) else {}             # helpers.py:578,627,715
+                    lst.append({"protocol_id": batch.protocol_ids[m], "payload": payload, "meta": meta})
+            results.append(lst)
+        return statuses, results
+
+    # ------------------------------------------------------------------ reference API
+    def demodulate(self, msg_data: Dict[str, Any], msg_type: str) -> list:
+        """sd_protocols.py:60-74"""
+        if msg_type == "MS":
+            return self.demodulate_ms(msg_data, msg_type)
+        elif msg_type == "MC":
+            return self.demodulate_mc(msg_data, msg_type)
+        elif msg_type == "MN":
+            return self.demodulate_mn(msg_data, msg_type)
+        elif msg_type == "MU":
+            return self.demodulate_mu(msg_data, msg_type)
+        self._logging(f"Unknown message type {msg_type}", 3)
+        return []
+
+    def _one(self, msg_data: Dict[str, Any], msg_type: str) -> list:
+        statuses, results = self.demodulate_batch([msg_data], msg_type)
+        if statuses[0] != "ok":
+            raise {"IndexError": IndexError, "TypeError": TypeError, "ValueError": ValueError}[statuses[0]](
+                f"reference demodulate_{msg_type.lower()} raises {statuses[0]} on this message")
+        return results[0]
+
+    def demodulate_ms(self, msg_data: Dict[str, Any], msg_type: str = "MS") -> List[Dict[str, Any]]:
+        """message_synced.py:10-243 (invalid input -> [] with a level-3 log line, :21-47)"""
+        raw_data = msg_data.get("data", "")
+        if not raw_data or not raw_data.isdigit():
+            self._logging(f"MS Demod: Invalid rawData D=: {raw_data}", 3)
+            return []
+        for key, label in (("CP", "CP"), ("SP", "SP")):
+            v = msg_data.get(key, "")
+            if not v or not v.isdigit():
+                self._logging(f"MS Demod: Invalid {label}: {v}", 3)
+                return []
+        if "R" in msg_data and not msg_data.get("R", "").isdigit():
+            self._logging(f"MS Demod: Invalid RSSI R=: {msg_data.get('R', '')}", 3)
+            return []
+        return self._one(msg_data, "MS")
+
+    def demodulate_mu(self, msg_data: Dict[str, Any], msg_type: str = "MU") -> List[Dict[str, Any]]:
+        """message_unsynced.py:11-296"""
+        raw_data = msg_data.get("data", "")
+        if not raw_data:
+            self._logging(f"MU Demod: Invalid rawData D=: {raw_data}", 3)
+            return []
+        return self._one(msg_data, "MU")
+
+    def demodulate_mc(self, msg_data: Dict[str, Any], msg_type: str, version: str | None = None) -> list:
+        """sd_protocols.py:76-111"""
+        protocol_id = msg_data.get("protocol_id")
+        if not protocol_id or not self.protocol_exists(protocol_id):
+            self._logging(f"MC Demodulation failed: Protocol ID {protocol_id} not found or missing.", 3)
+            return []
+        toggle = msg_type == "Mc" or bool(version and version[:6] == "V 3.2.")      # manchester.py:94
+        eng = self.engine()
+        index = {pid: i for i, pid in enumerate(eng.table.ids)}
+        batch = pack.pack_hex([msg_data], pack.KIND_MC, index, toggle_polarity=toggle)
+        res = eng.demod_host(batch, mc_repaired=self.mc_repaired)
+        statuses, results = self.format_results(batch, res)
+        if statuses[0] != "ok":
+            raise STATUS_EXC[int(res.out["status"][0])](f"reference demodulate_mc raises {statuses[0]} on this message")
+        return results[0]
+
+    def demodulate_mn(self, msg_data: Dict[str, Any], msg_type: str) -> list:
+        """sd_protocols.py:113-155"""
+        if "protocol_id" not in msg_data:
+            self._logging(f"MN Demodulation failed: Missing protocol_id in msg_data: {msg_data}", 3)
+            return []
+        protocol_id = msg_data["protocol_id"]
+        if not self.protocol_exists(protocol_id):
+            self._logging(f"MN Demodulation: Protocol ID {protocol_id} not found.", 3)
+            return []
+        if not self.get_property(protocol_id, "method"):
+            self._logging(f"MN Demodulation: No method defined for protocol {protocol_id}. Data: {msg_data.get('data', '')}", 3)
+            return []
+        return self._one(msg_data, "MN")
+
+    # ------------------------------------------------------------------ postDemo_* (unit ops on the device)
+    def _postdemo(self, method: str, bit_msg_array):
+        rc, out = self.engine().unit_postdemod(PD_IDS[method], bit_msg_array)
+        if rc == -2:
+            raise ValueError("invalid literal for int() with base 2: ''")    # postdemodulation.py:471
+        if rc < 1:
+            return (0, None)
+        return (1, out)
+
+    def postDemo_EM(self, name, bit_msg_array):
+        """postdemodulation.py:27-88"""
+        return self._postdemo("postDemo_EM", bit_msg_array)
+
+    def postDemo_Revolt(self, name, bit_msg_array):
+        """postdemodulation.py:90-137"""
+        return self._postdemo("postDemo_Revolt", bit_msg_array)
+
+    def postDemo_FS20(self, name, bit_msg_array):
+        """postdemodulation.py:139-243"""
+        return self._postdemo("postDemo_FS20", bit_msg_array)
+
+    def postDemo_FHT80(self, name, bit_msg_array):
+        """postdemodulation.py:245-337"""
+        return self._postdemo("postDemo_FHT80", bit_msg_array)
+
+    def postDemo_FHT80TF(self, name, bit_msg_array):
+        """postdemodulation.py:339-423"""
+        return self._postdemo("postDemo_FHT80TF", bit_msg_array)
+
+    def postDemo_WS2000(self, name, bit_msg_array):
+        """postdemodulation.py:425-578"""
+        return self._postdemo("postDemo_WS2000", bit_msg_array)
+
+    def postDemo_WS7035(self, name, bit_msg_array):
+        """postdemodulation.py:580-640"""
+        return self._postdemo("postDemo_WS7035", bit_msg_array)
+
+    def postDemo_WS7053(self, name, bit_msg_array):
+        """postdemodulation.py:642-706"""
+        return self._postdemo("postDemo_WS7053", bit_msg_array)
+
+    def postDemo_lengtnPrefix(self, name, bit_msg_array):
+        """postdemodulation.py:708-730"""
+        return self._postdemo("postDemo_lengtnPrefix", bit_msg_array)
+
+    # ------------------------------------------------------------------ small pure helpers (API surface)
+    def bin_str_2_hex_str(self, num):
+        """helpers.py:28-64: right-aligned nibbles, upper case; '' -> ''; non-binary -> None."""
+        if num is None:
+            return None
+        if not num:
+            return ""
+        if not isinstance(num, str) or any(c not in "01" for c in num):
+            return None
+        ndig = (len(num) + 3) // 4
+        return format(int(num, 2), "X").zfill(ndig)
+
+    def hex_to_bin_str(self, hex_string):
+        """helpers.py:168-188: leading zero nibbles are dropped ('00FF' -> '11111111')."""
+        if hex_string is None:
+            return None
+        try:
+            b = bin(int(hex_string, 16))[2:]
+        except ValueError:
+            return None
+        return b.zfill((len(b) + 3) // 4 * 4)
+
+    def length_in_range(self, protocol_id, message_length):
+        """helpers.py:124-166"""
+        if not self.protocol_exists(str(protocol_id)):
+            return (0, "protocol does not exists")
+        min_len = self.check_property(protocol_id, "length_min", -1)
+        if min_len is not None:
+            try:
+                min_len = int(min_len)
+            except (ValueError, TypeError):
+                pass
+        if min_len != -1 and message_length < min_len:
+            return (0, "message is too short")
+        max_len = self.get_property(protocol_id, "length_max")
+        if max_len is not None:
+            try:
+                if message_length > int(max_len):
+                    return (0, "message is too long")
+            except (ValueError, TypeError):
+                pass
+        return (1, "")
+
+    def mc2dmc(self, bit_data):
+        """helpers.py:6-26"""
+        if bit_data is None:
+            return (-1, "no bitData provided")
+        s = bit_data.replace("1", "lh").replace("0", "hl")
+        return "".join("0" if s[i] == s[i + 1] else "1" for i in range(1, len(s) - 1, 2))
+
+    def dec_2_bin_ppari(self, num):
+        """helpers.py:66-88"""
+        if num is None:
+            return None
+        nbin = format(num, "08b")
+        return nbin + str(nbin.count("1") & 1)
