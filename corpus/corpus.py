@@ -160,6 +160,48 @@ class Corpus:
         return pack.PulseBatch(kind, msgs, digits, RssiCodes(rssi), clock)
 
 
-def batch_to_dicts(batch: pack.PulseBatch) -> List[Dict[str, Any]]:
+    def hexmsgs(self, kind: int, n: int, seed: int | None = None, lo: int = 0, hi: int | None = None) -> pack.HexBatch:
+        """Messages [lo, hi) of an n-message MC (kind 2) or MN (kind 3) corpus."""
+        if hi is None:
+            hi = n
+        if seed is None:
+            seed = SEED_MC if kind == pack.KIND_MC else SEED_MC + 0x100
+        cnt = hi - lo
+        ids = self.mc_ids if kind == pack.KIND_MC else self.mn_ids
+        osv = -1
+        if kind == pack.KIND_MC and "10" in self.ids:
+            pos = np.nonzero(ids == self.ids.index("10"))[0]
+            osv = int(pos[0]) if len(pos) else -1
+        msgs = np.zeros(cnt, dtype=pack.HEX_DTYPE)
+        pool_p = C.c_void_p()
+        pool_n = C.c_int64()
+        L = lib()
+        L.sdc_gen_hex.restype = C.c_int
+        rc = L.sdc_gen_hex(self.tab, C.c_int(len(self.ids)), C.c_void_p(ids.ctypes.data), C.c_int(len(ids)), C.c_int(osv),
+                           C.c_int(kind), C.c_uint64(seed), C.c_int64(lo), C.c_int64(hi),
+                           C.c_void_p(msgs.ctypes.data), C.byref(pool_p), C.byref(pool_n))
+        if rc != 0:
+            raise RuntimeError("corpus generation failed")
+        digits = np.ctypeslib.as_array(C.cast(pool_p, C.POINTER(C.c_uint8)), shape=(pool_n.value,)).copy()
+        L.sdc_free(pool_p)
+        return pack.HexBatch(kind, msgs, digits, _LazyIds(self.ids, msgs["proto"]), None)
+
+
+class _LazyIds:
+    """protocol_id per message of a generated HexBatch (looked up on demand)."""
+
+    def __init__(self, ids, proto):
+        self.ids, self.proto = ids, proto
+
+    def __len__(self):
+        return len(self.proto)
+
+    def __getitem__(self, i):
+        return self.ids[int(self.proto[i])]
+
+
+def batch_to_dicts(batch) -> List[Dict[str, Any]]:
     """Parser-style dicts for the CPU reference (same messages, same slot order)."""
+    if isinstance(batch, pack.HexBatch):
+        return [pack.unpack_hex(batch, i) for i in range(batch.n)]
     return [pack.unpack_pulse(batch, i) for i in range(batch.n)]

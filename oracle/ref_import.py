@@ -41,3 +41,42 @@ def ref_demodulate(proto, msg: Dict[str, Any], msg_type: str):
         return ("ok", canonical(proto.demodulate(dict(msg), msg_type)))
     except Exception as e:  # noqa: BLE001 - the exception type IS the result
         return (type(e).__name__, [])
+
+
+_REPAIRED = None
+
+
+def repaired_class():
+    """The reference class with EXACTLY the two one-line MC repairs of SURVEY.md §8c applied in memory:
+
+        manchester.py:83   clock_min, clock_max = clockrange, clockrange
+                       ->  clock_min, clock_max = clockrange[0], clockrange[1]
+        manchester.py:120  rcode, res = method_func(self, name, bit_data, protocol_id, len(bit_data))
+                       ->  rcode, res = method_func(name, bit_data, protocol_id, len(bit_data))
+
+    Nothing is written to disk; /root/reference stays untouched.
+    """
+    global _REPAIRED
+    if _REPAIRED is not None:
+        return _REPAIRED
+    base = reference_class()
+    import types
+
+    import sd_protocols.manchester as man  # type: ignore
+
+    src = (REFERENCE_ROOT / "sd_protocols" / "manchester.py").read_text(encoding="utf-8")
+    a = "clock_min, clock_max = clockrange, clockrange"
+    b = "rcode, res = method_func(self, name, bit_data, protocol_id, len(bit_data))"
+    assert src.count(a) == 1 and src.count(b) == 1, "reference manchester.py changed: repairs do not apply"
+    src = src.replace(a, "clock_min, clock_max = clockrange[0], clockrange[1]")
+    src = src.replace(b, "rcode, res = method_func(name, bit_data, protocol_id, len(bit_data))")
+    mod = types.ModuleType("sd_protocols.manchester_repaired")
+    mod.__dict__["__name__"] = "sd_protocols.manchester_repaired"
+    mod.__dict__["__package__"] = "sd_protocols"
+    exec(compile(src, "manchester_repaired.py", "exec"), mod.__dict__)
+
+    class SDProtocolsRepaired(base):  # type: ignore
+        _demodulate_mc_data = mod.ManchesterMixin._demodulate_mc_data
+
+    _REPAIRED = SDProtocolsRepaired
+    return _REPAIRED

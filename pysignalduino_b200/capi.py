@@ -141,6 +141,16 @@ class Engine:
             nh, nw = int(ctr["hits"][0]), int(ctr["words"][0])
             return Result(kind, out, hits[:nh], bits[:nw], ctr[0])
 
+    def demod_host_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, hits: np.ndarray,
+                        bits: np.ndarray, ctr: np.ndarray, mc_repaired: bool = False) -> int:
+        """Same call with caller-owned (e.g. pinned) host arrays; returns the raw code (SDB_OK / SDB_E_OVERFLOW)."""
+        rc = self.lib.sdb_demod_host(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
+                                     digits.nbytes, len(msgs), out.ctypes.data, hits.ctypes.data, len(hits),
+                                     bits.ctypes.data, len(bits), ctr.ctypes.data)
+        if rc not in (SDB_OK, SDB_E_OVERFLOW):
+            raise self._err(rc, "sdb_demod_host")
+        return rc
+
     # ---- device-pointer call (pointers are ints, e.g. torch tensor.data_ptr()) ---------------
     def demod_pulse_device(self, kind: int, d_msgs: int, d_digits: int, n: int, d_out: int, d_hits: int, hits_cap: int,
                            d_bits: int, bits_cap: int, d_ctr: int, stream: int = 0) -> None:

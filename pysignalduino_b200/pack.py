@@ -301,3 +301,21 @@ def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, i
     pool, doff = pack_digit_streams(streams)
     rec["doff"] = doff
     return HexBatch(kind, rec, pool, pids, datas)
+
+
+def unpack_hex(batch: HexBatch, i: int) -> Dict[str, Any]:
+    """Inverse of :func:`pack_hex` for one message (corpus tools and tests)."""
+    r = batch.msgs[i]
+    if not (r["flags"] & MSG_VALID):
+        return {"data": ""}
+    base = int(r["doff"]) * 16
+    hl = int(r["hlen"])
+    by = batch.digits[base : base + (hl + 1) // 2]
+    nib = np.empty(len(by) * 2, dtype=np.uint8)
+    nib[0::2] = by & 0xF
+    nib[1::2] = by >> 4
+    d: Dict[str, Any] = {"protocol_id": batch.protocol_ids[i], "data": "".join("0123456789ABCDEF"[v] for v in nib[:hl])}
+    if batch.kind == KIND_MC:
+        d["clock"] = int(r["clock"])
+        d["bit_length"] = int(r["bitlen"])
+    return d

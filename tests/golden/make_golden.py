@@ -89,6 +89,11 @@ def main():
     dump("corpus_mu.json.gz", run(ref, [("MU", m) for m in batch_to_dicts(corp.pulse(pack.KIND_MU, 1500))]))
     dump("fuzz_ms.json.gz", run(ref, [("MS", m) for m in fuzz_pulse(rng, 1500, pack.KIND_MS, protocols)]))
     dump("fuzz_mu.json.gz", run(ref, [("MU", m) for m in fuzz_pulse(rng, 1500, pack.KIND_MU, protocols)]))
+    # MC: "strict" = the reference as shipped, "repaired" = with the two documented one-line repairs
+    mc = [("MC", m) for m in batch_to_dicts(corp.hexmsgs(pack.KIND_MC, 3000))]
+    dump("corpus_mc_strict.json.gz", run(ref, mc))
+    dump("corpus_mc_repaired.json.gz", run(ref_import.repaired_class()(), mc))
+    dump("corpus_mn.json.gz", run(ref, [("MN", m) for m in batch_to_dicts(corp.hexmsgs(pack.KIND_MN, 3000))]))
 
 
 if __name__ == "__main__":

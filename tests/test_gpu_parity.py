@@ -36,3 +36,12 @@ def test_empty_and_invalid(sdp):
     assert st == ["ok"] * 3 and res == [[], [], []]
     st, res = sdp.demodulate_batch([{"data": ""}, {"P0": "5"}], "MU")
     assert st == ["ok"] * 2 and res == [[], []]
+
+
+@pytest.mark.parametrize("kind,repaired", [(pack.KIND_MC, True), (pack.KIND_MC, False), (pack.KIND_MN, True)])
+def test_hex_corpus_parity(sdp, oracle, corpus, kind, repaired):
+    batch = corpus.hexmsgs(kind, 30000)
+    res = sdp.engine().demod_host(batch, mc_repaired=repaired)
+    got = canonical_gpu(sdp, batch, res)
+    exp = oracle.run_hex(batch, mc_repaired=repaired, nthreads=8)
+    assert got == exp, diff_report(got, exp)
