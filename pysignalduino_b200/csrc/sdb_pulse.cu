@@ -17,11 +17,16 @@
  *            all mandatory templates at all; survivors come back as a ballot mask.
  *   phase 2  one WARP per surviving (message x protocol) task, in protocol-table order:
  *            exact pattern_exists (lane = (distinct value, slot), gap ranks, mixed-radix
- *            product enumeration), symbol / start bitmaps by __ballot_sync over digit
- *            windows, run-length via shifted-AND doubling, bit emission by ballots,
- *            post-demodulation, padding, modulematch, hit staging.
+ *            product enumeration), symbol / start bitmaps (SWAR byte compares on 8 digits per
+ *            lane, or __ballot_sync over digit windows), run-length via shifted-AND doubling,
+ *            bit emission by ballots, post-demodulation, padding, modulematch, hit staging.
  * Hits of one message are staged in shared memory and published with one atomicAdd, so
  * they are contiguous and already in reference order (protocol order, then match order).
+ *
+ * Code size matters: the first version inlined everything (18 k SASS instructions, 295 KB) and
+ * ncu showed 74 % of the stall samples in "no instruction" (instruction-cache misses).  The cold
+ * parts (general candidate sort, post-demodulation, modulematch, second pass) are therefore
+ * __noinline__ and the hot loop is kept small.
  *
  * Float parity: the only float64 work is x = P/clock and CPython's round(x, 1), done with
  * correctly-rounded division and an FMA residual; every tolerance /
@@ -44,6 +49,18 @@ namespace sdb {
 #define ST_HITS 8
 #define ST_WORDS 48
 #define NONE32 0xffffffffu
+#define WARPS (SDB_PULSE_THREADS / 32)
+
+struct KArgs {
+    SdbDevTable tab;
+    const SdbPulseMsg *msgs;
+    const uint8_t *digits;
+    uint32_t n;
+    SdbMsgOut *out;
+    SdbHit *hits;  uint32_t hits_cap;
+    uint32_t *bits; uint32_t bits_cap;
+    SdbCounters *ctr;
+};
 
 struct __align__(16) WarpSm {
     uint32_t dig[DIG_WORDS];          /* nibble-packed digits, 0xF beyond dlen               */
@@ -57,7 +74,18 @@ struct __align__(16) WarpSm {
     SdbHit   st_hits[ST_HITS];        /* staged hits of the current message                  */
     uint32_t st_bits[ST_WORDS];
     int32_t  pd_rc, pd_no;
+    /* per-message scalars (so that the out-of-line helpers need few arguments) */
+    const uint16_t *rank;
+    int32_t  dlen, npat;
+    uint32_t pat_ids, msg;
+    /* hit sink */
+    uint32_t nh, nw;                  /* hits / words produced so far                        */
+    uint32_t hbase, wbase;            /* second pass: global bases                           */
+    int32_t  direct, overflow;
 };
+
+__shared__ WarpSm g_sm[WARPS];
+#define SM() (g_sm[threadIdx.x >> 5])
 
 /* ---- small helpers ------------------------------------------------------------------- */
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -123,48 +151,64 @@ __device__ __forceinline__ int first_set_from(uint32_t mine, int pos)
 }
 
 /* ---- warp-cooperative substring search: first p >= from with D[p:p+L] == tgt, else -1 ------- */
-__device__ __forceinline__ int warp_find(const uint32_t *dig, int dlen, uint64_t tgt, int L, int from)
+__device__ __noinline__ int warp_find(uint64_t tgt, int L, int from)
 {
+    WarpSm &sm = SM();
+    const int dlen = sm.dlen;
     uint64_t m = nibmask64(L);
     for (int base = from; base + L <= dlen; base += 32) {
         int p = base + lane_id();
-        bool hit = (p + L <= dlen) && ((win64(dig, p) & m) == tgt);
+        bool hit = (p + L <= dlen) && ((win64(sm.dig, p) & m) == tgt);
         uint32_t bal = __ballot_sync(FULL, hit);
         if (bal) return base + __ffs(bal) - 1;
     }
     return -1;
 }
 
-/*
- * pattern_exists (pattern_utils.py:34-136) for one template, warp-cooperative.
- *   t_slot : this lane's tenths value for slot (lane & 7)
- *   from   : the searched text is D[from:]
- * On success tgt = the id string (nibble-packed) and, when want_pos, pos = its first occurrence.
- */
-__device__ bool resolve_key(const SdbKeyTpl *__restrict__ k, const uint16_t *__restrict__ rank,
-                            int t_slot, int npat, uint32_t pat_ids, const WarpSm &sm, int dlen, int from,
-                            uint64_t &tgt, int &pos, bool want_pos)
+/* Is the id string `tg` (L digits, nibble-packed) a substring of D[from:] ?  (pattern_utils.py:133) */
+__device__ __forceinline__ bool target_present(WarpSm &sm, uint64_t tg, int L, int from, bool want_pos, int &pos)
 {
+    const int d0 = (int)(tg & 0xF), d1 = (int)((tg >> 4) & 0xF);
+    if (L == 1) {
+        if (sm.last1[d0] <= (uint32_t)from) return false;
+        if (want_pos) pos = (int)sm.first1[d0];           /* want_pos callers search from 0 */
+        return true;
+    }
+    if (L == 2) {
+        if (sm.last2[d0 * 10 + d1] <= (uint32_t)from) return false;
+        if (want_pos) pos = (int)sm.first2[d0 * 10 + d1];
+        return true;
+    }
+    int prev = d0;
+    for (int i = 1; i < L; i++) {                         /* necessary: every digram occurs late enough */
+        int d = (int)((tg >> (4 * i)) & 0xF);
+        if (sm.last2[prev * 10 + d] <= (uint32_t)(from + i - 1)) return false;
+        prev = d;
+    }
+    int p = warp_find(tg, L, from);
+    if (p < 0) return false;
+    pos = p;
+    return true;
+}
+
+/*
+ * General pattern_exists (pattern_utils.py:34-136): some distinct value has several candidate
+ * slots, so the candidates are ordered by gap rank (then slot) and the cartesian product is
+ * walked in itertools.product order, 32 combinations per step.
+ */
+__device__ __noinline__ bool resolve_general(const SdbKeyTpl *__restrict__ k, int t_slot, int from, bool want_pos,
+                                             uint64_t &tgt, int &pos, bool in, int lo, uint32_t bal)
+{
+    WarpSm &sm = SM();
     const int lane = lane_id();
     const int L = k->len, K = k->nuniq;
     const int v = lane >> 3, j = lane & 7;
-    /* candidates of distinct value v: slots whose tenths lie in [lo, hi] (:73-76) */
-    bool in = false;
+    const uint32_t pat_ids = sm.pat_ids;
     int key = 0x7fffffff;
-    if (v < K && j < npat) {
-        int lo = k->lo[v], hi = k->hi[v];
-        if (t_slot >= lo && t_slot <= hi) {
-            in = true;
-            key = ((int)__ldg(&rank[k->rank_off[v] + (t_slot - lo)]) << 3) | j;   /* gap rank, then slot order (:83 stable sort) */
-        }
-    }
-    uint32_t bal = __ballot_sync(FULL, in);
+    if (in) key = ((int)__ldg(&sm.rank[k->rank_off[v] + (t_slot - lo)]) << 3) | j;   /* gap rank, then slot order (:83 stable sort) */
     int cnt[SDB_MAX_UNIQ];
 #pragma unroll
     for (int u = 0; u < SDB_MAX_UNIQ; u++) cnt[u] = __popc((bal >> (8 * u)) & 0xff);
-#pragma unroll
-    for (int u = 0; u < SDB_MAX_UNIQ; u++) if (u < K && cnt[u] == 0) return false;   /* :78-80 */
-    /* position of this slot in its sorted candidate list */
     int ord = 0;
 #pragma unroll
     for (int o = 1; o < 8; o++) {
@@ -221,19 +265,51 @@ __device__ bool resolve_key(const SdbKeyTpl *__restrict__ k, const uint16_t *__r
             uint32_t tlo = __shfl_sync(FULL, (uint32_t)tg, w);
             uint32_t thi = __shfl_sync(FULL, (uint32_t)(tg >> 32), w);
             uint64_t cand = ((uint64_t)thi << 32) | tlo;
-            if (L <= 2) {
-                tgt = cand;
-                if (want_pos) {
-                    int d0 = (int)(cand & 0xF), d1 = (int)((cand >> 4) & 0xF);
-                    pos = (L == 1) ? (int)sm.first1[d0] : (int)sm.first2[d0 * 10 + d1];   /* want_pos callers search from 0 */
-                }
-                return true;
-            }
-            int p = warp_find(sm.dig, dlen, cand, L, from);
-            if (p >= 0) { tgt = cand; pos = p; return true; }
+            if (target_present(sm, cand, L, from, want_pos, pos)) { tgt = cand; return true; }
         }
     }
     return false;
+}
+
+/*
+ * pattern_exists for one template, warp-cooperative.  lane = (distinct value v, slot j).
+ *   t_slot : this lane's tenths value for slot (lane & 7);  from : the searched text is D[from:]
+ * Fast path: every distinct value has exactly one candidate slot -> a single combination.
+ */
+__device__ __noinline__ bool resolve_key(const SdbKeyTpl *__restrict__ k, int t_slot, int from, bool want_pos,
+                                         uint64_t &tgt, int &pos)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const int L = k->len, K = k->nuniq;
+    const int v = lane >> 3, j = lane & 7;
+    bool in = false;
+    int lo = 0;
+    if (v < K && j < sm.npat) {                                     /* :73-76 candidates = tenths inside [lo, hi] */
+        lo = k->lo[v];
+        in = t_slot >= lo && t_slot <= k->hi[v];
+    }
+    const uint32_t bal = __ballot_sync(FULL, in);
+    const uint32_t b0 = bal & 0xff, b1 = (bal >> 8) & 0xff, b2 = (bal >> 16) & 0xff, b3 = bal >> 24;
+    if (!b0 || (K > 1 && !b1) || (K > 2 && !b2) || (K > 3 && !b3)) return false;       /* :78-80 */
+    const bool single = !(b0 & (b0 - 1)) && !(b1 & (b1 - 1)) && !(b2 & (b2 - 1)) && !(b3 & (b3 - 1));
+    if (!single) return resolve_general(k, t_slot, from, want_pos, tgt, pos, in, lo, bal);
+    /* one combination: distinct sentinels keep absent values out of the duplicate test (:114) */
+    const int s0 = __ffs(b0) - 1, s1 = K > 1 ? __ffs(b1) - 1 : 8, s2 = K > 2 ? __ffs(b2) - 1 : 9, s3 = K > 3 ? __ffs(b3) - 1 : 10;
+    if (s0 == s1 || s0 == s2 || s0 == s3 || s1 == s2 || s1 == s3 || s2 == s3) return false;
+    const uint32_t ids = sm.pat_ids;
+    const int d0 = (ids >> (4 * s0)) & 0xF, d1 = (ids >> (4 * (s1 & 7))) & 0xF, d2 = (ids >> (4 * (s2 & 7))) & 0xF,
+              d3 = (ids >> (4 * (s3 & 7))) & 0xF;
+    const uint32_t uidx = k->uidx;
+    uint64_t tg = 0;
+    for (int i = 0; i < L; i++) {                                   /* :118-127 */
+        int u = (uidx >> (2 * i)) & 3;
+        int d = u == 0 ? d0 : (u == 1 ? d1 : (u == 2 ? d2 : d3));
+        tg |= (uint64_t)d << (4 * i);
+    }
+    if (!target_present(sm, tg, L, from, want_pos, pos)) return false;
+    tgt = tg;
+    return true;
 }
 
 /* ---- payload characters (for modulematch, message_unsynced.py:254-280) ------------------- */
@@ -269,13 +345,26 @@ __device__ int payload_char(const Payload &P, int i)
     if (i < pp->post_len) return (unsigned char)pp->postamble[i];
     return -1;
 }
-__device__ bool modulematch(const Payload &P, const SdbMmItem *__restrict__ items)
+/* modulematch (message_unsynced.py:277-280) as a fixed-offset character-class program */
+__device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmItem *__restrict__ items, int nb, bool has_f)
 {
-    const SdbPulseProto *pp = P.pp;
-    if (pp->flags & SDB_PF_MM_NEVER) return false;
-    if (pp->mm_off == 0xFFFF) return true;
+    WarpSm &sm = SM();
+    const int flags = pp->flags;
+    Payload P;
+    P.pp = pp; P.val = sm.val; P.fpl = sm.fpl; P.nb = nb; P.ndig = (nb + 3) >> 2;
+    P.has_f = has_f; P.bin = (flags & SDB_PF_DISPATCH_BIN) != 0; P.lz = 0;
+    if (P.bin) P.body = nb;
+    else if (has_f) P.body = 4;
+    else {
+        if (flags & SDB_PF_REMOVE_ZERO) {                 /* lstrip('0') :268-269 */
+            int z = 0;
+            while (z < P.ndig && hex_digit(sm.val, nb, P.ndig, z) == 0) z++;
+            P.lz = z;
+        }
+        P.body = P.ndig - P.lz;
+    }
     const int total = pp->pre_len + P.body + pp->post_len;
-    const bool end = (pp->flags & SDB_PF_MM_END) != 0;
+    const bool end = (flags & SDB_PF_MM_END) != 0;
     int pos = pp->pre_len;
     const int n = pp->mm_nitems;
     for (int it = 0; it < n; it++) {
@@ -295,98 +384,77 @@ __device__ bool modulematch(const Payload &P, const SdbMmItem *__restrict__ item
 }
 
 /* ---- hit sink: shared-memory staging, or direct global writes on the rare second pass ------ */
-struct Sink {
-    uint32_t nh, nw;       /* hits / words produced so far for this message */
-    bool direct;           /* second pass: write at hbase/wbase in global memory */
-    bool overflow;         /* staging too small */
-    uint32_t hbase, wbase;
-};
-
-struct KArgs {
-    SdbDevTable tab;
-    const SdbPulseMsg *msgs;
-    const uint8_t *digits;
-    uint32_t n;
-    SdbMsgOut *out;
-    SdbHit *hits;  uint32_t hits_cap;
-    uint32_t *bits; uint32_t bits_cap;
-    SdbCounters *ctr;
-};
-
-__device__ void emit_hit(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
-                         int nb, bool has_f, int ordinal)
+__device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, int nb, bool has_f, int ordinal)
 {
+    WarpSm &sm = SM();
     const int lane = lane_id();
     const int nwv = (nb + 31) >> 5;
     const int nw = has_f ? 2 * nwv : nwv;
     SdbHit h;
-    h.msg = msg; h.proto = pp->proto; h.nbits = (uint16_t)nb; h.aux = (uint16_t)ordinal;
+    h.msg = sm.msg; h.proto = pp->proto; h.nbits = (uint16_t)nb; h.aux = (uint16_t)ordinal;
     h.flags = has_f ? SDB_HIT_HAS_F : 0; h.rsv = 0;
-    if (!S.direct) {
-        if (S.nh < ST_HITS && S.nw + nw <= ST_WORDS && !S.overflow) {
-            h.bits_off = S.nw;
-            if (lane == 0) sm.st_hits[S.nh] = h;
-            for (int i = lane; i < nw; i += 32) sm.st_bits[S.nw + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
-        } else S.overflow = true;
+    const uint32_t nh0 = sm.nh, nw0 = sm.nw;
+    __syncwarp();
+    if (!sm.direct) {
+        if (nh0 < ST_HITS && nw0 + nw <= ST_WORDS && !sm.overflow) {
+            h.bits_off = nw0;
+            if (lane == 0) sm.st_hits[nh0] = h;
+            for (int i = lane; i < nw; i += 32) sm.st_bits[nw0 + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+        } else if (lane == 0) sm.overflow = 1;
     } else {
-        h.bits_off = S.wbase + S.nw;
-        if (S.hbase + S.nh < A.hits_cap && S.wbase + S.nw + nw <= A.bits_cap) {
-            if (lane == 0) A.hits[S.hbase + S.nh] = h;
-            for (int i = lane; i < nw; i += 32) A.bits[S.wbase + S.nw + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+        h.bits_off = sm.wbase + nw0;
+        if (sm.hbase + nh0 < A.hits_cap && sm.wbase + nw0 + nw <= A.bits_cap) {
+            if (lane == 0) A.hits[sm.hbase + nh0] = h;
+            for (int i = lane; i < nw; i += 32) A.bits[sm.wbase + nw0 + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
         }
     }
-    S.nh++; S.nw += nw;
+    __syncwarp();
+    if (lane == 0) { sm.nh = nh0 + 1; sm.nw = nw0 + nw; }
     __syncwarp();
 }
 
-/* Shared tail of an MS / MU match: the bits are in sm.val / sm.fpl (nb of them).
+/* post-demodulation on lane 0 (rare: ~10 of 129 protocols, frames <= ~150 bits) */
+__device__ __noinline__ void run_postdemod(int method, int nb)
+{
+    WarpSm &sm = SM();
+    if (lane_id() == 0) {
+        int no = 0;
+        for (int w = 0; w < BIT_WORDS; w++) sm.tmp[w] = 0;
+        sm.pd_rc = postdemod(method, sm.val, nb, sm.tmp, &no);
+        sm.pd_no = no;
+    }
+    __syncwarp();
+}
+
+/* Shared tail of an MS / MU match: the bits are in sm.val / sm.fpl (nb of them, zero beyond).
  * Returns SDB_ST_* (non-OK aborts the message). */
 template <bool MS>
-__device__ int finish_match(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
-                            int nb, int ordinal)
+__device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp, int nb, int ordinal, bool maybe_f)
 {
+    WarpSm &sm = SM();
     const int lane = lane_id();
     const int flags = pp->flags;
     __syncwarp();
-    uint32_t fany = 0;
-    for (int i = lane; i < ((nb + 31) >> 5); i += 32) fany |= sm.fpl[i];
-    bool has_f = __any_sync(FULL, fany != 0);
-
+    bool has_f = false;
+    if (maybe_f) {
+        uint32_t fany = 0;
+        for (int i = lane; i < ((nb + 31) >> 5); i += 32) fany |= sm.fpl[i];
+        has_f = __any_sync(FULL, fany != 0);
+    }
     if (MS) {
         /* length_in_range (helpers.py:124-166), message_synced.py:194 */
         if (pp->lir_min != -1 && nb < pp->lir_min) return SDB_ST_OK;
         if ((flags & SDB_PF_HAS_LIR_MAX) && nb > pp->lir_max) return SDB_ST_OK;
     }
     const int pad = pp->padbits;
-    auto do_pad = [&]() {
-        int nn = (nb + pad - 1) / pad * pad;      /* appended bits are '0' */
-        if (nn != nb) {
-            __syncwarp();
-            for (int w = lane; w < BIT_WORDS; w += 32) {
-                int lo = w * 32;
-                if (lo + 32 > nb) {
-                    uint32_t keep = nb > lo ? (FULL >> (32 - (nb - lo))) : 0u;
-                    sm.val[w] &= keep; sm.fpl[w] &= keep;
-                }
-            }
-            nb = nn;
-            __syncwarp();
-        }
-    };
-    if (MS) do_pad();                             /* message_synced.py:198-200: pad BEFORE postDemod */
+    if (MS) nb = (nb + pad - 1) / pad * pad;      /* message_synced.py:198-200: pad BEFORE postDemod (appended bits are 0 already) */
 
     if (pp->postdemod) {
         if (has_f) {
             if (MS) return SDB_ST_VALUEERROR;     /* message_synced.py:209 int('F') escapes */
             /* MU: ValueError swallowed (message_unsynced.py:249), bits kept */
         } else {
-            if (lane == 0) {
-                int no = 0;
-                for (int w = 0; w < BIT_WORDS; w++) sm.tmp[w] = 0;
-                sm.pd_rc = postdemod(pp->postdemod, sm.val, nb, sm.tmp, &no);
-                sm.pd_no = no;
-            }
-            __syncwarp();
+            run_postdemod(pp->postdemod, nb);
             int rc = sm.pd_rc, no = sm.pd_no;
             if (rc == -2) {
                 if (MS) return SDB_ST_VALUEERROR;
@@ -400,70 +468,105 @@ __device__ int finish_match(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, c
             __syncwarp();
         }
     }
-    if (!MS) do_pad();                            /* message_unsynced.py:257-259: pad AFTER postDemod */
+    if (!MS) nb = (nb + pad - 1) / pad * pad;     /* message_unsynced.py:257-259: pad AFTER postDemod */
 
     if (MS) {
         if (has_f) return SDB_ST_OK;              /* bin_str_2_hex_str -> None (:224-226) */
     } else {
-        Payload P;
-        P.pp = pp; P.val = sm.val; P.fpl = sm.fpl; P.nb = nb; P.ndig = (nb + 3) >> 2;
-        P.has_f = has_f; P.bin = (flags & SDB_PF_DISPATCH_BIN) != 0; P.lz = 0;
-        if (P.bin) P.body = nb;
-        else if (has_f) P.body = 4;
-        else {
-            if (flags & SDB_PF_REMOVE_ZERO) {     /* lstrip('0') :268-269 */
-                int z = 0;
-                while (z < P.ndig && hex_digit(sm.val, nb, P.ndig, z) == 0) z++;
-                P.lz = z;
-            }
-            P.body = P.ndig - P.lz;
-        }
-        if (!modulematch(P, A.tab.mm)) return SDB_ST_OK;   /* :277-280 */
+        if (flags & SDB_PF_MM_NEVER) return SDB_ST_OK;
+        if (pp->mm_off != 0xFFFF && !modulematch(pp, A.tab.mm, nb, has_f)) return SDB_ST_OK;   /* :277-280 */
     }
-    emit_hit(A, sm, S, msg, pp, nb, has_f, ordinal);
+    emit_hit(A, pp, nb, has_f, ordinal);
     return SDB_ST_OK;
 }
 
-/* ---- one (message x MU protocol) task: message_unsynced.py:59-290 --------------------------- */
-__device__ int decode_mu(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
-                         int dlen, int npat, uint32_t pat_ids)
+/* exact per-byte equality flags (0x80 in every byte of x equal to the byte c) */
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t x, uint32_t c4)
 {
+    uint32_t z = x ^ c4;
+    return ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z) & 0x80808080u;
+}
+/* 0x80 flags of bytes 0..3 -> bits 0,2,4,6 */
+__device__ __forceinline__ uint32_t spread_even(uint32_t t)
+{
+    uint32_t u = t >> 7;
+    return (u | (u >> 6) | (u >> 12) | (u >> 18)) & 0x55u;
+}
+
+/* ---- one (message x MU protocol) task: message_unsynced.py:59-290 --------------------------- */
+__device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
+{
+    WarpSm &sm = SM();
     const int lane = lane_id();
+    const int dlen = sm.dlen;
     const int t_slot = sm.T[pp->clk_idx][lane & 7];
-    const uint16_t *rank = A.tab.rank;
     const int w = pp->width;
     const int flags = pp->flags;
 
     /* start (:67-88) */
-    int s0 = 0, Ls = pp->key[0].len;
+    int s0 = 0;
+    const int Ls = pp->key[0].len;
     uint64_t start_t = 0;
-    if (Ls) {
-        if (!resolve_key(&pp->key[0], rank, t_slot, npat, pat_ids, sm, dlen, 0, start_t, s0, true)) return SDB_ST_OK;
-    }
+    if (Ls && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return SDB_ST_OK;
     /* one / zero / float on D' = D[s0:] (:99-141) */
     uint64_t t1 = 0, t0 = 0, tf = 0;
     int dummy;
-    if (!resolve_key(&pp->key[1], rank, t_slot, npat, pat_ids, sm, dlen, s0, t1, dummy, false)) return SDB_ST_OK;
-    bool has0 = pp->key[2].len != 0, hasf = false;
-    if (has0 && !resolve_key(&pp->key[2], rank, t_slot, npat, pat_ids, sm, dlen, s0, t0, dummy, false)) return SDB_ST_OK;
-    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], rank, t_slot, npat, pat_ids, sm, dlen, s0, tf, dummy, false);
+    if (!resolve_key(&pp->key[1], t_slot, s0, false, t1, dummy)) return SDB_ST_OK;
+    const bool has0 = pp->key[2].len != 0;
+    bool hasf = false;
+    if (has0 && !resolve_key(&pp->key[2], t_slot, s0, false, t0, dummy)) return SDB_ST_OK;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
 
     const uint32_t wm = nibmask32(w);
-    const uint32_t c1 = (uint32_t)t1, c0 = (uint32_t)t0, cf = (uint32_t)tf;
-    const uint64_t lm = nibmask64(Ls);
+    const uint32_t c1 = (uint32_t)t1, c0 = has0 ? (uint32_t)t0 : (uint32_t)t1, cf = hasf ? (uint32_t)tf : (uint32_t)t1;
     const bool use_tail = (flags & SDB_PF_RECONSTRUCT) && w > 1;   /* w == 1: the tail key is '' and matches nothing extra */
     const uint32_t em = nibmask32(w - 1);
 
-    /* symbol bitmap B and start bitmap Sm over positions of D (only p >= s0 matter) */
-    uint32_t myB = 0, myS = 0;
-    const int nr = (dlen + 31) >> 5;              /* an empty START at p == dlen needs MIN == 0, which the table compiler rejects */
-    for (int r = 0; r < nr; r++) {
-        int p = r * 32 + lane;
-        uint32_t x = win32(sm.dig, p) & wm;
-        bool sym = (p + w <= dlen) && (x == c1 || (has0 && x == c0) || (hasf && x == cf));
-        bool st = Ls == 0 ? (p < dlen) : ((p + Ls <= dlen) && ((win64(sm.dig, p) & lm) == start_t));
-        uint32_t bw = __ballot_sync(FULL, sym), sw = __ballot_sync(FULL, st && p >= s0);
-        if (lane == r) { myB = bw; myS = sw; }
+    /* symbol bitmap B and start bitmap S over the positions of D (lane r = positions 32r..32r+31) */
+    uint32_t myB = 0, myS = Ls ? 0u : FULL;
+    if (w == 2 && (Ls == 0 || Ls == 2)) {
+        /* SWAR: each lane compares the 8 two-digit windows of one digit word against the symbol bytes.
+         * Windows reaching past dlen contain 0xF padding and never equal a symbol (digits <= 9). */
+        const uint32_t k1 = c1 * 0x01010101u, k0 = c0 * 0x01010101u, kf = cf * 0x01010101u, ks = (uint32_t)start_t * 0x01010101u;
+        const int nwords = (dlen + 7) >> 3;
+        for (int r0 = 0; r0 < nwords; r0 += 32) {
+            const int wi = r0 + lane;
+            uint32_t x = sm.dig[min(wi, DIG_WORDS - 2)], nx = sm.dig[min(wi + 1, DIG_WORDS - 1)];
+            uint32_t y = __funnelshift_r(x, nx, 4);                /* windows at odd positions */
+            uint32_t be = eq_bytes(x, k1) | eq_bytes(x, k0) | eq_bytes(x, kf);
+            uint32_t bo = eq_bytes(y, k1) | eq_bytes(y, k0) | eq_bytes(y, kf);
+            uint32_t b8 = spread_even(be) | (spread_even(bo) << 1);
+            if (wi >= nwords) b8 = 0;
+            uint32_t v = b8 << (8 * (lane & 3));
+            v |= __shfl_xor_sync(FULL, v, 1);
+            v |= __shfl_xor_sync(FULL, v, 2);
+            uint32_t got = __shfl_sync(FULL, v, (lane & 7) * 4);   /* mask word (r0/4 + lane&7) */
+            if ((lane >> 3) == (r0 >> 5)) myB = got;
+            if (Ls) {
+                uint32_t s8 = spread_even(eq_bytes(x, ks)) | (spread_even(eq_bytes(y, ks)) << 1);
+                if (wi >= nwords) s8 = 0;
+                uint32_t sv = s8 << (8 * (lane & 3));
+                sv |= __shfl_xor_sync(FULL, sv, 1);
+                sv |= __shfl_xor_sync(FULL, sv, 2);
+                uint32_t sgot = __shfl_sync(FULL, sv, (lane & 7) * 4);
+                if ((lane >> 3) == (r0 >> 5)) myS = sgot;
+            }
+        }
+    } else {
+        const uint64_t lm = nibmask64(Ls);
+        const int nr = (dlen + 31) >> 5;          /* an empty START at p == dlen needs MIN == 0, which the table compiler rejects */
+        for (int r = 0; r < nr; r++) {
+            int p = r * 32 + lane;
+            uint32_t x = win32(sm.dig, p) & wm;
+            bool sym = (p + w <= dlen) && (x == c1 || x == c0 || x == cf);
+            uint32_t bw = __ballot_sync(FULL, sym);
+            if (lane == r) myB = bw;
+            if (Ls) {
+                bool st = (p + Ls <= dlen) && ((win64(sm.dig, p) & lm) == start_t);
+                uint32_t sw = __ballot_sync(FULL, st);
+                if (lane == r) myS = sw;
+            }
+        }
     }
     /* R[p] = B[p] & B[p+w] & ... (MIN terms), by binary doubling */
     const int MIN = pp->regex_min;
@@ -520,7 +623,7 @@ __device__ int decode_mu(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, cons
             if (tail == 0) sm.val[n >> 5] |= 1u << (n & 31);
             else if (tail == 2) sm.fpl[n >> 5] |= 1u << (n & 31);
         }
-        int st = finish_match<false>(A, sm, S, msg, pp, nch, ordinal);
+        int st = finish_match<false>(A, pp, nch, ordinal, hasf);
         if (st != SDB_ST_OK) return st;
         ordinal++;
     }
@@ -528,24 +631,25 @@ __device__ int decode_mu(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, cons
 }
 
 /* ---- one (message x MS protocol) task: message_synced.py:90-241 ----------------------------- */
-__device__ int decode_ms(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, const SdbPulseProto *pp,
-                         int dlen, int npat, uint32_t pat_ids, int t_slot)
+__device__ __noinline__ int decode_ms(const KArgs &A, const SdbPulseProto *pp, int t_slot)
 {
+    WarpSm &sm = SM();
     const int lane = lane_id();
-    const uint16_t *rank = A.tab.rank;
+    const int dlen = sm.dlen;
     const int w = pp->width;
     const int flags = pp->flags;
     uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
     int spos = 0, dummy;
     const int Lsy = pp->key[0].len;
     /* sync, then length_min against the digits left after it (:140-156) */
-    if (!resolve_key(&pp->key[0], rank, t_slot, npat, pat_ids, sm, dlen, 0, ts, spos, true)) return SDB_ST_OK;
+    if (!resolve_key(&pp->key[0], t_slot, 0, true, ts, spos)) return SDB_ST_OK;
     const int ms = spos + Lsy;
     if ((int)pp->regex_min * w > dlen - ms) return SDB_ST_OK;   /* length_min > (len - start) / width */
-    if (!resolve_key(&pp->key[1], rank, t_slot, npat, pat_ids, sm, dlen, 0, t1, dummy, false)) return SDB_ST_OK;
-    bool has0 = pp->key[2].len != 0, hasf = false;
-    if (has0 && !resolve_key(&pp->key[2], rank, t_slot, npat, pat_ids, sm, dlen, 0, t0, dummy, false)) return SDB_ST_OK;
-    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], rank, t_slot, npat, pat_ids, sm, dlen, 0, tf, dummy, false);
+    if (!resolve_key(&pp->key[1], t_slot, 0, false, t1, dummy)) return SDB_ST_OK;
+    const bool has0 = pp->key[2].len != 0;
+    bool hasf = false;
+    if (has0 && !resolve_key(&pp->key[2], t_slot, 0, false, t0, dummy)) return SDB_ST_OK;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, 0, false, tf, dummy);
 
     const uint32_t wm = nibmask32(w), em = nibmask32(w - 1), sm_ = nibmask32(Lsy);
     const uint32_t c1 = (uint32_t)t1, c0 = (uint32_t)t0, cf = (uint32_t)tf, cs = (uint32_t)ts;
@@ -603,11 +707,11 @@ __device__ int decode_ms(const KArgs &A, WarpSm &sm, Sink &S, uint32_t msg, cons
         if (stop) break;
     }
     if (nb == 0) return SDB_ST_OK;                 /* :191 */
-    return finish_match<true>(A, sm, S, msg, pp, nb, 0);
+    return finish_match<true>(A, pp, nb, 0, hasf);
 }
 
 /* ---- phase 0: stage one message ---------------------------------------------------------- */
-__device__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen)
+__device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
 {
     const int lane = lane_id();
     const uint4 *src = reinterpret_cast<const uint4 *>(A.digits + (size_t)m->doff * 16);
@@ -620,6 +724,10 @@ __device__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, 
     for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; }
     if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
     if (lane < 8) sm.pat[lane] = m->pat[lane];
+    if (lane == 0) {
+        sm.rank = A.tab.rank; sm.dlen = dlen; sm.npat = m->npat; sm.pat_ids = m->pat_ids; sm.msg = mi;
+        sm.nh = 0; sm.nw = 0; sm.hbase = 0; sm.wbase = 0; sm.direct = 0; sm.overflow = 0;
+    }
     __syncwarp();
     /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
     for (int base = 0; base < dlen; base += 32) {
@@ -659,11 +767,11 @@ __device__ __forceinline__ bool prefilter_ok(const SdbPrefilter *__restrict__ pf
 }
 
 template <bool MS>
-__device__ int run_message(const KArgs &A, WarpSm &sm, Sink &S, uint32_t mi, const SdbPulseMsg *m)
+__device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
 {
+    WarpSm &sm = SM();
     const int lane = lane_id();
-    const int dlen = m->dlen, npat = m->npat;
-    const uint32_t pat_ids = m->pat_ids;
+    const int npat = sm.npat;
     int status = SDB_ST_OK;
     if (MS) {
         const int cp = m->cp;
@@ -690,7 +798,7 @@ __device__ int run_message(const KArgs &A, WarpSm &sm, Sink &S, uint32_t mi, con
             while (surv) {
                 int b = __ffs(surv) - 1;
                 surv &= surv - 1;
-                status = decode_ms(A, sm, S, mi, &A.tab.ms[q0 + b], dlen, npat, pat_ids, t_slot);
+                status = decode_ms(A, &A.tab.ms[q0 + b], t_slot);
                 if (status != SDB_ST_OK) return status;
             }
         }
@@ -720,7 +828,7 @@ __device__ int run_message(const KArgs &A, WarpSm &sm, Sink &S, uint32_t mi, con
             while (surv) {
                 int b = __ffs(surv) - 1;
                 surv &= surv - 1;
-                status = decode_mu(A, sm, S, mi, &A.tab.mu[q0 + b], dlen, npat, pat_ids);
+                status = decode_mu(A, &A.tab.mu[q0 + b]);
                 if (status != SDB_ST_OK) return status;
             }
         }
@@ -729,10 +837,9 @@ __device__ int run_message(const KArgs &A, WarpSm &sm, Sink &S, uint32_t mi, con
 }
 
 template <bool MS>
-__global__ void __launch_bounds__(SDB_PULSE_THREADS) pulse_kernel(KArgs A)
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, 3) pulse_kernel(KArgs A)
 {
-    __shared__ WarpSm smem[SDB_PULSE_THREADS / 32];
-    WarpSm &sm = smem[threadIdx.x >> 5];
+    WarpSm &sm = SM();
     const int lane = lane_id();
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -743,37 +850,37 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS) pulse_kernel(KArgs A)
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
         const int dlen = m->dlen;
         if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
-            stage_message(A, sm, m, dlen);
-            Sink S;
-            S.nh = 0; S.nw = 0; S.direct = false; S.overflow = false; S.hbase = 0; S.wbase = 0;
-            int status = run_message<MS>(A, sm, S, mi, m);
+            stage_message(A, sm, m, dlen, mi);
+            int status = run_message<MS>(A, m);
             __syncwarp();
+            const uint32_t nh = sm.nh, nw = sm.nw;
             if (status != SDB_ST_OK) {
                 mo.status = (uint8_t)status;                     /* exception: earlier hits are lost */
                 if (lane == 0) atomicAdd(&A.ctr->raised, 1u);
-            } else if (S.nh) {
+            } else if (nh) {
                 uint32_t hb = 0, wb = 0;
                 if (lane == 0) {
-                    hb = atomicAdd(&A.ctr->hits, S.nh);
-                    wb = atomicAdd(&A.ctr->words, S.nw);
+                    hb = atomicAdd(&A.ctr->hits, nh);
+                    wb = atomicAdd(&A.ctr->words, nw);
                 }
                 hb = __shfl_sync(FULL, hb, 0);
                 wb = __shfl_sync(FULL, wb, 0);
-                mo.hit_off = hb; mo.nhits = (uint16_t)S.nh;
-                if (!S.overflow) {
-                    if (hb + S.nh <= A.hits_cap && wb + S.nw <= A.bits_cap) {
-                        for (uint32_t i = lane; i < S.nh; i += 32) {
+                mo.hit_off = hb; mo.nhits = (uint16_t)nh;
+                if (!sm.overflow) {
+                    if (hb + nh <= A.hits_cap && wb + nw <= A.bits_cap) {
+                        for (uint32_t i = lane; i < nh; i += 32) {
                             SdbHit h = sm.st_hits[i];
                             h.bits_off += wb;
                             A.hits[hb + i] = h;
                         }
-                        for (uint32_t i = lane; i < S.nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
+                        for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
                     }
                 } else {
                     /* rare: more output than the staging area holds -> decode again, writing in place */
-                    Sink D;
-                    D.nh = 0; D.nw = 0; D.direct = true; D.overflow = false; D.hbase = hb; D.wbase = wb;
-                    run_message<MS>(A, sm, D, mi, m);
+                    __syncwarp();
+                    if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
+                    __syncwarp();
+                    run_message<MS>(A, m);
                 }
             }
         }
