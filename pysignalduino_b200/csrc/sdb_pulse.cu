@@ -46,8 +46,8 @@ namespace sdb {
 #define FULL 0xffffffffu
 #define DIG_WORDS (SDB_MAX_DIGITS / 8 + 4)
 #define BIT_WORDS (SDB_MAX_DIGITS / 32 + 4)
-#define ST_HITS 8
-#define ST_WORDS 48
+#define ST_HITS 24
+#define ST_WORDS 112
 #define NONE32 0xffffffffu
 #define WARPS (SDB_PULSE_THREADS / 32)
 
@@ -493,41 +493,44 @@ __device__ __forceinline__ uint32_t spread_even(uint32_t t)
     return (u | (u >> 6) | (u >> 12) | (u >> 18)) & 0x55u;
 }
 
-/* ---- one (message x MU protocol) task: message_unsynced.py:59-290 --------------------------- */
-__device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
+/* exact per-nibble equality of the 8 digits of x with digit c -> bits 0..7 */
+__device__ __forceinline__ uint32_t eq_nibbles8(uint32_t x, uint32_t c8)
+{
+    uint32_t z = x ^ c8;
+    uint32_t u = (~(((z & 0x77777777u) + 0x77777777u) | z) & 0x88888888u) >> 3;   /* bit 4k = digit k equal */
+    u = (u | (u >> 3)) & 0x03030303u;
+    u = (u | (u >> 6)) & 0x000F000Fu;
+    return (u | (u >> 12)) & 0xFFu;
+}
+
+/*
+ * The regex scan of one (message x MU protocol) task once the templates are resolved:
+ * message_unsynced.py:146-290.  start_t / t1 / t0 / tf = id strings (nibble-packed) of start, one,
+ * zero, float; s0 = where D' begins.
+ */
+__device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int s0, uint64_t start_t,
+                                    uint32_t t1, uint32_t t0, uint32_t tf, bool hasf)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
     const int dlen = sm.dlen;
-    const int t_slot = sm.T[pp->clk_idx][lane & 7];
     const int w = pp->width;
     const int flags = pp->flags;
-
-    /* start (:67-88) */
-    int s0 = 0;
     const int Ls = pp->key[0].len;
-    uint64_t start_t = 0;
-    if (Ls && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return SDB_ST_OK;
-    /* one / zero / float on D' = D[s0:] (:99-141) */
-    uint64_t t1 = 0, t0 = 0, tf = 0;
-    int dummy;
-    if (!resolve_key(&pp->key[1], t_slot, s0, false, t1, dummy)) return SDB_ST_OK;
     const bool has0 = pp->key[2].len != 0;
-    bool hasf = false;
-    if (has0 && !resolve_key(&pp->key[2], t_slot, s0, false, t0, dummy)) return SDB_ST_OK;
-    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
 
     const uint32_t wm = nibmask32(w);
-    const uint32_t c1 = (uint32_t)t1, c0 = has0 ? (uint32_t)t0 : (uint32_t)t1, cf = hasf ? (uint32_t)tf : (uint32_t)t1;
+    const uint32_t c1 = t1, c0 = has0 ? t0 : t1, cf = hasf ? tf : t1;
     const bool use_tail = (flags & SDB_PF_RECONSTRUCT) && w > 1;   /* w == 1: the tail key is '' and matches nothing extra */
     const uint32_t em = nibmask32(w - 1);
 
     /* symbol bitmap B and start bitmap S over the positions of D (lane r = positions 32r..32r+31) */
     uint32_t myB = 0, myS = Ls ? 0u : FULL;
-    if (w == 2 && (Ls == 0 || Ls == 2)) {
+    if (w == 2 && Ls <= 2) {
         /* SWAR: each lane compares the 8 two-digit windows of one digit word against the symbol bytes.
          * Windows reaching past dlen contain 0xF padding and never equal a symbol (digits <= 9). */
-        const uint32_t k1 = c1 * 0x01010101u, k0 = c0 * 0x01010101u, kf = cf * 0x01010101u, ks = (uint32_t)start_t * 0x01010101u;
+        const uint32_t k1 = c1 * 0x01010101u, k0 = c0 * 0x01010101u, kf = cf * 0x01010101u;
+        const uint32_t ks = Ls == 2 ? (uint32_t)start_t * 0x01010101u : ((uint32_t)start_t & 0xF) * 0x11111111u;
         const int nwords = (dlen + 7) >> 3;
         for (int r0 = 0; r0 < nwords; r0 += 32) {
             const int wi = r0 + lane;
@@ -543,7 +546,8 @@ __device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
             uint32_t got = __shfl_sync(FULL, v, (lane & 7) * 4);   /* mask word (r0/4 + lane&7) */
             if ((lane >> 3) == (r0 >> 5)) myB = got;
             if (Ls) {
-                uint32_t s8 = spread_even(eq_bytes(x, ks)) | (spread_even(eq_bytes(y, ks)) << 1);
+                uint32_t s8 = Ls == 2 ? (spread_even(eq_bytes(x, ks)) | (spread_even(eq_bytes(y, ks)) << 1))
+                                      : eq_nibbles8(x, ks);        /* one-pulse start: plain digit compare */
                 if (wi >= nwords) s8 = 0;
                 uint32_t sv = s8 << (8 * (lane & 3));
                 sv |= __shfl_xor_sync(FULL, sv, 1);
@@ -628,6 +632,129 @@ __device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
         ordinal++;
     }
     return SDB_ST_OK;
+}
+
+/* ---- one (message x MU protocol) task, warp-level resolution (long `start`, 1- or 4-digit symbols):
+ *      message_unsynced.py:59-141, then the scan ------------------------------------------------ */
+__device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
+{
+    WarpSm &sm = SM();
+    const int t_slot = sm.T[pp->clk_idx][lane_id() & 7];
+    /* start (:67-88) */
+    int s0 = 0;
+    uint64_t start_t = 0;
+    if (pp->key[0].len && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return SDB_ST_OK;
+    /* one / zero / float on D' = D[s0:] (:99-141) */
+    uint64_t t1 = 0, t0 = 0, tf = 0;
+    int dummy;
+    if (!resolve_key(&pp->key[1], t_slot, s0, false, t1, dummy)) return SDB_ST_OK;
+    bool hasf = false;
+    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, s0, false, t0, dummy)) return SDB_ST_OK;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
+    return scan_mu(A, pp, s0, start_t, (uint32_t)t1, (uint32_t)t0, (uint32_t)tf, hasf);
+}
+
+/* ---- thread-level pattern_exists for templates of <= 2 pulses (<= 2 distinct values) -----------
+ * One LANE resolves one protocol: candidates are ordered by (gap rank, slot) by repeated
+ * min-extraction from 8 registers, the product is walked in itertools.product order, and
+ * "target in D[from:]" is one shared-memory table lookup.  (pattern_utils.py:34-136) */
+#define TKEY_NONE 0x7fffffff
+__device__ __forceinline__ int tkey_min8(const int k[8])
+{
+    int m = min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
+    return m;
+}
+__device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int t[8], const WarpSm &sm, int from,
+                                     uint32_t &code, int &pos)
+{
+    const int L = k->len, K = k->nuniq;
+    const uint32_t uidx = k->uidx, ids = sm.pat_ids;
+    const int npat = sm.npat;
+    const uint16_t *__restrict__ rank = sm.rank;
+    int ka[8], kb[8];
+    int na = 0, nb = 0;
+    {
+        const int lo = k->lo[0], hi = k->hi[0];
+        const uint32_t ro = k->rank_off[0];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            bool in = j < npat && t[j] >= lo && t[j] <= hi;
+            ka[j] = in ? (((int)__ldg(&rank[ro + (t[j] - lo)]) << 3) | j) : TKEY_NONE;
+            na += in;
+        }
+    }
+    if (!na) return false;                                    /* :78-80 */
+    if (K > 1) {
+        const int lo = k->lo[1], hi = k->hi[1];
+        const uint32_t ro = k->rank_off[1];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            bool in = j < npat && t[j] >= lo && t[j] <= hi;
+            kb[j] = in ? (((int)__ldg(&rank[ro + (t[j] - lo)]) << 3) | j) : TKEY_NONE;
+            nb += in;
+        }
+        if (!nb) return false;
+    }
+    for (int ia = 0; ia < na; ia++) {                         /* :111 product order: first list slowest */
+        const int ma = tkey_min8(ka);
+        const int sa = ma & 7;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (ka[j] == ma) ka[j] = TKEY_NONE;
+        const int da = (ids >> (4 * sa)) & 0xF;
+        if (K == 1) {
+            bool ok;
+            if (L == 1) { ok = sm.last1[da] > (uint32_t)from; if (ok) { code = da; pos = (int)sm.first1[da]; } }
+            else { ok = sm.last2[da * 11] > (uint32_t)from; if (ok) { code = da * 0x11; pos = (int)sm.first2[da * 11]; } }
+            if (ok) return true;
+            continue;
+        }
+        int kc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) kc[j] = kb[j];
+        for (int ib = 0; ib < nb; ib++) {
+            const int mb = tkey_min8(kc);
+            const int sb = mb & 7;
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (kc[j] == mb) kc[j] = TKEY_NONE;
+            if (sb == sa) continue;                           /* :114 one id for two values */
+            const int db = (ids >> (4 * sb)) & 0xF;
+            const int d0 = (uidx & 3) ? db : da, d1 = ((uidx >> 2) & 3) ? db : da;   /* :118-127 */
+            if (sm.last2[d0 * 10 + d1] > (uint32_t)from) {    /* :133 */
+                code = (uint32_t)(d0 | (d1 << 4));
+                pos = (int)sm.first2[d0 * 10 + d1];
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+/* Thread-level resolution of one MU protocol (2-digit symbols, start of <= 2 pulses).
+ * Returns 0 dead, 1 resolved (codes = start | one<<8 | zero<<16 | float<<24, s0f = s0 | hasf<<16),
+ * 2 = needs the warp-level path. */
+__device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const int t[8], const WarpSm &sm,
+                                                 uint32_t &codes, uint32_t &s0f)
+{
+    if (pp->width != 2 || pp->key[0].len > 2) return 2;
+    uint32_t acc = 0, hasf = 0;
+    int s0 = 0;
+#pragma unroll 1
+    for (int kk = 0; kk < 4; kk++) {                          /* start (:67-88), then one / zero / float (:99-141) */
+        const SdbKeyTpl *k = &pp->key[kk];
+        if (!k->len) continue;
+        uint32_t code = 0;
+        int p = 0;
+        if (!tres(k, t, sm, kk == 0 ? 0 : s0, code, p)) {
+            if (kk == 3) break;                               /* float is optional (:138) */
+            return 0;
+        }
+        if (kk == 0) s0 = p;                                  /* D' = D[find(start):] */
+        if (kk == 3) hasf = 1;
+        acc |= code << (8 * kk);
+    }
+    codes = acc;
+    s0f = (uint32_t)s0 | (hasf << 16);
+    return 1;
 }
 
 /* ---- one (message x MS protocol) task: message_synced.py:90-241 ----------------------------- */
@@ -814,6 +941,8 @@ __device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
         for (uint32_t q0 = 0; q0 < n; q0 += 32) {
             uint32_t q = q0 + lane;
             bool alive = false;
+            int state = 0;
+            uint32_t codes = 0, s0f = 0;
             if (q < n) {
                 const SdbPrefilter *pf = &A.tab.mu_pf[q];
                 const int4 row = *reinterpret_cast<const int4 *>(&sm.T[pf->clk_idx][0]);
@@ -823,12 +952,20 @@ __device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
                 t[4] = (int16_t)(row.z & 0xffff); t[5] = row.z >> 16;
                 t[6] = (int16_t)(row.w & 0xffff); t[7] = row.w >> 16;
                 alive = prefilter_ok(pf, t);
+                if (alive) {                                  /* exact template resolution, one lane per protocol */
+                    state = thread_resolve_mu(&A.tab.mu[q], t, sm, codes, s0f);
+                    alive = state != 0;
+                }
             }
             uint32_t surv = __ballot_sync(FULL, alive);
-            while (surv) {
+            while (surv) {                                    /* protocol-table order */
                 int b = __ffs(surv) - 1;
                 surv &= surv - 1;
-                status = decode_mu(A, &A.tab.mu[q0 + b]);
+                const int st_b = __shfl_sync(FULL, state, b);
+                const uint32_t cd = __shfl_sync(FULL, codes, b), sf = __shfl_sync(FULL, s0f, b);
+                const SdbPulseProto *pp = &A.tab.mu[q0 + b];
+                if (st_b == 2) status = decode_mu(A, pp);
+                else status = scan_mu(A, pp, (int)(sf & 0xFFFF), cd & 0xFF, (cd >> 8) & 0xFF, (cd >> 16) & 0xFF, cd >> 24, (sf >> 16) != 0);
                 if (status != SDB_ST_OK) return status;
             }
         }
