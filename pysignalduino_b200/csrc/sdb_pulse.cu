@@ -125,7 +125,7 @@ __device__ __forceinline__ int tenths(int p, double c)
 }
 
 /* X >> nb for a 1024-bit value spread little-endian over the warp (lane r = bits 32r..32r+31) */
-__device__ __forceinline__ uint32_t shr_dist(uint32_t mine, int nb)
+__device__ __noinline__ uint32_t shr_dist(uint32_t mine, int nb)
 {
     int lane = lane_id();
     int ws = nb >> 5, bs = nb & 31;
@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t shr_dist(uint32_t mine, int nb)
 }
 
 /* first set bit at position >= pos of a distributed 1024-bit value, -1 if none */
-__device__ __forceinline__ int first_set_from(uint32_t mine, int pos)
+__device__ __noinline__ int first_set_from(uint32_t mine, int pos)
 {
     int base = lane_id() * 32;
     uint32_t w = mine;
@@ -532,6 +532,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
         const uint32_t k1 = c1 * 0x01010101u, k0 = c0 * 0x01010101u, kf = cf * 0x01010101u;
         const uint32_t ks = Ls == 2 ? (uint32_t)start_t * 0x01010101u : ((uint32_t)start_t & 0xF) * 0x11111111u;
         const int nwords = (dlen + 7) >> 3;
+        #pragma unroll 1
         for (int r0 = 0; r0 < nwords; r0 += 32) {
             const int wi = r0 + lane;
             uint32_t x = sm.dig[min(wi, DIG_WORDS - 2)], nx = sm.dig[min(wi + 1, DIG_WORDS - 1)];
@@ -559,6 +560,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
     } else {
         const uint64_t lm = nibmask64(Ls);
         const int nr = (dlen + 31) >> 5;          /* an empty START at p == dlen needs MIN == 0, which the table compiler rejects */
+        #pragma unroll 1
         for (int r = 0; r < nr; r++) {
             int p = r * 32 + lane;
             uint32_t x = win32(sm.dig, p) & wm;
@@ -576,6 +578,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
     const int MIN = pp->regex_min;
     uint32_t R = FULL, Acc = myB;
     int rl = 0, al = 1;
+    #pragma unroll 1
     for (int m = MIN; m > 0; m >>= 1) {
         if (m & 1) { R &= rl ? shr_dist(Acc, rl * w) : Acc; rl += al; }
         if (m > 1) { Acc &= shr_dist(Acc, al * w); al <<= 1; }
@@ -607,6 +610,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
         if (pp->mu_len_max >= 0 && nch > pp->mu_len_max) continue;   /* :217 */
         /* chunks -> bits (:220-228): later keys overwrite earlier ones on identical strings */
         __syncwarp();
+        #pragma unroll 1
         for (int b0 = 0; b0 < n; b0 += 32) {
             int c = b0 + lane;
             bool isf = false, one = false;
@@ -883,6 +887,7 @@ __device__ __forceinline__ bool prefilter_ok(const SdbPrefilter *__restrict__ pf
 {
     const int nreq = pf->nreq;
     bool ok = true;
+    #pragma unroll 1
     for (int r = 0; r < nreq && ok; r++) {
         int lo = pf->lo[r], hi = pf->hi[r];
         bool any = false;
@@ -932,6 +937,7 @@ __device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
     } else {
         /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
         const int ncl = A.tab.n_clk;
+        #pragma unroll 1
         for (int idx = lane; idx < ncl * 8; idx += 32) {
             int c = idx >> 3, j = idx & 7;
             sm.T[c][j] = (int16_t)(j < npat ? tenths(sm.pat[j], __ldg(&A.tab.clk[c])) : -32768);
