@@ -33,6 +33,8 @@ struct SdbHandle {
     uint32_t *d_bits = nullptr;  size_t cap_bits = 0;
     SdbCounters *d_ctr = nullptr;
     uint8_t *d_unit = nullptr;          /* unit-op scratch */
+    void *d_mu_scratch = nullptr;       /* MU survivor slots (resolve kernel -> scan kernel), allocated on first MU call */
+    uint32_t mu_chunk = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -101,7 +103,7 @@ extern "C" void sdb_destroy(SdbHandle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit);
+    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -119,9 +121,20 @@ extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
     int grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
-    uint32_t need = (n + (SDB_PULSE_THREADS / 32) - 1) / (SDB_PULSE_THREADS / 32);
-    if (need < (uint32_t)grid) grid = (int)(need ? need : 1);
-    int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid, st);
+    if (kind == SDB_KIND_MU && n) {
+        /* scratch is sized for the worst case (every protocol of every message survives), once per handle */
+        uint32_t chunk = n < SDB_MU_CHUNK ? ((n + 1023u) & ~1023u) : SDB_MU_CHUNK;
+        if (chunk > h->mu_chunk) {
+            CK(cudaSetDevice(h->device));
+            CK(cudaStreamSynchronize(st));
+            if (h->d_mu_scratch) CK(cudaFree(h->d_mu_scratch));
+            h->d_mu_scratch = nullptr; h->mu_chunk = 0;
+            CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_mu, chunk)));
+            h->mu_chunk = chunk;
+        }
+    }
+    int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid,
+                               h->d_mu_scratch, h->mu_chunk, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "pulse kernel launch", static_cast<cudaError_t>(rc));
     return SDB_OK;
 }

@@ -51,15 +51,25 @@ namespace sdb {
 #define NONE32 0xffffffffu
 #define WARPS (SDB_PULSE_THREADS / 32)
 
+/* One resolved (message x MU protocol) task handed from the resolve kernel to the scan kernel, 16 bytes. */
+struct __align__(16) SdbSurv {
+    uint64_t start;        /* bits 0..55: id string of `start` (nibble-packed), bits 56..63: MU table row */
+    uint16_t c1, c0, cf;   /* id strings of one / zero / float (<= 4 digits) */
+    uint16_t meta;         /* bits 0..10: s0 (where D' begins), bit 11: float resolved */
+};
+
 struct KArgs {
     SdbDevTable tab;
-    const SdbPulseMsg *msgs;
+    const SdbPulseMsg *msgs;   /* already offset to the first message of this launch */
     const uint8_t *digits;
-    uint32_t n;
-    SdbMsgOut *out;
+    uint32_t n;                /* messages of this launch */
+    uint32_t msg_base;         /* batch index of msgs[0] (hit.msg is a batch index) */
+    SdbMsgOut *out;            /* already offset */
     SdbHit *hits;  uint32_t hits_cap;
     uint32_t *bits; uint32_t bits_cap;
     SdbCounters *ctr;
+    SdbSurv *surv;             /* MU: n x n_mu survivor slots (resolve -> scan) */
+    uint32_t *surv_cnt;        /* MU: survivors per message */
 };
 
 struct __align__(16) WarpSm {
@@ -842,7 +852,8 @@ __device__ __noinline__ int decode_ms(const KArgs &A, const SdbPulseProto *pp, i
 }
 
 /* ---- phase 0: stage one message ---------------------------------------------------------- */
-__device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
+/* digits + per-message scalars only (all the scan kernel needs) */
+__device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
 {
     const int lane = lane_id();
     const uint4 *src = reinterpret_cast<const uint4 *>(A.digits + (size_t)m->doff * 16);
@@ -852,14 +863,20 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
         reinterpret_cast<uint4 *>(sm.dig)[lane] = v;
     }
     if (lane < 4) sm.dig[4 * nq + lane] = FULL;    /* windows may read 3 words past the last digit */
-    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; }
-    if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
     if (lane < 8) sm.pat[lane] = m->pat[lane];
     if (lane == 0) {
-        sm.rank = A.tab.rank; sm.dlen = dlen; sm.npat = m->npat; sm.pat_ids = m->pat_ids; sm.msg = mi;
+        sm.rank = A.tab.rank; sm.dlen = dlen; sm.npat = m->npat; sm.pat_ids = m->pat_ids; sm.msg = A.msg_base + mi;
         sm.nh = 0; sm.nw = 0; sm.hbase = 0; sm.wbase = 0; sm.direct = 0; sm.overflow = 0;
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
+{
+    const int lane = lane_id();
+    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; }
+    if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
+    stage_digits(A, sm, m, dlen, mi);
     /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
     for (int base = 0; base < dlen; base += 32) {
         int p = base + lane;
@@ -934,53 +951,12 @@ __device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
                 if (status != SDB_ST_OK) return status;
             }
         }
-    } else {
-        /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
-        const int ncl = A.tab.n_clk;
-        #pragma unroll 1
-        for (int idx = lane; idx < ncl * 8; idx += 32) {
-            int c = idx >> 3, j = idx & 7;
-            sm.T[c][j] = (int16_t)(j < npat ? tenths(sm.pat[j], __ldg(&A.tab.clk[c])) : -32768);
-        }
-        __syncwarp();
-        const uint32_t n = A.tab.n_mu;
-        for (uint32_t q0 = 0; q0 < n; q0 += 32) {
-            uint32_t q = q0 + lane;
-            bool alive = false;
-            int state = 0;
-            uint32_t codes = 0, s0f = 0;
-            if (q < n) {
-                const SdbPrefilter *pf = &A.tab.mu_pf[q];
-                const int4 row = *reinterpret_cast<const int4 *>(&sm.T[pf->clk_idx][0]);
-                int t[8];
-                t[0] = (int16_t)(row.x & 0xffff); t[1] = row.x >> 16;
-                t[2] = (int16_t)(row.y & 0xffff); t[3] = row.y >> 16;
-                t[4] = (int16_t)(row.z & 0xffff); t[5] = row.z >> 16;
-                t[6] = (int16_t)(row.w & 0xffff); t[7] = row.w >> 16;
-                alive = prefilter_ok(pf, t);
-                if (alive) {                                  /* exact template resolution, one lane per protocol */
-                    state = thread_resolve_mu(&A.tab.mu[q], t, sm, codes, s0f);
-                    alive = state != 0;
-                }
-            }
-            uint32_t surv = __ballot_sync(FULL, alive);
-            while (surv) {                                    /* protocol-table order */
-                int b = __ffs(surv) - 1;
-                surv &= surv - 1;
-                const int st_b = __shfl_sync(FULL, state, b);
-                const uint32_t cd = __shfl_sync(FULL, codes, b), sf = __shfl_sync(FULL, s0f, b);
-                const SdbPulseProto *pp = &A.tab.mu[q0 + b];
-                if (st_b == 2) status = decode_mu(A, pp);
-                else status = scan_mu(A, pp, (int)(sf & 0xFFFF), cd & 0xFF, (cd >> 8) & 0xFF, (cd >> 16) & 0xFF, cd >> 24, (sf >> 16) != 0);
-                if (status != SDB_ST_OK) return status;
-            }
-        }
     }
     return status;
 }
 
 template <bool MS>
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, 3) pulse_kernel(KArgs A)
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) pulse_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1032,12 +1008,195 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, 3) pulse_kernel(KArgs A)
     }
 }
 
+/* =========================================================================================
+ * MU runs as TWO kernels so that each has a small instruction footprint (ncu: the fused kernel
+ * spent > 50 % of its stall samples waiting for instruction fetch):
+ *   mu_resolve_kernel  message_unsynced.py:59-141 for every protocol -> SdbSurv records
+ *   mu_scan_kernel     message_unsynced.py:146-290 for every survivor, in protocol-table order
+ * Both are one warp per message; the survivor slots of message i are surv[i*n_mu .. +n_mu).
+ * ========================================================================================= */
+
+/* warp-level template resolution of one "complex" MU protocol (long start / 1- or 4-digit symbols) */
+__device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &rec)
+{
+    WarpSm &sm = SM();
+    const int t_slot = sm.T[pp->clk_idx][lane_id() & 7];
+    int s0 = 0, dummy;
+    uint64_t start_t = 0, t1 = 0, t0 = 0, tf = 0;
+    if (pp->key[0].len && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return false;      /* :67-88 */
+    if (!resolve_key(&pp->key[1], t_slot, s0, false, t1, dummy)) return false;                        /* :99-141 */
+    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, s0, false, t0, dummy)) return false;
+    bool hasf = false;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
+    rec.start = start_t;
+    rec.c1 = (uint16_t)t1; rec.c0 = (uint16_t)t0; rec.cf = (uint16_t)tf;
+    rec.meta = (uint16_t)(s0 | (hasf ? 0x800 : 0));
+    return true;
+}
+
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_resolve_kernel(KArgs A)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_mu = A.tab.n_mu;
+
+    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+        const SdbPulseMsg *m = &A.msgs[mi];
+        const int dlen = m->dlen;
+        uint32_t nsurv = 0;
+        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
+            stage_message(A, sm, m, dlen, mi);
+            const int npat = sm.npat;
+            /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
+            const int ncl = A.tab.n_clk;
+#pragma unroll 1
+            for (int idx = lane; idx < ncl * 8; idx += 32) {
+                int c = idx >> 3, j = idx & 7;
+                sm.T[c][j] = (int16_t)(j < npat ? tenths(sm.pat[j], __ldg(&A.tab.clk[c])) : -32768);
+            }
+            __syncwarp();
+            SdbSurv *slots = A.surv + (size_t)mi * n_mu;
+#pragma unroll 1
+            for (uint32_t q0 = 0; q0 < n_mu; q0 += 32) {
+                const uint32_t q = q0 + lane;
+                int state = 0;
+                SdbSurv rec;
+                rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
+                if (q < n_mu) {
+                    const SdbPrefilter *pf = &A.tab.mu_pf[q];
+                    const int4 row = *reinterpret_cast<const int4 *>(&sm.T[pf->clk_idx][0]);
+                    int t[8];
+                    t[0] = (int16_t)(row.x & 0xffff); t[1] = row.x >> 16;
+                    t[2] = (int16_t)(row.y & 0xffff); t[3] = row.y >> 16;
+                    t[4] = (int16_t)(row.z & 0xffff); t[5] = row.z >> 16;
+                    t[6] = (int16_t)(row.w & 0xffff); t[7] = row.w >> 16;
+                    if (prefilter_ok(pf, t)) {                    /* exact template resolution, one lane per protocol */
+                        uint32_t codes = 0, s0f = 0;
+                        state = thread_resolve_mu(&A.tab.mu[q], t, sm, codes, s0f);
+                        rec.start = codes & 0xFF;
+                        rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
+                        rec.meta = (uint16_t)((s0f & 0x7FF) | ((s0f >> 16) ? 0x800 : 0));
+                    }
+                }
+                /* the few protocols that need warp-wide searches are resolved one after the other */
+                uint32_t cx = __ballot_sync(FULL, state == 2);
+                while (cx) {
+                    const int b = __ffs(cx) - 1;
+                    cx &= cx - 1;
+                    SdbSurv r2;
+                    const bool ok = resolve_mu_warp(&A.tab.mu[q0 + b], r2);
+                    if (lane == b) { state = ok ? 1 : 0; rec = r2; }
+                }
+                const uint32_t alive = __ballot_sync(FULL, state == 1);
+                if (state == 1) {                                 /* protocol-table order is the slot order */
+                    rec.start |= (uint64_t)q << 56;
+                    slots[nsurv + __popc(alive & ((1u << lane) - 1))] = rec;
+                }
+                nsurv += __popc(alive);
+            }
+        }
+        if (lane == 0) A.surv_cnt[mi] = nsurv;
+        __syncwarp();
+    }
+}
+
+__device__ __noinline__ int mu_scan_survivors(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
+{
+    const int lane = lane_id();
+#pragma unroll 1
+    for (uint32_t s0i = 0; s0i < nsurv; s0i += 32) {
+        SdbSurv mine;
+        mine.start = 0; mine.c1 = mine.c0 = mine.cf = 0; mine.meta = 0;
+        if (s0i + lane < nsurv) mine = slots[s0i + lane];             /* coalesced 16-byte loads */
+        const int cnt = min(32u, nsurv - s0i);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const uint32_t slo = __shfl_sync(FULL, (uint32_t)mine.start, k);
+            const uint32_t shi = __shfl_sync(FULL, (uint32_t)(mine.start >> 32), k);
+            const uint32_t c10 = __shfl_sync(FULL, (uint32_t)mine.c1 | ((uint32_t)mine.c0 << 16), k);
+            const uint32_t cfm = __shfl_sync(FULL, (uint32_t)mine.cf | ((uint32_t)mine.meta << 16), k);
+            const SdbPulseProto *pp = &A.tab.mu[shi >> 24];
+            const uint64_t start_t = (((uint64_t)(shi & 0x00FFFFFFu)) << 32) | slo;
+            const int st = scan_mu(A, pp, (int)((cfm >> 16) & 0x7FF), start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF,
+                                   ((cfm >> 16) & 0x800) != 0);
+            if (st != SDB_ST_OK) return st;
+        }
+    }
+    return SDB_ST_OK;
+}
+
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_scan_kernel(KArgs A)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_mu = A.tab.n_mu;
+
+    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+        const SdbPulseMsg *m = &A.msgs[mi];
+        SdbMsgOut mo;
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        const uint32_t nsurv = A.surv_cnt[mi];
+        if (nsurv) {
+            const SdbSurv *slots = A.surv + (size_t)mi * n_mu;
+            stage_digits(A, sm, m, m->dlen, mi);
+            int status = mu_scan_survivors(A, slots, nsurv);
+            __syncwarp();
+            const uint32_t nh = sm.nh, nw = sm.nw;
+            if (status != SDB_ST_OK) {
+                mo.status = (uint8_t)status;                     /* exception: earlier hits are lost */
+                if (lane == 0) atomicAdd(&A.ctr->raised, 1u);
+            } else if (nh) {
+                uint32_t hb = 0, wb = 0;
+                if (lane == 0) {
+                    hb = atomicAdd(&A.ctr->hits, nh);
+                    wb = atomicAdd(&A.ctr->words, nw);
+                }
+                hb = __shfl_sync(FULL, hb, 0);
+                wb = __shfl_sync(FULL, wb, 0);
+                mo.hit_off = hb; mo.nhits = (uint16_t)nh;
+                if (!sm.overflow) {
+                    if (hb + nh <= A.hits_cap && wb + nw <= A.bits_cap) {
+                        for (uint32_t i = lane; i < nh; i += 32) {
+                            SdbHit h = sm.st_hits[i];
+                            h.bits_off += wb;
+                            A.hits[hb + i] = h;
+                        }
+                        for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
+                    }
+                } else {
+                    /* rare: more output than the staging area holds -> scan again, writing in place */
+                    __syncwarp();
+                    if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
+                    __syncwarp();
+                    mu_scan_survivors(A, slots, nsurv);
+                }
+            }
+        }
+        if (lane == 0) A.out[mi] = mo;
+        __syncwarp();
+    }
+}
+
 int pulse_blocks_per_sm(int kind)
 {
     int nb = 0;
     if (kind == SDB_KIND_MS) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pulse_kernel<true>, SDB_PULSE_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pulse_kernel<false>, SDB_PULSE_THREADS, 0);
+    else {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mu_resolve_kernel, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mu_scan_kernel, SDB_PULSE_THREADS, 0);
+        nb = a < b ? a : b;
+    }
     return nb > 0 ? nb : 1;
+}
+
+size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk)
+{
+    return (size_t)chunk * n_mu * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t);
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
@@ -1063,14 +1222,30 @@ int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, cudaStream_t stream)
+                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, cudaStream_t stream)
 {
     KArgs A;
-    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.out = d_out;
+    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = 0; A.out = d_out;
     A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
+    A.surv = nullptr; A.surv_cnt = nullptr;
     if (n == 0) return 0;
-    if (kind == SDB_KIND_MS) pulse_kernel<true><<<grid, SDB_PULSE_THREADS, 0, stream>>>(A);
-    else pulse_kernel<false><<<grid, SDB_PULSE_THREADS, 0, stream>>>(A);
+    const uint32_t wpc = SDB_PULSE_THREADS / 32;
+    if (kind == SDB_KIND_MS) {
+        uint32_t need = (n + wpc - 1) / wpc;
+        pulse_kernel<true><<<need < (uint32_t)grid ? need : grid, SDB_PULSE_THREADS, 0, stream>>>(A);
+        return (int)cudaGetLastError();
+    }
+    if (!mu_scratch || !mu_chunk) return (int)cudaErrorInvalidValue;
+    A.surv = static_cast<SdbSurv *>(mu_scratch);
+    A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * tab.n_mu * sizeof(SdbSurv));
+    for (uint32_t off = 0; off < n; off += mu_chunk) {
+        A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = off;
+        A.n = n - off < mu_chunk ? n - off : mu_chunk;
+        uint32_t need = (A.n + wpc - 1) / wpc;
+        int g = need < (uint32_t)grid ? (int)need : grid;
+        mu_resolve_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+        mu_scan_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+    }
     return (int)cudaGetLastError();
 }
 

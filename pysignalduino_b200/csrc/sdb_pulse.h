@@ -6,14 +6,20 @@
 #include "sdb_table.h"
 
 #define SDB_PULSE_THREADS 256   /* 8 warps = 8 messages in flight per CTA */
+#ifndef SDB_PULSE_MIN_CTAS
+#define SDB_PULSE_MIN_CTAS 4  /* register cap = 65536 / (256 * MIN_CTAS) */
+#endif
 #define SDB_HEX_THREADS   128
 
 namespace sdb {
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, cudaStream_t stream);
+                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, cudaStream_t stream);
 int pulse_blocks_per_sm(int kind);
+size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots handed from mu_resolve_kernel to mu_scan_kernel */
+
+#define SDB_MU_CHUNK 262144u    /* messages per resolve/scan launch pair (bounds the survivor scratch: chunk * n_mu * 16 B) */
 
 int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMsg *d_msgs, const uint8_t *d_digits,
                uint32_t n, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
