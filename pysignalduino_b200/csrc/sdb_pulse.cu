@@ -76,6 +76,7 @@ struct __align__(16) WarpSm {
     uint32_t dig[DIG_WORDS];          /* nibble-packed digits, 0xF beyond dlen               */
     uint32_t first2[100], last2[100]; /* digram ab: first position / last position + 1       */
     uint32_t first1[12], last1[12];   /* digit a                                             */
+    uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
     int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
     int32_t  pat[8];
     uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
@@ -132,6 +133,24 @@ __device__ __forceinline__ int tenths(int p, double c)
     if (r > 32000.0) r = 32000.0;              /* far outside every accept interval */
     if (r < -32000.0) r = -32000.0;
     return (int)r;
+}
+
+/* Same value, usually without the division: y' = p * (10/c) differs from the exact 10*RN(p/c) by < 1e-10,
+ * so whenever y' is further than 1e-6 from a tie both round to the same integer; only near-ties (and
+ * they do occur: p/c = 0.25, 0.35, ...) take the exact path. */
+__device__ __forceinline__ int tenths_fast(int p, double c, double inv10c)
+{
+    double y = __dmul_rn((double)p, inv10c);
+    if (y >= 40000.0) return 32000;
+    if (y <= -40000.0) return -32000;
+    double r = rint(y);
+    double d = fabs(__dsub_rn(y, r));
+    if (fabs(d - 0.5) > 1e-6) {
+        if (r > 32000.0) r = 32000.0;
+        if (r < -32000.0) r = -32000.0;
+        return (int)r;
+    }
+    return tenths(p, c);
 }
 
 /* X >> nb for a 1024-bit value spread little-endian over the warp (lane r = bits 32r..32r+31) */
@@ -683,31 +702,46 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int 
 {
     const int L = k->len, K = k->nuniq;
     const uint32_t uidx = k->uidx, ids = sm.pat_ids;
-    const int npat = sm.npat;
     const uint16_t *__restrict__ rank = sm.rank;
-    int ka[8], kb[8];
-    int na = 0, nb = 0;
-    {
-        const int lo = k->lo[0], hi = k->hi[0];
-        const uint32_t ro = k->rank_off[0];
+    /* candidate slots of the (<= 2) distinct values; empty slots hold -32768 and never qualify (:73-76) */
+    const int lo0 = k->lo[0], hi0 = k->hi[0];
+    const int lo1 = K > 1 ? k->lo[1] : 1, hi1 = K > 1 ? k->hi[1] : 0;
+    uint32_t ca = 0, cb = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            bool in = j < npat && t[j] >= lo && t[j] <= hi;
-            ka[j] = in ? (((int)__ldg(&rank[ro + (t[j] - lo)]) << 3) | j) : TKEY_NONE;
-            na += in;
-        }
+    for (int j = 0; j < 8; j++) {
+        ca |= (uint32_t)(t[j] >= lo0 && t[j] <= hi0) << j;
+        cb |= (uint32_t)(t[j] >= lo1 && t[j] <= hi1) << j;
     }
-    if (!na) return false;                                    /* :78-80 */
-    if (K > 1) {
-        const int lo = k->lo[1], hi = k->hi[1];
-        const uint32_t ro = k->rank_off[1];
+    if (!ca || (K > 1 && !cb)) return false;                  /* :78-80 */
+    if (!(ca & (ca - 1)) && !(cb & (cb - 1))) {
+        /* the common case: one candidate per value -> a single combination, no ordering needed */
+        const int sa = __ffs(ca) - 1;
+        const int da = (ids >> (4 * sa)) & 0xF;
+        int d0 = da, d1 = da;
+        if (K > 1) {
+            const int sb = __ffs(cb) - 1;
+            if (sb == sa) return false;                       /* :114 */
+            const int db = (ids >> (4 * sb)) & 0xF;
+            d0 = (uidx & 3) ? db : da; d1 = ((uidx >> 2) & 3) ? db : da;
+        }
+        if (L == 1) {
+            if (sm.last1[d0] <= (uint32_t)from) return false;
+            code = (uint32_t)d0; pos = (int)sm.first1[d0];
+        } else {
+            if (sm.last2[d0 * 10 + d1] <= (uint32_t)from) return false;
+            code = (uint32_t)(d0 | (d1 << 4)); pos = (int)sm.first2[d0 * 10 + d1];
+        }
+        return true;
+    }
+    int ka[8], kb[8];
+    const int na = __popc(ca), nb = __popc(cb);
+    {
+        const uint32_t ro0 = k->rank_off[0], ro1 = K > 1 ? k->rank_off[1] : 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            bool in = j < npat && t[j] >= lo && t[j] <= hi;
-            kb[j] = in ? (((int)__ldg(&rank[ro + (t[j] - lo)]) << 3) | j) : TKEY_NONE;
-            nb += in;
+            ka[j] = ((ca >> j) & 1) ? (((int)__ldg(&rank[ro0 + (t[j] - lo0)]) << 3) | j) : TKEY_NONE;
+            kb[j] = ((cb >> j) & 1) ? (((int)__ldg(&rank[ro1 + (t[j] - lo1)]) << 3) | j) : TKEY_NONE;
         }
-        if (!nb) return false;
     }
     for (int ia = 0; ia < na; ia++) {                         /* :111 product order: first list slowest */
         const int ma = tkey_min8(ka);
@@ -749,11 +783,12 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int 
 __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const int t[8], const WarpSm &sm,
                                                  uint32_t &codes, uint32_t &s0f)
 {
-    if (pp->width != 2 || pp->key[0].len > 2) return 2;
+    if (pp->width != 2) return 2;
+    const bool long_start = pp->key[0].len > 2;               /* needs a warp-wide search: only pre-screen one / zero here */
     uint32_t acc = 0, hasf = 0;
     int s0 = 0;
 #pragma unroll 1
-    for (int kk = 0; kk < 4; kk++) {                          /* start (:67-88), then one / zero / float (:99-141) */
+    for (int kk = long_start ? 1 : 0; kk < 4; kk++) {         /* start (:67-88), then one / zero / float (:99-141) */
         const SdbKeyTpl *k = &pp->key[kk];
         if (!k->len) continue;
         uint32_t code = 0;
@@ -765,6 +800,16 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
         if (kk == 0) s0 = p;                                  /* D' = D[find(start):] */
         if (kk == 3) hasf = 1;
         acc |= code << (8 * kk);
+    }
+    if (long_start) return 2;                                 /* one / zero exist somewhere in D: worth the warp-level path */
+    /* a match needs regex_min consecutive symbols, all at positions of one parity: count them (necessary condition) */
+    {
+        const uint32_t c1 = (acc >> 8) & 0xFF, c0 = (acc >> 16) & 0xFF, cf = acc >> 24;
+        uint32_t cnt = sm.cnt2[(c1 & 15) * 10 + (c1 >> 4)];
+        if (pp->key[2].len && c0 != c1) cnt += sm.cnt2[(c0 & 15) * 10 + (c0 >> 4)];
+        if (hasf && cf != c1 && cf != c0) cnt += sm.cnt2[(cf & 15) * 10 + (cf >> 4)];
+        const int best = max((int)(cnt & 0xFFFF), (int)(cnt >> 16));
+        if (best < (int)pp->regex_min) return 0;
     }
     codes = acc;
     s0f = (uint32_t)s0 | (hasf << 16);
@@ -874,7 +919,7 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
 __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
 {
     const int lane = lane_id();
-    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; }
+    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; sm.cnt2[i] = 0; }
     if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
     stage_digits(A, sm, m, dlen, mi);
     /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
@@ -892,7 +937,11 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
         }
         if (vb) {
             int code = a * 10 + b;
-            if (lane == __ffs(gb) - 1 && sm.first2[code] == NONE32) sm.first2[code] = p;
+            if (lane == __ffs(gb) - 1) {
+                if (sm.first2[code] == NONE32) sm.first2[code] = p;
+                /* base is a multiple of 32, so lane parity == position parity */
+                sm.cnt2[code] += (uint32_t)__popc(gb & 0x55555555u) | ((uint32_t)__popc(gb & 0xAAAAAAAAu) << 16);
+            }
             if (lane == 31 - __clz(gb)) sm.last2[code] = p + 1;
         }
         __syncwarp();
@@ -1054,7 +1103,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
 #pragma unroll 1
             for (int idx = lane; idx < ncl * 8; idx += 32) {
                 int c = idx >> 3, j = idx & 7;
-                sm.T[c][j] = (int16_t)(j < npat ? tenths(sm.pat[j], __ldg(&A.tab.clk[c])) : -32768);
+                sm.T[c][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
             }
             __syncwarp();
             SdbSurv *slots = A.surv + (size_t)mi * n_mu;

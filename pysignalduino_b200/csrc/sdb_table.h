@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 4u
+#define SDB_TBL_VERSION 5u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -146,7 +146,7 @@ static_assert(sizeof(SdbTblHeader) == 80, "SdbTblHeader layout");
 typedef struct SdbDevTable {
     const SdbPulseProto *ms;    const SdbPrefilter *ms_pf;   uint32_t n_ms;
     const SdbPulseProto *mu;    const SdbPrefilter *mu_pf;   uint32_t n_mu;
-    const double        *clk;   uint32_t n_clk;
+    const double        *clk;   uint32_t n_clk;     /* clk[0..n_clk) clocks, clk[n_clk..2n_clk) = 10/clock */
     const uint16_t      *rank;
     const SdbMmItem     *mm;
     const SdbHexProto   *hex;   uint32_t nproto;

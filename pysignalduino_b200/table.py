@@ -30,7 +30,7 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 4
+TBL_VERSION = 5
 
 MAX_UNIQ = 4
 MAX_TPL = 14
@@ -456,7 +456,8 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
 
     ms_arr, mu_arr = arr(ms_rows, PULSEPROTO_DTYPE), arr(mu_rows, PULSEPROTO_DTYPE)
     ms_pf_arr, mu_pf_arr = arr(ms_pf, PREFILTER_DTYPE), arr(mu_pf, PREFILTER_DTYPE)
-    clk_arr = np.asarray(clocks, dtype="<f8")
+    # n_clk clocks followed by n_clk values of 10/clock (device fast path of round(p/clock, 1), exact path on near-ties)
+    clk_arr = np.asarray(clocks + [10.0 / c for c in clocks], dtype="<f8")
     rank_arr = np.asarray(pool.data, dtype="<u2")
     mm_arr = np.zeros(len(mm_items), dtype=MMITEM_DTYPE)
     for i, (mask, lo, hi) in enumerate(mm_items):
@@ -477,7 +478,7 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         return start
 
     hdr["magic"], hdr["version"], hdr["nproto"] = TBL_MAGIC, TBL_VERSION, len(ids)
-    hdr["n_ms"], hdr["n_mu"], hdr["n_clk"] = len(ms_arr), len(mu_arr), len(clk_arr)
+    hdr["n_ms"], hdr["n_mu"], hdr["n_clk"] = len(ms_arr), len(mu_arr), len(clocks)
     hdr["n_rank"], hdr["n_mm"] = len(rank_arr), len(mm_arr)
     hdr["off_ms"] = add(ms_arr)
     hdr["off_mu"] = add(mu_arr)
@@ -493,7 +494,7 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
     blob[: HEADER_DTYPE.itemsize] = hdr.tobytes()
     for start, b in sections:
         blob[start : start + len(b)] = b
-    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clk_arr), "n_rank": len(rank_arr),
+    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr),
             "n_mm_items": len(mm_arr), "bytes": total, "clocks": clocks}
     return CompiledTable(bytes(blob), ids, ms_ids, mu_ids, info)
 
