@@ -35,8 +35,15 @@ struct SdbHandle {
     uint8_t *d_unit = nullptr;          /* unit-op scratch */
     void *d_mu_scratch = nullptr;       /* MU survivor slots (resolve kernel -> scan kernel), allocated on first MU call */
     uint32_t mu_chunk = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      /* compute + final copies of the host-buffer path */
+    cudaStream_t copy_stream = nullptr; /* pipelined H2D */
+    cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
+    std::vector<cudaEvent_t> ev_h2d, ev_done;
 };
+
+static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                         uint32_t msg_base, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                         uint32_t *d_bits, uint32_t bits_cap, SdbCounters *d_counters, cudaStream_t st);
 
 static thread_local std::string g_create_err;
 
@@ -80,6 +87,8 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     CKC(cudaMalloc(&h->d_ctr, sizeof(SdbCounters)));
     CKC(cudaMalloc(&h->d_unit, 16384));
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     const uint8_t *b = h->d_blob;
     h->tab.ms = reinterpret_cast<const SdbPulseProto *>(b + hd->off_ms);
     h->tab.mu = reinterpret_cast<const SdbPulseProto *>(b + hd->off_mu);
@@ -105,7 +114,11 @@ extern "C" void sdb_destroy(SdbHandle *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
+    for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
 }
 
@@ -120,6 +133,14 @@ extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
     if (n && (!d_msgs || !d_digits || !d_out || !d_counters)) return set_err(h, SDB_E_ARG, "sdb_demod_pulse_device: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
+    return enqueue_pulse(h, kind, d_msgs, d_digits, n, 0, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, st);
+}
+
+/* Enqueue the kernels for messages [0, n) at d_msgs whose batch indices start at msg_base; counters are NOT reset. */
+static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                         uint32_t msg_base, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
+                         uint32_t *d_bits, uint32_t bits_cap, SdbCounters *d_counters, cudaStream_t st)
+{
     int grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
     if (kind == SDB_KIND_MU && n) {
         /* scratch is sized for the worst case (every protocol of every message survives), once per handle */
@@ -134,7 +155,7 @@ extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
         }
     }
     int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid,
-                               h->d_mu_scratch, h->mu_chunk, st);
+                               h->d_mu_scratch, h->mu_chunk, msg_base, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "pulse kernel launch", static_cast<cudaError_t>(rc));
     return SDB_OK;
 }
@@ -191,18 +212,56 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
     if ((rc = grow(h, h->d_hits, h->cap_hits, sizeof(SdbHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
     if ((rc = grow(h, h->d_bits, h->cap_bits, sizeof(uint32_t) * (size_t)(bits_cap ? bits_cap : 1)))) return rc;
     cudaStream_t st = h->stream;
-    CK(cudaMemcpyAsync(h->d_msgs, msgs, rec * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_digits, digits, digits_len, cudaMemcpyHostToDevice, st));
-    if (pulse)
-        rc = sdb_demod_pulse_device(h, kind, static_cast<const SdbPulseMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
-                                    h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
-    else
-        rc = sdb_demod_hex_device(h, kind, mc_repaired, static_cast<const SdbHexMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
-                                  h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
-    if (rc != SDB_OK) return rc;
-    CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const SdbPulseMsg *pm = static_cast<const SdbPulseMsg *>(msgs);
+    /* Pipelined path (MS / MU, several chunks): the H2D copy of chunk k+1 and the D2H copy of the result slots of
+     * chunk k-1 overlap the kernels of chunk k.  Needs the digit streams stored in message order (doff non-decreasing),
+     * which is what pack.py and the corpus generator produce; checked at the chunk boundaries. */
+    const uint32_t C = SDB_MU_CHUNK;
+    bool pipelined = pulse && n > C;
+    if (pipelined)
+        for (uint32_t b = C; b < n; b += C)
+            if (pm[b].doff < pm[b - 1].doff || (size_t)pm[b].doff * 16 > digits_len) { pipelined = false; break; }
+    if (pipelined) {
+        const uint32_t nchunks = (n + C - 1) / C;
+        while (h->ev_h2d.size() < nchunks) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            h->ev_h2d.push_back(a); h->ev_done.push_back(b);
+        }
+        SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
+        CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));
+        for (uint32_t k = 0; k < nchunks; k++) {
+            const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
+            const size_t dlo = (size_t)pm[lo].doff * 16;
+            const size_t dhi = k + 1 < nchunks ? (size_t)pm[lo + cnt].doff * 16 : digits_len;
+            CK(cudaMemcpyAsync(dm + lo, pm + lo, sizeof(SdbPulseMsg) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
+            if (dhi > dlo) CK(cudaMemcpyAsync(h->d_digits + dlo, digits + dlo, dhi - dlo, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->ev_h2d[k], h->copy_stream));
+            CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
+            rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+            if (rc != SDB_OK) return rc;
+            CK(cudaEventRecord(h->ev_done[k], st));
+            CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
+            CK(cudaMemcpyAsync(out + lo, h->d_out + lo, sizeof(SdbMsgOut) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
+        CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(h->d2h_stream));
+    } else {
+        CK(cudaMemcpyAsync(h->d_msgs, msgs, rec * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_digits, digits, digits_len, cudaMemcpyHostToDevice, st));
+        if (pulse)
+            rc = sdb_demod_pulse_device(h, kind, static_cast<const SdbPulseMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
+                                        h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+        else
+            rc = sdb_demod_hex_device(h, kind, mc_repaired, static_cast<const SdbHexMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
+                                      h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+        if (rc != SDB_OK) return rc;
+        CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
     if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
     if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));

@@ -1271,10 +1271,10 @@ int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, cudaStream_t stream)
+                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream)
 {
     KArgs A;
-    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = 0; A.out = d_out;
+    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
     A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
     A.surv = nullptr; A.surv_cnt = nullptr;
     if (n == 0) return 0;
@@ -1288,7 +1288,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     A.surv = static_cast<SdbSurv *>(mu_scratch);
     A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * tab.n_mu * sizeof(SdbSurv));
     for (uint32_t off = 0; off < n; off += mu_chunk) {
-        A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = off;
+        A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;

@@ -15,7 +15,7 @@ namespace sdb {
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, cudaStream_t stream);
+                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream);
 int pulse_blocks_per_sm(int kind);
 size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots handed from mu_resolve_kernel to mu_scan_kernel */
 
