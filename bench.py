@@ -39,6 +39,24 @@ METRIC = "messages demodulated/sec x all protocols (bit-exact)"
 UNIT = "messages/s"
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Library banners (e.g. "NCCL version ...") must not pollute stdout: route fd 1 to stderr and keep the
+    real stdout for the ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def shard_counts(m: int):
     c = [int(m * f) for _, _, f in MIX]
     c[0] += m - sum(c)
@@ -160,7 +178,7 @@ def run_reference(args):
         "note": "reference arm = C oracle port of the reference's Python path (the Python reference cannot travel to the GPU box); "
                 "survey-time probe of the real Python reference: ~1.7k MS msg/s/core, ~450 MU msg/s/core",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -374,7 +392,7 @@ def run_ours(args):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "per_kernel": per_kernel,
         "corpus_gen_s": t_gen,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -390,6 +408,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
