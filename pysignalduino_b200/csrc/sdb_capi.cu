@@ -69,6 +69,7 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     if (hd->magic != SDB_TBL_MAGIC || hd->version != SDB_TBL_VERSION || hd->total != blob_len)
         return set_err(nullptr, SDB_E_ARG, "sdb_create: not a protocol table blob of this version");
     if (hd->n_clk > SDB_MAX_CLK) return set_err(nullptr, SDB_E_ARG, "sdb_create: too many distinct clocks");
+    if (hd->n_vals > SDB_MAX_VALS) return set_err(nullptr, SDB_E_ARG, "sdb_create: too many distinct (clock, interval) pairs");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) return set_err(nullptr, SDB_E_NOGPU, "sdb_create: no CUDA device (there is no CPU fallback)", ce);
@@ -96,6 +97,8 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     h->tab.mu_pf = reinterpret_cast<const SdbPrefilter *>(b + hd->off_mu_pf);
     h->tab.clk = reinterpret_cast<const double *>(b + hd->off_clk);
     h->tab.rank = reinterpret_cast<const uint16_t *>(b + hd->off_rank);
+    h->tab.vals = reinterpret_cast<const SdbValRow *>(b + hd->off_vals);
+    h->tab.n_vals = hd->n_vals;
     h->tab.mm = reinterpret_cast<const SdbMmItem *>(b + hd->off_mm);
     h->tab.hex = reinterpret_cast<const SdbHexProto *>(b + hd->off_hex);
     h->tab.n_ms = hd->n_ms; h->tab.n_mu = hd->n_mu; h->tab.n_clk = hd->n_clk; h->tab.nproto = hd->nproto;

@@ -78,6 +78,7 @@ struct __align__(16) WarpSm {
     uint32_t first1[12], last1[12];   /* digit a                                             */
     uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
     int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
+    uint8_t  M[SDB_MAX_VALS];         /* MU: candidate-slot mask per (clock, interval) pair  */
     int32_t  pat[8];
     uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
     uint32_t fpl[BIT_WORDS];          /* 'F' plane                                           */
@@ -697,21 +698,14 @@ __device__ __forceinline__ int tkey_min8(const int k[8])
     int m = min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
     return m;
 }
-__device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int t[8], const WarpSm &sm, int from,
+__device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_idx, const WarpSm &sm, int from,
                                      uint32_t &code, int &pos)
 {
     const int L = k->len, K = k->nuniq;
     const uint32_t uidx = k->uidx, ids = sm.pat_ids;
-    const uint16_t *__restrict__ rank = sm.rank;
-    /* candidate slots of the (<= 2) distinct values; empty slots hold -32768 and never qualify (:73-76) */
-    const int lo0 = k->lo[0], hi0 = k->hi[0];
-    const int lo1 = K > 1 ? k->lo[1] : 1, hi1 = K > 1 ? k->hi[1] : 0;
-    uint32_t ca = 0, cb = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        ca |= (uint32_t)(t[j] >= lo0 && t[j] <= hi0) << j;
-        cb |= (uint32_t)(t[j] >= lo1 && t[j] <= hi1) << j;
-    }
+    /* candidate slots of the (<= 2) distinct values (:73-76): looked up in the per-message mask table */
+    const uint32_t ca = sm.M[k->vidx[0]];
+    const uint32_t cb = K > 1 ? sm.M[k->vidx[1]] : 0u;
     if (!ca || (K > 1 && !cb)) return false;                  /* :78-80 */
     if (!(ca & (ca - 1)) && !(cb & (cb - 1))) {
         /* the common case: one candidate per value -> a single combination, no ordering needed */
@@ -733,14 +727,19 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int 
         }
         return true;
     }
+    /* several candidates for some value: order them by (gap rank, slot) */
     int ka[8], kb[8];
     const int na = __popc(ca), nb = __popc(cb);
     {
+        const uint16_t *__restrict__ rank = sm.rank;
+        const int lo0 = k->lo[0], lo1 = K > 1 ? k->lo[1] : 0;
         const uint32_t ro0 = k->rank_off[0], ro1 = K > 1 ? k->rank_off[1] : 0;
+        const int16_t *trow = sm.T[clk_idx];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            ka[j] = ((ca >> j) & 1) ? (((int)__ldg(&rank[ro0 + (t[j] - lo0)]) << 3) | j) : TKEY_NONE;
-            kb[j] = ((cb >> j) & 1) ? (((int)__ldg(&rank[ro1 + (t[j] - lo1)]) << 3) | j) : TKEY_NONE;
+            const int tj = trow[j];
+            ka[j] = ((ca >> j) & 1) ? (((int)__ldg(&rank[ro0 + (tj - lo0)]) << 3) | j) : TKEY_NONE;
+            kb[j] = ((cb >> j) & 1) ? (((int)__ldg(&rank[ro1 + (tj - lo1)]) << 3) | j) : TKEY_NONE;
         }
     }
     for (int ia = 0; ia < na; ia++) {                         /* :111 product order: first list slowest */
@@ -780,10 +779,11 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, const int 
 /* Thread-level resolution of one MU protocol (2-digit symbols, start of <= 2 pulses).
  * Returns 0 dead, 1 resolved (codes = start | one<<8 | zero<<16 | float<<24, s0f = s0 | hasf<<16),
  * 2 = needs the warp-level path. */
-__device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const int t[8], const WarpSm &sm,
+__device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
                                                  uint32_t &codes, uint32_t &s0f)
 {
     if (pp->width != 2) return 2;
+    const int clk_idx = pp->clk_idx;
     const bool long_start = pp->key[0].len > 2;               /* needs a warp-wide search: only pre-screen one / zero here */
     uint32_t acc = 0, hasf = 0;
     int s0 = 0;
@@ -793,7 +793,7 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
         if (!k->len) continue;
         uint32_t code = 0;
         int p = 0;
-        if (!tres(k, t, sm, kk == 0 ? 0 : s0, code, p)) {
+        if (!tres(k, clk_idx, sm, kk == 0 ? 0 : s0, code, p)) {
             if (kk == 3) break;                               /* float is optional (:138) */
             return 0;
         }
@@ -1106,6 +1106,22 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
                 sm.T[c][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
             }
             __syncwarp();
+            /* candidate-slot mask of every distinct (clock, accept interval) pair of the table: one lane per pair */
+            const int nv = A.tab.n_vals;
+#pragma unroll 1
+            for (int v = lane; v < nv; v += 32) {
+                const SdbValRow vr = A.tab.vals[v];
+                const int4 row = *reinterpret_cast<const int4 *>(&sm.T[vr.clk_idx][0]);
+                const int lo = vr.lo, hi = vr.hi;
+                int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
+                int t4 = (int16_t)(row.z & 0xffff), t5 = row.z >> 16, t6 = (int16_t)(row.w & 0xffff), t7 = row.w >> 16;
+                uint32_t mk = (uint32_t)(t0 >= lo && t0 <= hi) | ((uint32_t)(t1 >= lo && t1 <= hi) << 1) |
+                              ((uint32_t)(t2 >= lo && t2 <= hi) << 2) | ((uint32_t)(t3 >= lo && t3 <= hi) << 3) |
+                              ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
+                              ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
+                sm.M[v] = (uint8_t)mk;                            /* empty slots hold -32768 and never qualify */
+            }
+            __syncwarp();
             SdbSurv *slots = A.surv + (size_t)mi * n_mu;
 #pragma unroll 1
             for (uint32_t q0 = 0; q0 < n_mu; q0 += 32) {
@@ -1113,21 +1129,12 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
                 int state = 0;
                 SdbSurv rec;
                 rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
-                if (q < n_mu) {
-                    const SdbPrefilter *pf = &A.tab.mu_pf[q];
-                    const int4 row = *reinterpret_cast<const int4 *>(&sm.T[pf->clk_idx][0]);
-                    int t[8];
-                    t[0] = (int16_t)(row.x & 0xffff); t[1] = row.x >> 16;
-                    t[2] = (int16_t)(row.y & 0xffff); t[3] = row.y >> 16;
-                    t[4] = (int16_t)(row.z & 0xffff); t[5] = row.z >> 16;
-                    t[6] = (int16_t)(row.w & 0xffff); t[7] = row.w >> 16;
-                    if (prefilter_ok(pf, t)) {                    /* exact template resolution, one lane per protocol */
-                        uint32_t codes = 0, s0f = 0;
-                        state = thread_resolve_mu(&A.tab.mu[q], t, sm, codes, s0f);
-                        rec.start = codes & 0xFF;
-                        rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
-                        rec.meta = (uint16_t)((s0f & 0x7FF) | ((s0f >> 16) ? 0x800 : 0));
-                    }
+                if (q < n_mu) {                                   /* exact template resolution, one lane per protocol */
+                    uint32_t codes = 0, s0f = 0;
+                    state = thread_resolve_mu(&A.tab.mu[q], sm, codes, s0f);
+                    rec.start = codes & 0xFF;
+                    rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
+                    rec.meta = (uint16_t)((s0f & 0x7FF) | ((s0f >> 16) ? 0x800 : 0));
                 }
                 /* the few protocols that need warp-wide searches are resolved one after the other */
                 uint32_t cx = __ballot_sync(FULL, state == 2);

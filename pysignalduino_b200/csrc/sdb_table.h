@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 5u
+#define SDB_TBL_VERSION 6u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -67,7 +67,7 @@
 #define SDB_HF_MAX_IS_STR 0x20
 #define SDB_HF_IS_119     0x40
 
-/* One pulse template (sync / start / one / zero / float), 40 bytes. */
+/* One pulse template (sync / start / one / zero / float), 48 bytes. */
 typedef struct SdbKeyTpl {
     uint8_t  len;                     /* pulses in the template, 0 = key absent                     */
     uint8_t  nuniq;                   /* distinct values, first-appearance order                    */
@@ -76,9 +76,19 @@ typedef struct SdbKeyTpl {
     int16_t  lo[SDB_MAX_UNIQ];        /* accepted tenths interval of each distinct value            */
     int16_t  hi[SDB_MAX_UNIQ];
     uint32_t rank_off[SDB_MAX_UNIQ];  /* gap-rank table slice: rank[rank_off + (t - lo)]            */
+    uint16_t vidx[SDB_MAX_UNIQ];      /* MU: row of (clock, interval) in SdbValRow[] = slot of the per-message candidate mask */
 } SdbKeyTpl;
 
-/* One MS or MU protocol, 216 bytes. key[0] = sync (MS) / start (MU), [1] one, [2] zero, [3] float. */
+/* One distinct (clock, accept interval) pair of the MU table: the resolve kernel computes, once per message,
+ * the 8-bit mask of pattern slots whose tenths value lies inside it. */
+typedef struct SdbValRow {
+    uint16_t clk_idx;
+    int16_t  lo, hi;
+    uint16_t rsv;
+} SdbValRow;
+#define SDB_MAX_VALS 512
+
+/* One MS or MU protocol, 248 bytes. key[0] = sync (MS) / start (MU), [1] one, [2] zero, [3] float. */
 typedef struct SdbPulseProto {
     SdbKeyTpl key[4];
     double   clock;                   /* MS: clockabs for the 30 % gate (0 = no gate); MU: clockabs */
@@ -130,12 +140,14 @@ typedef struct SdbTblHeader {
     uint32_t n_ms, n_mu, n_clk, n_rank, n_mm;
     uint32_t off_ms, off_mu, off_ms_pf, off_mu_pf, off_clk, off_rank, off_mm, off_hex;
     uint32_t total;
-    uint32_t rsv[3];
+    uint32_t n_vals, off_vals;
+    uint32_t rsv;
 } SdbTblHeader;
 
 #ifdef __cplusplus
-static_assert(sizeof(SdbKeyTpl) == 40, "SdbKeyTpl layout");
-static_assert(sizeof(SdbPulseProto) == 216, "SdbPulseProto layout");
+static_assert(sizeof(SdbKeyTpl) == 48, "SdbKeyTpl layout");
+static_assert(sizeof(SdbValRow) == 8, "SdbValRow layout");
+static_assert(sizeof(SdbPulseProto) == 248, "SdbPulseProto layout");
 static_assert(sizeof(SdbPrefilter) == 52, "SdbPrefilter layout");
 static_assert(sizeof(SdbMmItem) == 20, "SdbMmItem layout");
 static_assert(sizeof(SdbHexProto) == 36, "SdbHexProto layout");
@@ -148,6 +160,7 @@ typedef struct SdbDevTable {
     const SdbPulseProto *mu;    const SdbPrefilter *mu_pf;   uint32_t n_mu;
     const double        *clk;   uint32_t n_clk;     /* clk[0..n_clk) clocks, clk[n_clk..2n_clk) = 10/clock */
     const uint16_t      *rank;
+    const SdbValRow     *vals;  uint32_t n_vals;
     const SdbMmItem     *mm;
     const SdbHexProto   *hex;   uint32_t nproto;
 } SdbDevTable;

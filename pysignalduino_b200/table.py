@@ -30,7 +30,7 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 5
+TBL_VERSION = 6
 
 MAX_UNIQ = 4
 MAX_TPL = 14
@@ -64,9 +64,10 @@ KEYTPL_DTYPE = np.dtype(
         ("uidx", "<u4"),
         ("lo", "<i2", (MAX_UNIQ,)), ("hi", "<i2", (MAX_UNIQ,)),
         ("rank_off", "<u4", (MAX_UNIQ,)),
+        ("vidx", "<u2", (MAX_UNIQ,)),          # MU: slot of (clock, interval) in the per-message candidate-mask table
     ]
 )
-assert KEYTPL_DTYPE.itemsize == 40
+assert KEYTPL_DTYPE.itemsize == 48
 
 PULSEPROTO_DTYPE = np.dtype(
     [
@@ -80,12 +81,16 @@ PULSEPROTO_DTYPE = np.dtype(
         ("mm_nitems", "u1"), ("rsv", "u1", (7,)),
     ]
 )
-assert PULSEPROTO_DTYPE.itemsize == 216, PULSEPROTO_DTYPE.itemsize
+assert PULSEPROTO_DTYPE.itemsize == 248, PULSEPROTO_DTYPE.itemsize
 
 PREFILTER_DTYPE = np.dtype(
     [("clk_idx", "<u2"), ("nreq", "<u2"), ("lo", "<i2", (MAX_REQ,)), ("hi", "<i2", (MAX_REQ,))]
 )
 assert PREFILTER_DTYPE.itemsize == 52
+
+VALROW_DTYPE = np.dtype([("clk_idx", "<u2"), ("lo", "<i2"), ("hi", "<i2"), ("rsv", "<u2")])
+assert VALROW_DTYPE.itemsize == 8
+MAX_VALS = 512
 
 MMITEM_DTYPE = np.dtype([("mask", "<u4", (4,)), ("min", "<u2"), ("max", "<u2")])
 assert MMITEM_DTYPE.itemsize == 20
@@ -113,7 +118,7 @@ HEADER_DTYPE = np.dtype(
         ("n_ms", "<u4"), ("n_mu", "<u4"), ("n_clk", "<u4"), ("n_rank", "<u4"), ("n_mm", "<u4"),
         ("off_ms", "<u4"), ("off_mu", "<u4"), ("off_ms_pf", "<u4"), ("off_mu_pf", "<u4"),
         ("off_clk", "<u4"), ("off_rank", "<u4"), ("off_mm", "<u4"), ("off_hex", "<u4"),
-        ("total", "<u4"), ("rsv", "<u4", (3,)),
+        ("total", "<u4"), ("n_vals", "<u4"), ("off_vals", "<u4"), ("rsv", "<u4"),
     ]
 )
 assert HEADER_DTYPE.itemsize == 80
@@ -368,6 +373,7 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
 
     # ---------------- MU: get_keys('clockabs') + active (message_unsynced.py:45-49) ----------------
     mu_rows, mu_pf, mu_ids, clocks = [], [], [], []
+    mu_vals: Dict[Tuple[int, int, int], int] = {}
     for idx, (pid, pr) in enumerate(protocols.items()):
         if "clockabs" not in pr:
             continue
@@ -405,6 +411,13 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
                 items[-1] = (mask, lo, lo)
                 if lo == 0:
                     items.pop()
+            merged: List[Tuple[int, int, int]] = []
+            for it in items:                           # "......" -> one atom with count 6 (fixed-count atoms only)
+                if merged and merged[-1][0] == it[0] and merged[-1][1] == merged[-1][2] and it[1] == it[2]:
+                    merged[-1] = (it[0], merged[-1][1] + it[1], merged[-1][2] + it[2])
+                else:
+                    merged.append(it)
+            items = merged
             if never:
                 rec["flags"] |= PF_MM_NEVER
             elif items or end:
@@ -413,6 +426,14 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
                 mm_items.extend(items)
                 if end:
                     rec["flags"] |= PF_MM_END
+        # every (clock, accept interval) pair gets one slot of the per-message candidate-mask table
+        for kk in range(4):
+            kt = rec["key"][kk]
+            for u in range(int(kt["nuniq"])):
+                vkey = (int(rec["clk_idx"]), int(kt["lo"][u]), int(kt["hi"][u]))
+                if vkey not in mu_vals:
+                    mu_vals[vkey] = len(mu_vals)
+                kt["vidx"][u] = mu_vals[vkey]
         mu_rows.append(rec)
         mu_pf.append(_prefilter(rec, keys=(0, 1, 2)))
         mu_ids.append(pid)
@@ -488,13 +509,20 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
     hdr["off_rank"] = add(rank_arr)
     hdr["off_mm"] = add(mm_arr)
     hdr["off_hex"] = add(hexrows)
+    if len(mu_vals) > MAX_VALS:
+        raise NotImplementedError(f"{len(mu_vals)} distinct (clock, interval) pairs (max {MAX_VALS})")
+    val_arr = np.zeros(len(mu_vals), dtype=VALROW_DTYPE)
+    for (ck, lo, hi), i in mu_vals.items():
+        val_arr[i] = (ck, lo, hi, 0)
+    hdr["n_vals"] = len(val_arr)
+    hdr["off_vals"] = add(val_arr)
     total = (off + 15) // 16 * 16
     hdr["total"] = total
     blob = bytearray(total)
     blob[: HEADER_DTYPE.itemsize] = hdr.tobytes()
     for start, b in sections:
         blob[start : start + len(b)] = b
-    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr),
+    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr), "n_vals": len(mu_vals),
             "n_mm_items": len(mm_arr), "bytes": total, "clocks": clocks}
     return CompiledTable(bytes(blob), ids, ms_ids, mu_ids, info)
 
