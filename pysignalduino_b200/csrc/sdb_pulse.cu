@@ -402,6 +402,12 @@ __device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmIte
         int mn = m->min, mx = m->max;
         int cnt = 0;
         int lim = (end && it == n - 1) ? mx : mn;
+        if (m->mask[0] == 0xFFFFFBFFu && (m->mask[1] & m->mask[2] & m->mask[3]) == 0xFFFFFFFFu) {
+            cnt = min(lim, total - pos);          /* '.': the payload never contains a newline, only the length matters */
+            pos += cnt;
+            if (cnt < mn) return false;
+            continue;
+        }
         while (cnt < lim && pos < total) {
             int c = payload_char(P, pos);
             if (c < 0 || c >= 128 || !((m->mask[c >> 5] >> (c & 31)) & 1)) break;
@@ -604,16 +610,22 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
             }
         }
     }
-    /* R[p] = B[p] & B[p+w] & ... (MIN terms), by binary doubling */
     const int MIN = pp->regex_min;
-    uint32_t R = FULL, Acc = myB;
-    int rl = 0, al = 1;
-    #pragma unroll 1
-    for (int m = MIN; m > 0; m >>= 1) {
-        if (m & 1) { R &= rl ? shr_dist(Acc, rl * w) : Acc; rl += al; }
-        if (m > 1) { Acc &= shr_dist(Acc, al * w); al <<= 1; }
+    /* Candidate match positions.  With a start string that occurs only a few times, every occurrence is simply
+     * tried in turn (the run length is needed anyway); otherwise R[p] = B[p] & B[p+w] & ... (MIN terms) is built by
+     * binary doubling so that the leftmost feasible position is one find-first-set away. */
+    const bool direct = Ls && __reduce_add_sync(FULL, __popc(myS)) <= 8u;
+    uint32_t myC = myS;
+    if (!direct) {
+        uint32_t R = FULL, Acc = myB;
+        int rl = 0, al = 1;
+        #pragma unroll 1
+        for (int m = MIN; m > 0; m >>= 1) {
+            if (m & 1) { R &= rl ? shr_dist(Acc, rl * w) : Acc; rl += al; }
+            if (m > 1) { Acc &= shr_dist(Acc, al * w); al <<= 1; }
+        }
+        myC = myS & (Ls ? shr_dist(R, Ls) : R);
     }
-    const uint32_t myC = myS & (Ls ? shr_dist(R, Ls) : R);
 
     /* re.finditer (:192): leftmost match from pos, then continue at its end */
     int pos = s0, ordinal = 0;
@@ -625,6 +637,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
         uint32_t cls = w == 1 ? FULL : (w == 2 ? 0x55555555u << (p & 1) : 0x11111111u << (p & 3));
         int ns = first_set_from(~myB & cls, p);
         int n = ns >= 0 ? (ns - p) / w : (SDB_MAX_DIGITS - p + w - 1) / w;
+        if (direct && n < MIN) { pos = i + 1; continue; }   /* {MIN,} not met here: the regex retries one position later */
         int end = p + n * w;
         int tail = -1;                             /* 0/1/2 = bit '1'/'0'/'F' of the reconstructed chunk */
         if (use_tail) {
