@@ -830,28 +830,71 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
 }
 
 /* ---- one (message x MS protocol) task: message_synced.py:90-241 ----------------------------- */
+/* Thread-level resolution of one MS protocol (2-digit symbols, sync of <= 2 pulses): message_synced.py:109-163.
+ * Returns 0 dead, 1 resolved (codes = sync | one<<8 | zero<<16 | float<<24, msf = message_start | hasf<<16),
+ * 2 = needs the warp-level path.  Every pattern_exists call of MS searches the whole D (from = 0). */
+__device__ __forceinline__ int thread_resolve_ms(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
+                                                 uint32_t &codes, uint32_t &msf)
+{
+    if (pp->width != 2 || pp->key[0].len > 2) return 2;
+    uint32_t acc = 0, hasf = 0;
+    int spos = 0;
+#pragma unroll 1
+    for (int kk = 0; kk < 4; kk++) {                          /* sync, one, zero, float (:109) */
+        const SdbKeyTpl *k = &pp->key[kk];
+        if (!k->len) continue;
+        uint32_t code = 0;
+        int p = 0;
+        if (!tres(k, 0, sm, 0, code, p)) {
+            if (kk == 3) break;                               /* :160-163 float may be missing */
+            return 0;
+        }
+        if (kk == 0) {                                        /* :140-156 */
+            spos = p + k->len;
+            if ((int)pp->regex_min * 2 > sm.dlen - spos) return 0;
+        }
+        if (kk == 3) hasf = 1;
+        acc |= code << (8 * kk);
+    }
+    codes = acc;
+    msf = (uint32_t)spos | (hasf << 16);
+    return 1;
+}
+
+__device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
+                                    uint32_t cf, bool hasf);
+
+/* warp-level resolution for the MS protocols with 4-digit symbols or a 4-pulse sync, then the chunk loop */
 __device__ __noinline__ int decode_ms(const KArgs &A, const SdbPulseProto *pp, int t_slot)
 {
     WarpSm &sm = SM();
-    const int lane = lane_id();
-    const int dlen = sm.dlen;
     const int w = pp->width;
-    const int flags = pp->flags;
     uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
     int spos = 0, dummy;
     const int Lsy = pp->key[0].len;
     /* sync, then length_min against the digits left after it (:140-156) */
     if (!resolve_key(&pp->key[0], t_slot, 0, true, ts, spos)) return SDB_ST_OK;
     const int ms = spos + Lsy;
-    if ((int)pp->regex_min * w > dlen - ms) return SDB_ST_OK;   /* length_min > (len - start) / width */
+    if ((int)pp->regex_min * w > sm.dlen - ms) return SDB_ST_OK;   /* length_min > (len - start) / width */
     if (!resolve_key(&pp->key[1], t_slot, 0, false, t1, dummy)) return SDB_ST_OK;
-    const bool has0 = pp->key[2].len != 0;
     bool hasf = false;
-    if (has0 && !resolve_key(&pp->key[2], t_slot, 0, false, t0, dummy)) return SDB_ST_OK;
+    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, 0, false, t0, dummy)) return SDB_ST_OK;
     if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, 0, false, tf, dummy);
+    return scan_ms(A, pp, ms, (uint32_t)ts, (uint32_t)t1, (uint32_t)t0, (uint32_t)tf, hasf);
+}
 
+/* the chunk loop of one resolved (message x MS protocol) task: message_synced.py:171-241 */
+__device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
+                                    uint32_t cf, bool hasf)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const int dlen = sm.dlen;
+    const int w = pp->width;
+    const int flags = pp->flags;
+    const int Lsy = pp->key[0].len;
+    const bool has0 = pp->key[2].len != 0;
     const uint32_t wm = nibmask32(w), em = nibmask32(w - 1), sm_ = nibmask32(Lsy);
-    const uint32_t c1 = (uint32_t)t1, c0 = (uint32_t)t0, cf = (uint32_t)tf, cs = (uint32_t)ts;
     const bool recon = (flags & SDB_PF_RECONSTRUCT) != 0;
 
     /* chunk loop (:174-189): class per chunk = '1' / '0' / 'F' / skip (sync string) / stop */
@@ -990,26 +1033,40 @@ __device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
         const int pc = sm.pat[cp];
         if (pc == 0) return SDB_ST_OK;                           /* :65-66 */
         const double clock_abs = fabs((double)pc);
-        int t[8];
+        /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
+        const int t_slot = (lane & 7) < npat ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
+        if (lane < 8) sm.T[0][lane] = (int16_t)t_slot;
+        __syncwarp();
+        /* candidate-slot masks of the MS intervals (they follow the MU pairs in the value table) */
+        for (int v = A.tab.n_mu_vals + lane; v < (int)A.tab.n_vals; v += 32) {
+            const SdbValRow vr = A.tab.vals[v];
+            uint32_t mk = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) t[j] = j < npat ? tenths(sm.pat[j], clock_abs) : -32768;   /* :70-72 */
-        int t_slot = t[0];
-#pragma unroll
-        for (int j = 1; j < 8; j++) if ((lane & 7) == j) t_slot = t[j];
+            for (int j = 0; j < 8; j++) { const int tj = sm.T[0][j]; mk |= (uint32_t)(tj >= vr.lo && tj <= vr.hi) << j; }
+            sm.M[v] = (uint8_t)mk;
+        }
+        __syncwarp();
         const uint32_t n = A.tab.n_ms;
+#pragma unroll 1
         for (uint32_t q0 = 0; q0 < n; q0 += 32) {
-            uint32_t q = q0 + lane;
-            bool alive = false;
+            const uint32_t q = q0 + lane;
+            int state = 0;
+            uint32_t codes = 0, msf = 0;
             if (q < n) {
-                double pclk = A.tab.ms[q].clock;                  /* :83-88 */
-                bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
-                alive = !gate && prefilter_ok(&A.tab.ms_pf[q], t);
+                const SdbPulseProto *pq = &A.tab.ms[q];
+                const double pclk = pq->clock;                    /* :83-88 */
+                const bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
+                if (!gate) state = thread_resolve_ms(pq, sm, codes, msf);   /* one lane per protocol */
             }
-            uint32_t surv = __ballot_sync(FULL, alive);
-            while (surv) {
-                int b = __ffs(surv) - 1;
+            uint32_t surv = __ballot_sync(FULL, state != 0);
+            while (surv) {                                        /* protocol-table order */
+                const int b = __ffs(surv) - 1;
                 surv &= surv - 1;
-                status = decode_ms(A, &A.tab.ms[q0 + b], t_slot);
+                const int st_b = __shfl_sync(FULL, state, b);
+                const uint32_t cd = __shfl_sync(FULL, codes, b), mf = __shfl_sync(FULL, msf, b);
+                const SdbPulseProto *pp = &A.tab.ms[q0 + b];
+                if (st_b == 2) status = decode_ms(A, pp, t_slot);
+                else status = scan_ms(A, pp, (int)(mf & 0xFFFF), cd & 0xFF, (cd >> 8) & 0xFF, (cd >> 16) & 0xFF, cd >> 24, (mf >> 16) != 0);
                 if (status != SDB_ST_OK) return status;
             }
         }
@@ -1120,7 +1177,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
             }
             __syncwarp();
             /* candidate-slot mask of every distinct (clock, accept interval) pair of the table: one lane per pair */
-            const int nv = A.tab.n_vals;
+            const int nv = A.tab.n_mu_vals;
 #pragma unroll 1
             for (int v = lane; v < nv; v += 32) {
                 const SdbValRow vr = A.tab.vals[v];

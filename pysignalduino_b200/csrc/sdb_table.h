@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 6u
+#define SDB_TBL_VERSION 7u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -140,8 +140,8 @@ typedef struct SdbTblHeader {
     uint32_t n_ms, n_mu, n_clk, n_rank, n_mm;
     uint32_t off_ms, off_mu, off_ms_pf, off_mu_pf, off_clk, off_rank, off_mm, off_hex;
     uint32_t total;
-    uint32_t n_vals, off_vals;
-    uint32_t rsv;
+    uint32_t n_vals, off_vals;   /* SdbValRow[]: MU pairs first, then the MS intervals (clock slot 0) */
+    uint32_t n_mu_vals;
 } SdbTblHeader;
 
 #ifdef __cplusplus
@@ -160,7 +160,7 @@ typedef struct SdbDevTable {
     const SdbPulseProto *mu;    const SdbPrefilter *mu_pf;   uint32_t n_mu;
     const double        *clk;   uint32_t n_clk;     /* clk[0..n_clk) clocks, clk[n_clk..2n_clk) = 10/clock */
     const uint16_t      *rank;
-    const SdbValRow     *vals;  uint32_t n_vals;
+    const SdbValRow     *vals;  uint32_t n_vals, n_mu_vals;
     const SdbMmItem     *mm;
     const SdbHexProto   *hex;   uint32_t nproto;
 } SdbDevTable;

@@ -30,7 +30,7 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 6
+TBL_VERSION = 7
 
 MAX_UNIQ = 4
 MAX_TPL = 14
@@ -118,7 +118,7 @@ HEADER_DTYPE = np.dtype(
         ("n_ms", "<u4"), ("n_mu", "<u4"), ("n_clk", "<u4"), ("n_rank", "<u4"), ("n_mm", "<u4"),
         ("off_ms", "<u4"), ("off_mu", "<u4"), ("off_ms_pf", "<u4"), ("off_mu_pf", "<u4"),
         ("off_clk", "<u4"), ("off_rank", "<u4"), ("off_mm", "<u4"), ("off_hex", "<u4"),
-        ("total", "<u4"), ("n_vals", "<u4"), ("off_vals", "<u4"), ("rsv", "<u4"),
+        ("total", "<u4"), ("n_vals", "<u4"), ("off_vals", "<u4"), ("n_mu_vals", "<u4"),
     ]
 )
 assert HEADER_DTYPE.itemsize == 80
@@ -438,6 +438,18 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         mu_pf.append(_prefilter(rec, keys=(0, 1, 2)))
         mu_ids.append(pid)
 
+    # MS rows use the same per-message mask table: their intervals follow the MU pairs, with clock slot 0
+    # (the MS kernel puts the message's own tenths, normalised by P[CP], into T[0])
+    ms_vals: Dict[Tuple[int, int], int] = {}
+    for rec in ms_rows:
+        for kk in range(4):
+            kt = rec["key"][kk]
+            for u in range(int(kt["nuniq"])):
+                vkey2 = (int(kt["lo"][u]), int(kt["hi"][u]))
+                if vkey2 not in ms_vals:
+                    ms_vals[vkey2] = len(ms_vals)
+                kt["vidx"][u] = len(mu_vals) + ms_vals[vkey2]
+
     # ---------------- MC / MN protocol rows (every protocol id, table order) ----------------
     hexrows = np.zeros(len(ids), dtype=HEXPROTO_DTYPE)
     for idx, (pid, pr) in enumerate(protocols.items()):
@@ -509,12 +521,15 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
     hdr["off_rank"] = add(rank_arr)
     hdr["off_mm"] = add(mm_arr)
     hdr["off_hex"] = add(hexrows)
-    if len(mu_vals) > MAX_VALS:
-        raise NotImplementedError(f"{len(mu_vals)} distinct (clock, interval) pairs (max {MAX_VALS})")
-    val_arr = np.zeros(len(mu_vals), dtype=VALROW_DTYPE)
+    if len(mu_vals) + len(ms_vals) > MAX_VALS:
+        raise NotImplementedError(f"{len(mu_vals) + len(ms_vals)} distinct (clock, interval) pairs (max {MAX_VALS})")
+    val_arr = np.zeros(len(mu_vals) + len(ms_vals), dtype=VALROW_DTYPE)
     for (ck, lo, hi), i in mu_vals.items():
         val_arr[i] = (ck, lo, hi, 0)
+    for (lo, hi), i in ms_vals.items():
+        val_arr[len(mu_vals) + i] = (0, lo, hi, 0)
     hdr["n_vals"] = len(val_arr)
+    hdr["n_mu_vals"] = len(mu_vals)
     hdr["off_vals"] = add(val_arr)
     total = (off + 15) // 16 * 16
     hdr["total"] = total
@@ -522,7 +537,7 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
     blob[: HEADER_DTYPE.itemsize] = hdr.tobytes()
     for start, b in sections:
         blob[start : start + len(b)] = b
-    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr), "n_vals": len(mu_vals),
+    info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr), "n_vals": len(mu_vals) + len(ms_vals), "n_mu_vals": len(mu_vals),
             "n_mm_items": len(mm_arr), "bytes": total, "clocks": clocks}
     return CompiledTable(bytes(blob), ids, ms_ids, mu_ids, info)
 
