@@ -245,9 +245,9 @@ def run_ours(args):
                                  s["d_hits"].data_ptr(), s["hits_cap"], s["d_bits"].data_ptr(), s["bits_cap"],
                                  s["d_ctr"].data_ptr(), stream)
 
-    # our kernels per step: MS 1, MU = (resolve + scan) per 262144-message chunk, MC 1, MN 1
-    MU_CHUNK = 262144
-    launches_per_step = sum((2 * ((s["n"] + MU_CHUNK - 1) // MU_CHUNK)) if s["kind"] == 1 else 1 for s in slots)
+    # our kernels per step: MS and MU = (resolve + scan) per 262144-message chunk, MC 1, MN 1
+    CHUNK = 262144
+    launches_per_step = sum((2 * ((s["n"] + CHUNK - 1) // CHUNK)) if s["kind"] <= 1 else 1 for s in slots)
 
     def barrier():
         if world > 1:
@@ -364,7 +364,7 @@ def run_ours(args):
         if tj and tj.get("messages"):
             traffic = tj["dram_bytes_per_message"] * s["n"]
     roofline = {
-        "bound": "hbm", "kernel": {0: "pulse_kernel<MS>", 1: "mu_resolve_kernel + mu_scan_kernel (one MU pass)"}.get(s["kind"], "hex_kernel"),
+        "bound": "hbm", "kernel": {0: "resolve_kernel<MS> + scan_kernel<MS> (one MS pass)", 1: "resolve_kernel<MU> + scan_kernel<MU> (one MU pass)"}.get(s["kind"], "hex_kernel"),
         "achieved": achieved,
         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kern_ms[dom],

@@ -145,7 +145,7 @@ static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, cons
                          uint32_t *d_bits, uint32_t bits_cap, SdbCounters *d_counters, cudaStream_t st)
 {
     int grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
-    if (kind == SDB_KIND_MU && n) {
+    if (n) {
         /* scratch is sized for the worst case (every protocol of every message survives), once per handle */
         uint32_t chunk = n < SDB_MU_CHUNK ? ((n + 1023u) & ~1023u) : SDB_MU_CHUNK;
         if (chunk > h->mu_chunk) {
@@ -153,7 +153,7 @@ static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, cons
             CK(cudaStreamSynchronize(st));
             if (h->d_mu_scratch) CK(cudaFree(h->d_mu_scratch));
             h->d_mu_scratch = nullptr; h->mu_chunk = 0;
-            CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_mu, chunk)));
+            CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_ms > h->tab.n_mu ? h->tab.n_ms : h->tab.n_mu, chunk)));
             h->mu_chunk = chunk;
         }
     }

@@ -68,8 +68,9 @@ struct KArgs {
     SdbHit *hits;  uint32_t hits_cap;
     uint32_t *bits; uint32_t bits_cap;
     SdbCounters *ctr;
-    SdbSurv *surv;             /* MU: n x n_mu survivor slots (resolve -> scan) */
-    uint32_t *surv_cnt;        /* MU: survivors per message */
+    SdbSurv *surv;             /* n x surv_stride survivor slots (resolve -> scan) */
+    uint32_t *surv_cnt;        /* survivors per message */
+    uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
 };
 
 struct __align__(16) WarpSm {
@@ -681,26 +682,6 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
     return SDB_ST_OK;
 }
 
-/* ---- one (message x MU protocol) task, warp-level resolution (long `start`, 1- or 4-digit symbols):
- *      message_unsynced.py:59-141, then the scan ------------------------------------------------ */
-__device__ __noinline__ int decode_mu(const KArgs &A, const SdbPulseProto *pp)
-{
-    WarpSm &sm = SM();
-    const int t_slot = sm.T[pp->clk_idx][lane_id() & 7];
-    /* start (:67-88) */
-    int s0 = 0;
-    uint64_t start_t = 0;
-    if (pp->key[0].len && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return SDB_ST_OK;
-    /* one / zero / float on D' = D[s0:] (:99-141) */
-    uint64_t t1 = 0, t0 = 0, tf = 0;
-    int dummy;
-    if (!resolve_key(&pp->key[1], t_slot, s0, false, t1, dummy)) return SDB_ST_OK;
-    bool hasf = false;
-    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, s0, false, t0, dummy)) return SDB_ST_OK;
-    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
-    return scan_mu(A, pp, s0, start_t, (uint32_t)t1, (uint32_t)t0, (uint32_t)tf, hasf);
-}
-
 /* ---- thread-level pattern_exists for templates of <= 2 pulses (<= 2 distinct values) -----------
  * One LANE resolves one protocol: candidates are ordered by (gap rank, slot) by repeated
  * min-extraction from 8 registers, the product is walked in itertools.product order, and
@@ -864,25 +845,6 @@ __device__ __forceinline__ int thread_resolve_ms(const SdbPulseProto *__restrict
 __device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
                                     uint32_t cf, bool hasf);
 
-/* warp-level resolution for the MS protocols with 4-digit symbols or a 4-pulse sync, then the chunk loop */
-__device__ __noinline__ int decode_ms(const KArgs &A, const SdbPulseProto *pp, int t_slot)
-{
-    WarpSm &sm = SM();
-    const int w = pp->width;
-    uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
-    int spos = 0, dummy;
-    const int Lsy = pp->key[0].len;
-    /* sync, then length_min against the digits left after it (:140-156) */
-    if (!resolve_key(&pp->key[0], t_slot, 0, true, ts, spos)) return SDB_ST_OK;
-    const int ms = spos + Lsy;
-    if ((int)pp->regex_min * w > sm.dlen - ms) return SDB_ST_OK;   /* length_min > (len - start) / width */
-    if (!resolve_key(&pp->key[1], t_slot, 0, false, t1, dummy)) return SDB_ST_OK;
-    bool hasf = false;
-    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, 0, false, t0, dummy)) return SDB_ST_OK;
-    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, 0, false, tf, dummy);
-    return scan_ms(A, pp, ms, (uint32_t)ts, (uint32_t)t1, (uint32_t)t0, (uint32_t)tf, hasf);
-}
-
 /* the chunk loop of one resolved (message x MS protocol) task: message_synced.py:171-241 */
 __device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
                                     uint32_t cf, bool hasf)
@@ -1004,135 +966,15 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
     }
 }
 
-/* phase 1: does protocol row `pf` have >= 1 candidate slot for every mandatory distinct value? */
-__device__ __forceinline__ bool prefilter_ok(const SdbPrefilter *__restrict__ pf, const int t[8])
-{
-    const int nreq = pf->nreq;
-    bool ok = true;
-    #pragma unroll 1
-    for (int r = 0; r < nreq && ok; r++) {
-        int lo = pf->lo[r], hi = pf->hi[r];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 8; j++) any |= (t[j] >= lo) & (t[j] <= hi);
-        ok = any;
-    }
-    return ok;
-}
-
-template <bool MS>
-__device__ __noinline__ int run_message(const KArgs &A, const SdbPulseMsg *m)
-{
-    WarpSm &sm = SM();
-    const int lane = lane_id();
-    const int npat = sm.npat;
-    int status = SDB_ST_OK;
-    if (MS) {
-        const int cp = m->cp;
-        if (cp == 0xFF) return SDB_ST_OK;                        /* message_synced.py:60-62 */
-        const int pc = sm.pat[cp];
-        if (pc == 0) return SDB_ST_OK;                           /* :65-66 */
-        const double clock_abs = fabs((double)pc);
-        /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
-        const int t_slot = (lane & 7) < npat ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
-        if (lane < 8) sm.T[0][lane] = (int16_t)t_slot;
-        __syncwarp();
-        /* candidate-slot masks of the MS intervals (they follow the MU pairs in the value table) */
-        for (int v = A.tab.n_mu_vals + lane; v < (int)A.tab.n_vals; v += 32) {
-            const SdbValRow vr = A.tab.vals[v];
-            uint32_t mk = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const int tj = sm.T[0][j]; mk |= (uint32_t)(tj >= vr.lo && tj <= vr.hi) << j; }
-            sm.M[v] = (uint8_t)mk;
-        }
-        __syncwarp();
-        const uint32_t n = A.tab.n_ms;
-#pragma unroll 1
-        for (uint32_t q0 = 0; q0 < n; q0 += 32) {
-            const uint32_t q = q0 + lane;
-            int state = 0;
-            uint32_t codes = 0, msf = 0;
-            if (q < n) {
-                const SdbPulseProto *pq = &A.tab.ms[q];
-                const double pclk = pq->clock;                    /* :83-88 */
-                const bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
-                if (!gate) state = thread_resolve_ms(pq, sm, codes, msf);   /* one lane per protocol */
-            }
-            uint32_t surv = __ballot_sync(FULL, state != 0);
-            while (surv) {                                        /* protocol-table order */
-                const int b = __ffs(surv) - 1;
-                surv &= surv - 1;
-                const int st_b = __shfl_sync(FULL, state, b);
-                const uint32_t cd = __shfl_sync(FULL, codes, b), mf = __shfl_sync(FULL, msf, b);
-                const SdbPulseProto *pp = &A.tab.ms[q0 + b];
-                if (st_b == 2) status = decode_ms(A, pp, t_slot);
-                else status = scan_ms(A, pp, (int)(mf & 0xFFFF), cd & 0xFF, (cd >> 8) & 0xFF, (cd >> 16) & 0xFF, cd >> 24, (mf >> 16) != 0);
-                if (status != SDB_ST_OK) return status;
-            }
-        }
-    }
-    return status;
-}
-
-template <bool MS>
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) pulse_kernel(KArgs A)
-{
-    WarpSm &sm = SM();
-    const int lane = lane_id();
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-
-    for (uint32_t mi = wid; mi < A.n; mi += warps) {
-        const SdbPulseMsg *m = &A.msgs[mi];
-        SdbMsgOut mo;
-        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
-        const int dlen = m->dlen;
-        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
-            stage_message(A, sm, m, dlen, mi);
-            int status = run_message<MS>(A, m);
-            __syncwarp();
-            const uint32_t nh = sm.nh, nw = sm.nw;
-            if (status != SDB_ST_OK) {
-                mo.status = (uint8_t)status;                     /* exception: earlier hits are lost */
-                if (lane == 0) atomicAdd(&A.ctr->raised, 1u);
-            } else if (nh) {
-                uint32_t hb = 0, wb = 0;
-                if (lane == 0) {
-                    hb = atomicAdd(&A.ctr->hits, nh);
-                    wb = atomicAdd(&A.ctr->words, nw);
-                }
-                hb = __shfl_sync(FULL, hb, 0);
-                wb = __shfl_sync(FULL, wb, 0);
-                mo.hit_off = hb; mo.nhits = (uint16_t)nh;
-                if (!sm.overflow) {
-                    if (hb + nh <= A.hits_cap && wb + nw <= A.bits_cap) {
-                        for (uint32_t i = lane; i < nh; i += 32) {
-                            SdbHit h = sm.st_hits[i];
-                            h.bits_off += wb;
-                            A.hits[hb + i] = h;
-                        }
-                        for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
-                    }
-                } else {
-                    /* rare: more output than the staging area holds -> decode again, writing in place */
-                    __syncwarp();
-                    if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
-                    __syncwarp();
-                    run_message<MS>(A, m);
-                }
-            }
-        }
-        if (lane == 0) A.out[mi] = mo;
-        __syncwarp();
-    }
-}
-
 /* =========================================================================================
- * MU runs as TWO kernels so that each has a small instruction footprint (ncu: the fused kernel
- * spent > 50 % of its stall samples waiting for instruction fetch):
- *   mu_resolve_kernel  message_unsynced.py:59-141 for every protocol -> SdbSurv records
- *   mu_scan_kernel     message_unsynced.py:146-290 for every survivor, in protocol-table order
- * Both are one warp per message; the survivor slots of message i are surv[i*n_mu .. +n_mu).
+ * MS and MU each run as TWO kernels so that each has a small instruction footprint (ncu: a fused
+ * kernel spends > 50 % of its stall samples waiting for instruction fetch, because the warps of an
+ * SM sit in different phases of a large body of code):
+ *   resolve_kernel<MS|MU>  template resolution for every protocol -> SdbSurv records
+ *                          (message_synced.py:83-163 / message_unsynced.py:59-141)
+ *   scan_kernel<MS|MU>     chunk loop / regex scan for every survivor, in protocol-table order
+ *                          (message_synced.py:171-241 / message_unsynced.py:146-290)
+ * Both are one warp per message; the survivor slots of message i are surv[i*stride .. +stride).
  * ========================================================================================= */
 
 /* warp-level template resolution of one "complex" MU protocol (long start / 1- or 4-digit symbols) */
@@ -1153,13 +995,82 @@ __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &r
     return true;
 }
 
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_resolve_kernel(KArgs A)
+/* warp-level resolution of one "complex" MS protocol (4-digit symbols or a 4-pulse sync): message_synced.py:109-163 */
+__device__ __noinline__ bool resolve_ms_warp(const SdbPulseProto *pp, SdbSurv &rec)
+{
+    WarpSm &sm = SM();
+    const int t_slot = sm.T[0][lane_id() & 7];
+    const int w = pp->width;
+    uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
+    int spos = 0, dummy;
+    if (!resolve_key(&pp->key[0], t_slot, 0, true, ts, spos)) return false;
+    const int ms = spos + pp->key[0].len;
+    if ((int)pp->regex_min * w > sm.dlen - ms) return false;          /* :150-156 length_min > (len - start) / width */
+    if (!resolve_key(&pp->key[1], t_slot, 0, false, t1, dummy)) return false;
+    if (pp->key[2].len && !resolve_key(&pp->key[2], t_slot, 0, false, t0, dummy)) return false;
+    bool hasf = false;
+    if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, 0, false, tf, dummy);
+    rec.start = ts;
+    rec.c1 = (uint16_t)t1; rec.c0 = (uint16_t)t0; rec.cf = (uint16_t)tf;
+    rec.meta = (uint16_t)(ms | (hasf ? 0x800 : 0));
+    return true;
+}
+
+/* per-message preparation of the tenths rows and candidate-slot masks; false = the message yields [] */
+template <bool MS>
+__device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, double &clock_abs)
+{
+    const int lane = lane_id();
+    const int npat = sm.npat;
+    int v0, v1;
+    if (MS) {
+        const int cp = m->cp;
+        if (cp == 0xFF) return false;                                /* message_synced.py:60-62 */
+        const int pc = sm.pat[cp];
+        if (pc == 0) return false;                                   /* :65-66 */
+        clock_abs = fabs((double)pc);
+        /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
+        const int t = (lane & 7) < npat ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
+        if (lane < 8) sm.T[0][lane] = (int16_t)t;
+        v0 = (int)A.tab.n_mu_vals; v1 = (int)A.tab.n_vals;          /* the MS intervals follow the MU pairs */
+    } else {
+        /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
+        const int ncl = A.tab.n_clk;
+#pragma unroll 1
+        for (int idx = lane; idx < ncl * 8; idx += 32) {
+            int c = idx >> 3, j = idx & 7;
+            sm.T[c][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
+        }
+        v0 = 0; v1 = (int)A.tab.n_mu_vals;
+    }
+    __syncwarp();
+    /* candidate-slot mask of every distinct (clock, accept interval) pair: one lane per pair */
+#pragma unroll 1
+    for (int v = v0 + lane; v < v1; v += 32) {
+        const SdbValRow vr = A.tab.vals[v];
+        const int4 row = *reinterpret_cast<const int4 *>(&sm.T[vr.clk_idx][0]);
+        const int lo = vr.lo, hi = vr.hi;
+        int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
+        int t4 = (int16_t)(row.z & 0xffff), t5 = row.z >> 16, t6 = (int16_t)(row.w & 0xffff), t7 = row.w >> 16;
+        uint32_t mk = (uint32_t)(t0 >= lo && t0 <= hi) | ((uint32_t)(t1 >= lo && t1 <= hi) << 1) |
+                      ((uint32_t)(t2 >= lo && t2 <= hi) << 2) | ((uint32_t)(t3 >= lo && t3 <= hi) << 3) |
+                      ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
+                      ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
+        sm.M[v] = (uint8_t)mk;                                       /* empty slots hold -32768 and never qualify */
+    }
+    __syncwarp();
+    return true;
+}
+
+template <bool MS>
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_mu = A.tab.n_mu;
+    const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
+    const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
 
     for (uint32_t mi = wid; mi < A.n; mi += warps) {
         const SdbPulseMsg *m = &A.msgs[mi];
@@ -1167,60 +1078,45 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
         uint32_t nsurv = 0;
         if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
             stage_message(A, sm, m, dlen, mi);
-            const int npat = sm.npat;
-            /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
-            const int ncl = A.tab.n_clk;
+            double clock_abs = 0.0;
+            if (prepare_tables<MS>(A, sm, m, clock_abs)) {
+                SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
 #pragma unroll 1
-            for (int idx = lane; idx < ncl * 8; idx += 32) {
-                int c = idx >> 3, j = idx & 7;
-                sm.T[c][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
-            }
-            __syncwarp();
-            /* candidate-slot mask of every distinct (clock, accept interval) pair of the table: one lane per pair */
-            const int nv = A.tab.n_mu_vals;
-#pragma unroll 1
-            for (int v = lane; v < nv; v += 32) {
-                const SdbValRow vr = A.tab.vals[v];
-                const int4 row = *reinterpret_cast<const int4 *>(&sm.T[vr.clk_idx][0]);
-                const int lo = vr.lo, hi = vr.hi;
-                int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
-                int t4 = (int16_t)(row.z & 0xffff), t5 = row.z >> 16, t6 = (int16_t)(row.w & 0xffff), t7 = row.w >> 16;
-                uint32_t mk = (uint32_t)(t0 >= lo && t0 <= hi) | ((uint32_t)(t1 >= lo && t1 <= hi) << 1) |
-                              ((uint32_t)(t2 >= lo && t2 <= hi) << 2) | ((uint32_t)(t3 >= lo && t3 <= hi) << 3) |
-                              ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
-                              ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
-                sm.M[v] = (uint8_t)mk;                            /* empty slots hold -32768 and never qualify */
-            }
-            __syncwarp();
-            SdbSurv *slots = A.surv + (size_t)mi * n_mu;
-#pragma unroll 1
-            for (uint32_t q0 = 0; q0 < n_mu; q0 += 32) {
-                const uint32_t q = q0 + lane;
-                int state = 0;
-                SdbSurv rec;
-                rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
-                if (q < n_mu) {                                   /* exact template resolution, one lane per protocol */
-                    uint32_t codes = 0, s0f = 0;
-                    state = thread_resolve_mu(&A.tab.mu[q], sm, codes, s0f);
-                    rec.start = codes & 0xFF;
-                    rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
-                    rec.meta = (uint16_t)((s0f & 0x7FF) | ((s0f >> 16) ? 0x800 : 0));
+                for (uint32_t q0 = 0; q0 < nrows; q0 += 32) {
+                    const uint32_t q = q0 + lane;
+                    int state = 0;
+                    SdbSurv rec;
+                    rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
+                    if (q < nrows) {                                  /* exact template resolution, one lane per protocol */
+                        const SdbPulseProto *pq = &rows[q];
+                        uint32_t codes = 0, sf = 0;
+                        if (MS) {
+                            const double pclk = pq->clock;            /* message_synced.py:83-88: 30 % clock gate */
+                            const bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
+                            if (!gate) state = thread_resolve_ms(pq, sm, codes, sf);
+                        } else {
+                            state = thread_resolve_mu(pq, sm, codes, sf);
+                        }
+                        rec.start = codes & 0xFF;
+                        rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
+                        rec.meta = (uint16_t)((sf & 0x7FF) | ((sf >> 16) ? 0x800 : 0));
+                    }
+                    /* the few protocols that need warp-wide searches are resolved one after the other */
+                    uint32_t cx = __ballot_sync(FULL, state == 2);
+                    while (cx) {
+                        const int b = __ffs(cx) - 1;
+                        cx &= cx - 1;
+                        SdbSurv r2;
+                        const bool ok = MS ? resolve_ms_warp(&rows[q0 + b], r2) : resolve_mu_warp(&rows[q0 + b], r2);
+                        if (lane == b) { state = ok ? 1 : 0; rec = r2; }
+                    }
+                    const uint32_t alive = __ballot_sync(FULL, state == 1);
+                    if (state == 1) {                                 /* protocol-table order is the slot order */
+                        rec.start |= (uint64_t)q << 56;
+                        slots[nsurv + __popc(alive & ((1u << lane) - 1))] = rec;
+                    }
+                    nsurv += __popc(alive);
                 }
-                /* the few protocols that need warp-wide searches are resolved one after the other */
-                uint32_t cx = __ballot_sync(FULL, state == 2);
-                while (cx) {
-                    const int b = __ffs(cx) - 1;
-                    cx &= cx - 1;
-                    SdbSurv r2;
-                    const bool ok = resolve_mu_warp(&A.tab.mu[q0 + b], r2);
-                    if (lane == b) { state = ok ? 1 : 0; rec = r2; }
-                }
-                const uint32_t alive = __ballot_sync(FULL, state == 1);
-                if (state == 1) {                                 /* protocol-table order is the slot order */
-                    rec.start |= (uint64_t)q << 56;
-                    slots[nsurv + __popc(alive & ((1u << lane) - 1))] = rec;
-                }
-                nsurv += __popc(alive);
             }
         }
         if (lane == 0) A.surv_cnt[mi] = nsurv;
@@ -1228,9 +1124,11 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_reso
     }
 }
 
-__device__ __noinline__ int mu_scan_survivors(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
+template <bool MS>
+__device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
 {
     const int lane = lane_id();
+    const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
 #pragma unroll 1
     for (uint32_t s0i = 0; s0i < nsurv; s0i += 32) {
         SdbSurv mine;
@@ -1243,23 +1141,25 @@ __device__ __noinline__ int mu_scan_survivors(const KArgs &A, const SdbSurv *slo
             const uint32_t shi = __shfl_sync(FULL, (uint32_t)(mine.start >> 32), k);
             const uint32_t c10 = __shfl_sync(FULL, (uint32_t)mine.c1 | ((uint32_t)mine.c0 << 16), k);
             const uint32_t cfm = __shfl_sync(FULL, (uint32_t)mine.cf | ((uint32_t)mine.meta << 16), k);
-            const SdbPulseProto *pp = &A.tab.mu[shi >> 24];
+            const SdbPulseProto *pp = &rows[shi >> 24];
             const uint64_t start_t = (((uint64_t)(shi & 0x00FFFFFFu)) << 32) | slo;
-            const int st = scan_mu(A, pp, (int)((cfm >> 16) & 0x7FF), start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF,
-                                   ((cfm >> 16) & 0x800) != 0);
+            const int pos0 = (int)((cfm >> 16) & 0x7FF);
+            const bool hasf = ((cfm >> 16) & 0x800) != 0;
+            const int st = MS ? scan_ms(A, pp, pos0, (uint32_t)start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf)
+                              : scan_mu(A, pp, pos0, start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf);
             if (st != SDB_ST_OK) return st;
         }
     }
     return SDB_ST_OK;
 }
 
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_scan_kernel(KArgs A)
+template <bool MS>
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_mu = A.tab.n_mu;
 
     for (uint32_t mi = wid; mi < A.n; mi += warps) {
         const SdbPulseMsg *m = &A.msgs[mi];
@@ -1267,9 +1167,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_scan
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
         const uint32_t nsurv = A.surv_cnt[mi];
         if (nsurv) {
-            const SdbSurv *slots = A.surv + (size_t)mi * n_mu;
+            const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
             stage_digits(A, sm, m, m->dlen, mi);
-            int status = mu_scan_survivors(A, slots, nsurv);
+            int status = scan_survivors<MS>(A, slots, nsurv);
             __syncwarp();
             const uint32_t nh = sm.nh, nw = sm.nw;
             if (status != SDB_ST_OK) {
@@ -1298,7 +1198,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_scan
                     __syncwarp();
                     if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
                     __syncwarp();
-                    mu_scan_survivors(A, slots, nsurv);
+                    scan_survivors<MS>(A, slots, nsurv);
                 }
             }
         }
@@ -1309,20 +1209,21 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_scan
 
 int pulse_blocks_per_sm(int kind)
 {
-    int nb = 0;
-    if (kind == SDB_KIND_MS) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pulse_kernel<true>, SDB_PULSE_THREADS, 0);
-    else {
-        int a = 0, b = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mu_resolve_kernel, SDB_PULSE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mu_scan_kernel, SDB_PULSE_THREADS, 0);
-        nb = a < b ? a : b;
+    int a = 0, b = 0;
+    if (kind == SDB_KIND_MS) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, SDB_PULSE_THREADS, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false>, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<false>, SDB_PULSE_THREADS, 0);
     }
+    int nb = a < b ? a : b;
     return nb > 0 ? nb : 1;
 }
 
-size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk)
+size_t mu_scratch_bytes(uint32_t stride, uint32_t chunk)
 {
-    return (size_t)chunk * n_mu * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t);
+    return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t);
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
@@ -1353,24 +1254,27 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     KArgs A;
     A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
     A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
-    A.surv = nullptr; A.surv_cnt = nullptr;
+    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0;
     if (n == 0) return 0;
     const uint32_t wpc = SDB_PULSE_THREADS / 32;
-    if (kind == SDB_KIND_MS) {
-        uint32_t need = (n + wpc - 1) / wpc;
-        pulse_kernel<true><<<need < (uint32_t)grid ? need : grid, SDB_PULSE_THREADS, 0, stream>>>(A);
-        return (int)cudaGetLastError();
-    }
     if (!mu_scratch || !mu_chunk) return (int)cudaErrorInvalidValue;
+    const bool ms = kind == SDB_KIND_MS;
+    const uint32_t stride = tab.n_ms > tab.n_mu ? tab.n_ms : tab.n_mu;       /* scratch is sized for the larger class */
     A.surv = static_cast<SdbSurv *>(mu_scratch);
-    A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * tab.n_mu * sizeof(SdbSurv));
+    A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * stride * sizeof(SdbSurv));
+    A.surv_stride = ms ? tab.n_ms : tab.n_mu;
     for (uint32_t off = 0; off < n; off += mu_chunk) {
         A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;
-        mu_resolve_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-        mu_scan_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+        if (ms) {
+            resolve_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+        } else {
+            resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+        }
     }
     return (int)cudaGetLastError();
 }
