@@ -70,6 +70,7 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
         return set_err(nullptr, SDB_E_ARG, "sdb_create: not a protocol table blob of this version");
     if (hd->n_clk > SDB_MAX_CLK) return set_err(nullptr, SDB_E_ARG, "sdb_create: too many distinct clocks");
     if (hd->n_vals > SDB_MAX_VALS) return set_err(nullptr, SDB_E_ARG, "sdb_create: too many distinct (clock, interval) pairs");
+    if (hd->n_ms > 255 || hd->n_mu > 255) return set_err(nullptr, SDB_E_ARG, "sdb_create: more than 255 protocols in one class");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) return set_err(nullptr, SDB_E_NOGPU, "sdb_create: no CUDA device (there is no CPU fallback)", ce);

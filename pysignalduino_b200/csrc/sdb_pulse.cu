@@ -79,7 +79,8 @@ struct __align__(16) WarpSm {
     uint32_t first1[12], last1[12];   /* digit a                                             */
     uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
     int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
-    uint8_t  M[SDB_MAX_VALS];         /* MU: candidate-slot mask per (clock, interval) pair  */
+    uint8_t  M[SDB_MAX_VALS];         /* candidate-slot mask per (clock, interval) pair      */
+    uint8_t  plist[256];              /* table rows that passed the prefilter, in table order */
     int32_t  pat[8];
     uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
     uint32_t fpl[BIT_WORDS];          /* 'F' plane                                           */
@@ -1071,6 +1072,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
     const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
+    const SdbPrefilter *pfs = MS ? A.tab.ms_pf : A.tab.mu_pf;
 
     for (uint32_t mi = wid; mi < A.n; mi += warps) {
         const SdbPulseMsg *m = &A.msgs[mi];
@@ -1081,22 +1083,41 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
             double clock_abs = 0.0;
             if (prepare_tables<MS>(A, sm, m, clock_abs)) {
                 SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
+                /* pass 1 (lane = protocol): keep the protocols whose mandatory values all have a candidate slot
+                 * (pattern_utils.py:78-80; MS also the 30 % clock gate, message_synced.py:83-88); compact their
+                 * row numbers, in table order, into plist */
+                uint32_t nalive = 0;
 #pragma unroll 1
                 for (uint32_t q0 = 0; q0 < nrows; q0 += 32) {
                     const uint32_t q = q0 + lane;
+                    bool ok = false;
+                    if (q < nrows) {
+                        const SdbPrefilter *pf = &pfs[q];
+                        const int nreq = pf->nreq;
+                        ok = true;
+                        for (int r = 0; r < nreq; r++) ok = ok && sm.M[pf->vreq[r]] != 0;
+                        if (MS && ok) {
+                            const double pclk = rows[q].clock;
+                            ok = !(pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3));
+                        }
+                    }
+                    const uint32_t bal = __ballot_sync(FULL, ok);
+                    if (ok) sm.plist[nalive + __popc(bal & ((1u << lane) - 1))] = (uint8_t)q;
+                    nalive += __popc(bal);
+                }
+                __syncwarp();
+                /* pass 2 (lane = surviving protocol): exact template resolution */
+#pragma unroll 1
+                for (uint32_t q0 = 0; q0 < nalive; q0 += 32) {
+                    const bool have = q0 + lane < nalive;
+                    const uint32_t q = have ? sm.plist[q0 + lane] : 0;
                     int state = 0;
                     SdbSurv rec;
                     rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
-                    if (q < nrows) {                                  /* exact template resolution, one lane per protocol */
+                    if (have) {
                         const SdbPulseProto *pq = &rows[q];
                         uint32_t codes = 0, sf = 0;
-                        if (MS) {
-                            const double pclk = pq->clock;            /* message_synced.py:83-88: 30 % clock gate */
-                            const bool gate = pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3);
-                            if (!gate) state = thread_resolve_ms(pq, sm, codes, sf);
-                        } else {
-                            state = thread_resolve_mu(pq, sm, codes, sf);
-                        }
+                        state = MS ? thread_resolve_ms(pq, sm, codes, sf) : thread_resolve_mu(pq, sm, codes, sf);
                         rec.start = codes & 0xFF;
                         rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
                         rec.meta = (uint16_t)((sf & 0x7FF) | ((sf >> 16) ? 0x800 : 0));
@@ -1106,8 +1127,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                     while (cx) {
                         const int b = __ffs(cx) - 1;
                         cx &= cx - 1;
+                        const uint32_t qb = __shfl_sync(FULL, q, b);
                         SdbSurv r2;
-                        const bool ok = MS ? resolve_ms_warp(&rows[q0 + b], r2) : resolve_mu_warp(&rows[q0 + b], r2);
+                        const bool ok = MS ? resolve_ms_warp(&rows[qb], r2) : resolve_mu_warp(&rows[qb], r2);
                         if (lane == b) { state = ok ? 1 : 0; rec = r2; }
                     }
                     const uint32_t alive = __ballot_sync(FULL, state == 1);

@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 7u
+#define SDB_TBL_VERSION 8u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -110,12 +110,11 @@ typedef struct SdbPulseProto {
     uint8_t  rsv[7];
 } SdbPulseProto;
 
-/* Phase-1 prefilter row, 52 bytes. */
+/* Phase-1 prefilter row, 28 bytes: rows of the candidate-mask table that must all be non-zero. */
 typedef struct SdbPrefilter {
     uint16_t clk_idx;
     uint16_t nreq;
-    int16_t  lo[SDB_MAX_REQ];
-    int16_t  hi[SDB_MAX_REQ];
+    uint16_t vreq[SDB_MAX_REQ];
 } SdbPrefilter;
 
 /* One modulematch atom: `min` (..`max` for the last, '$'-anchored atom) characters inside `mask`. */
@@ -148,7 +147,7 @@ typedef struct SdbTblHeader {
 static_assert(sizeof(SdbKeyTpl) == 48, "SdbKeyTpl layout");
 static_assert(sizeof(SdbValRow) == 8, "SdbValRow layout");
 static_assert(sizeof(SdbPulseProto) == 248, "SdbPulseProto layout");
-static_assert(sizeof(SdbPrefilter) == 52, "SdbPrefilter layout");
+static_assert(sizeof(SdbPrefilter) == 28, "SdbPrefilter layout");
 static_assert(sizeof(SdbMmItem) == 20, "SdbMmItem layout");
 static_assert(sizeof(SdbHexProto) == 36, "SdbHexProto layout");
 static_assert(sizeof(SdbTblHeader) == 80, "SdbTblHeader layout");

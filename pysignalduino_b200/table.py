@@ -30,7 +30,7 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 7
+TBL_VERSION = 8
 
 MAX_UNIQ = 4
 MAX_TPL = 14
@@ -83,10 +83,8 @@ PULSEPROTO_DTYPE = np.dtype(
 )
 assert PULSEPROTO_DTYPE.itemsize == 248, PULSEPROTO_DTYPE.itemsize
 
-PREFILTER_DTYPE = np.dtype(
-    [("clk_idx", "<u2"), ("nreq", "<u2"), ("lo", "<i2", (MAX_REQ,)), ("hi", "<i2", (MAX_REQ,))]
-)
-assert PREFILTER_DTYPE.itemsize == 52
+PREFILTER_DTYPE = np.dtype([("clk_idx", "<u2"), ("nreq", "<u2"), ("vreq", "<u2", (MAX_REQ,))])
+assert PREFILTER_DTYPE.itemsize == 28
 
 VALROW_DTYPE = np.dtype([("clk_idx", "<u2"), ("lo", "<i2"), ("hi", "<i2"), ("rsv", "<u2")])
 assert VALROW_DTYPE.itemsize == 8
@@ -368,7 +366,6 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         if pr.get("postDemodulation") and rec["postdemod"] and pr.get("float"):
             raise NotImplementedError(f"protocol {pid}: MS postDemodulation with 'float' symbols raises in the reference")
         ms_rows.append(rec)
-        ms_pf.append(_prefilter(rec, keys=(0, 1, 2)))
         ms_ids.append(pid)
 
     # ---------------- MU: get_keys('clockabs') + active (message_unsynced.py:45-49) ----------------
@@ -435,7 +432,6 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
                     mu_vals[vkey] = len(mu_vals)
                 kt["vidx"][u] = mu_vals[vkey]
         mu_rows.append(rec)
-        mu_pf.append(_prefilter(rec, keys=(0, 1, 2)))
         mu_ids.append(pid)
 
     # MS rows use the same per-message mask table: their intervals follow the MU pairs, with clock slot 0
@@ -488,6 +484,8 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         return a
 
     ms_arr, mu_arr = arr(ms_rows, PULSEPROTO_DTYPE), arr(mu_rows, PULSEPROTO_DTYPE)
+    ms_pf = [_prefilter(rec, keys=(0, 1, 2)) for rec in ms_rows]
+    mu_pf = [_prefilter(rec, keys=(0, 1, 2)) for rec in mu_rows]
     ms_pf_arr, mu_pf_arr = arr(ms_pf, PREFILTER_DTYPE), arr(mu_pf, PREFILTER_DTYPE)
     # n_clk clocks followed by n_clk values of 10/clock (device fast path of round(p/clock, 1), exact path on near-ties)
     clk_arr = np.asarray(clocks + [10.0 / c for c in clocks], dtype="<f8")
@@ -591,21 +589,20 @@ def _fill_common(rec, idx: int, pid: str, pr: Dict[str, Any], pool: _RankPool, m
 
 
 def _prefilter(rec, keys) -> np.ndarray:
-    """Every unique value of the mandatory keys needs >= 1 slot inside its interval (pattern_utils.py:78-80)."""
+    """Every unique value of the mandatory keys needs >= 1 candidate slot (pattern_utils.py:78-80):
+    the rows of the per-message candidate-mask table that must be non-zero for the protocol to stay alive."""
     pf = np.zeros((), dtype=PREFILTER_DTYPE)
     pf["clk_idx"] = rec["clk_idx"]
-    n = 0
-    seen = set()
+    req: List[int] = []
     for k in keys:
         kt = rec["key"][k]
         for u in range(int(kt["nuniq"])):
-            iv = (int(kt["lo"][u]), int(kt["hi"][u]))
-            if iv in seen:
-                continue
-            seen.add(iv)
-            if n >= MAX_REQ:
-                raise NotImplementedError("prefilter overflow")
-            pf["lo"][n], pf["hi"][n] = iv
-            n += 1
-    pf["nreq"] = n
+            v = int(kt["vidx"][u])
+            if v not in req:
+                req.append(v)
+    if len(req) > MAX_REQ:
+        raise NotImplementedError("prefilter overflow")
+    for i, v in enumerate(req):
+        pf["vreq"][i] = v
+    pf["nreq"] = len(req)
     return pf

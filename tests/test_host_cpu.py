@@ -42,7 +42,7 @@ def test_record_layouts_match_header():
     assert pack.PULSE_DTYPE.itemsize == 48 and pack.HEX_DTYPE.itemsize == 16
     assert pack.MSGOUT_DTYPE.itemsize == 8 and pack.HIT_DTYPE.itemsize == 16 and pack.COUNTERS_DTYPE.itemsize == 16
     assert table.PULSEPROTO_DTYPE.itemsize == 248 and table.KEYTPL_DTYPE.itemsize == 48
-    assert table.PREFILTER_DTYPE.itemsize == 52 and table.MMITEM_DTYPE.itemsize == 20 and table.HEXPROTO_DTYPE.itemsize == 36
+    assert table.PREFILTER_DTYPE.itemsize == 28 and table.MMITEM_DTYPE.itemsize == 20 and table.HEXPROTO_DTYPE.itemsize == 36
 
 
 def test_pack_pattern_order_and_duplicates():
