@@ -177,6 +177,13 @@ int sdb_format_hits(const SdbHandle *h, int kind,
 int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_t n_in,
                        uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode);
 
+/*
+ * Bounds-check build only (libsdb200_chk.so, -DSDB_BOUNDS_CHECK): number of out-of-range shared-memory
+ * indices the kernels have seen so far (compute-sanitizer is not available on the GPU pool).
+ * Returns 0xFFFFFFFF from the normal build.
+ */
+unsigned int sdb_debug_violations(SdbHandle *h, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libsdb200.so"
+LIB_CHK = PKG / "libsdb200_chk.so"      # same sources with -DSDB_BOUNDS_CHECK
 SOURCES = ["sdb_capi.cu", "sdb_pulse.cu", "sdb_hex.cu"]
 HEADERS = ["sdb_table.h", "sdb_pulse.h", "sdb_postdemod.cuh", "../../include/sdb200.h"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -25,26 +26,27 @@ def nvcc_path() -> str:
     return cand
 
 
-def needs_build() -> bool:
-    if not LIB.exists():
+def needs_build(lib: Path = LIB) -> bool:
+    if not lib.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = lib.stat().st_mtime
     return any((CSRC / f).stat().st_mtime > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
+def build(force: bool = False, verbose: bool = False, check: bool = False) -> Path:
+    lib = LIB_CHK if check else LIB
+    if not force and not needs_build(lib):
+        return lib
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-lineinfo", *ARCH_FLAGS, "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+           "-Xptxas", "-v" if verbose else "-O3", "-o", str(lib)] + (["-DSDB_BOUNDS_CHECK"] if check else []) \
+        + [str(CSRC / s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libsdb200.so")
-    return LIB
+        raise RuntimeError(f"nvcc failed building {lib.name}")
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(LIB)
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, check="--check" in sys.argv))

@@ -14,7 +14,10 @@ import numpy as np
 from . import pack
 from .table import CompiledTable
 
-LIB_PATH = Path(__file__).resolve().parent / "libsdb200.so"
+import os
+
+CHECKED = os.environ.get("SDB200_CHECKED") == "1"      # use the bounds-check build (libsdb200_chk.so)
+LIB_PATH = Path(__file__).resolve().parent / ("libsdb200_chk.so" if CHECKED else "libsdb200.so")
 
 SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU = 0, -1, -2, -3, -4
 ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR = 0, 1, 2, 3
@@ -26,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_debug_violations",
 ]
 
 
@@ -48,7 +51,7 @@ def load_library() -> C.CDLL:
     if not LIB_PATH.exists():
         from .build_ext import build
 
-        build()
+        build(check=CHECKED)
     L = C.CDLL(str(LIB_PATH))
     L.sdb_abi_version.restype = C.c_int
     L.sdb_last_error.restype = C.c_char_p
@@ -72,6 +75,8 @@ def load_library() -> C.CDLL:
     L.sdb_unit_postdemod.restype = C.c_int
     L.sdb_unit_postdemod.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.sdb_debug_violations.restype = C.c_uint
+    L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
         raise SdbError("libsdb200.so ABI version mismatch")
     _lib = L
@@ -185,6 +190,10 @@ class Engine:
             if rc != SDB_OK:
                 raise self._err(rc, "sdb_format_hits")
             return pool[: used.value].tobytes(), off
+
+    def debug_violations(self, reset: bool = False) -> int:
+        """Out-of-range index count of the bounds-check build (0xFFFFFFFF from the normal build)."""
+        return int(self.lib.sdb_debug_violations(self.h, 1 if reset else 0))
 
     # ---- unit ops --------------------------------------------------------------------------
     def unit_postdemod(self, method: int, bits_in) -> Tuple[int, List[int]]:

@@ -59,6 +59,14 @@ static int set_err(SdbHandle *h, int code, const char *what, cudaError_t ce = cu
 
 extern "C" int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 
+extern "C" unsigned int sdb_debug_violations(SdbHandle *h, int reset)
+{
+    if (!h) return 0xFFFFFFFFu;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    return sdb::debug_violations(reset != 0);
+}
+
 extern "C" const char *sdb_last_error(const SdbHandle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHandle **out)

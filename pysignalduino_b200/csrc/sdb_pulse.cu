@@ -51,6 +51,19 @@ namespace sdb {
 #define NONE32 0xffffffffu
 #define WARPS (SDB_PULSE_THREADS / 32)
 
+/* compute-sanitizer is not available on the GPU pool, so the library can be built with its own bounds checks
+ * (-DSDB_BOUNDS_CHECK, python -m pysignalduino_b200.build_ext --check): every data-dependent shared-memory index
+ * goes through IDX(), violations are counted in g_sdb_oob and read back with sdb_debug_violations(). */
+#ifdef SDB_BOUNDS_CHECK
+__device__ unsigned int g_sdb_oob = 0;
+__device__ __forceinline__ int sdb_chk_idx(int i, int n) { if ((unsigned)i >= (unsigned)n) { atomicAdd(&g_sdb_oob, 1u); return 0; } return i; }
+#define IDX(i, n) sdb_chk_idx((int)(i), (int)(n))
+#define SDB_CHK(c) do { if (!(c)) atomicAdd(&g_sdb_oob, 1u); } while (0)
+#else
+#define IDX(i, n) (i)
+#define SDB_CHK(c) do { } while (0)
+#endif
+
 /* One resolved (message x MU protocol) task handed from the resolve kernel to the scan kernel, 16 bytes. */
 struct __align__(16) SdbSurv {
     uint64_t start;        /* bits 0..55: id string of `start` (nibble-packed), bits 56..63: MU table row */
@@ -108,12 +121,14 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t win32(const uint32_t *dig, int p)
 {
     int wi = p >> 3, sh = (p & 7) * 4;
+    SDB_CHK(p >= 0 && wi + 1 < DIG_WORDS);
     return __funnelshift_r(dig[wi], dig[wi + 1], sh);
 }
 /* 16 digits starting at position p */
 __device__ __forceinline__ uint64_t win64(const uint32_t *dig, int p)
 {
     int wi = p >> 3, sh = (p & 7) * 4;
+    SDB_CHK(p >= 0 && wi + 2 < DIG_WORDS);
     uint32_t a = dig[wi], b = dig[wi + 1], c = dig[wi + 2];
     return ((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
 }
@@ -190,7 +205,8 @@ __device__ __noinline__ int warp_find(uint64_t tgt, int L, int from)
     uint64_t m = nibmask64(L);
     for (int base = from; base + L <= dlen; base += 32) {
         int p = base + lane_id();
-        bool hit = (p + L <= dlen) && ((win64(sm.dig, p) & m) == tgt);
+        bool hit = false;
+        if (p + L <= dlen) hit = (win64(sm.dig, p) & m) == tgt;      /* never read past the staged digits */
         uint32_t bal = __ballot_sync(FULL, hit);
         if (bal) return base + __ffs(bal) - 1;
     }
@@ -202,19 +218,19 @@ __device__ __forceinline__ bool target_present(WarpSm &sm, uint64_t tg, int L, i
 {
     const int d0 = (int)(tg & 0xF), d1 = (int)((tg >> 4) & 0xF);
     if (L == 1) {
-        if (sm.last1[d0] <= (uint32_t)from) return false;
-        if (want_pos) pos = (int)sm.first1[d0];           /* want_pos callers search from 0 */
+        if (sm.last1[IDX(d0, 12)] <= (uint32_t)from) return false;
+        if (want_pos) pos = (int)sm.first1[IDX(d0, 12)];           /* want_pos callers search from 0 */
         return true;
     }
     if (L == 2) {
-        if (sm.last2[d0 * 10 + d1] <= (uint32_t)from) return false;
-        if (want_pos) pos = (int)sm.first2[d0 * 10 + d1];
+        if (sm.last2[IDX(d0 * 10 + d1, 100)] <= (uint32_t)from) return false;
+        if (want_pos) pos = (int)sm.first2[IDX(d0 * 10 + d1, 100)];
         return true;
     }
     int prev = d0;
     for (int i = 1; i < L; i++) {                         /* necessary: every digram occurs late enough */
         int d = (int)((tg >> (4 * i)) & 0xF);
-        if (sm.last2[prev * 10 + d] <= (uint32_t)(from + i - 1)) return false;
+        if (sm.last2[IDX(prev * 10 + d, 100)] <= (uint32_t)(from + i - 1)) return false;
         prev = d;
     }
     int p = warp_find(tg, L, from);
@@ -285,8 +301,8 @@ __device__ __noinline__ bool resolve_general(const SdbKeyTpl *__restrict__ k, in
             int d = (pat_ids >> (4 * s)) & 0xF;
             tg |= (uint64_t)d << (4 * i);
             if (ok) {
-                if (L == 1) ok = sm.last1[d] > (uint32_t)from;
-                else if (i > 0) ok = sm.last2[prev * 10 + d] > (uint32_t)(from + i - 1);   /* digram filter (exact for L == 2) */
+                if (L == 1) ok = sm.last1[IDX(d, 12)] > (uint32_t)from;
+                else if (i > 0) ok = sm.last2[IDX(prev * 10 + d, 100)] > (uint32_t)(from + i - 1);   /* digram filter (exact for L == 2) */
             }
             prev = d;
         }
@@ -436,14 +452,14 @@ __device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, i
     if (!sm.direct) {
         if (nh0 < ST_HITS && nw0 + nw <= ST_WORDS && !sm.overflow) {
             h.bits_off = nw0;
-            if (lane == 0) sm.st_hits[nh0] = h;
-            for (int i = lane; i < nw; i += 32) sm.st_bits[nw0 + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+            if (lane == 0) sm.st_hits[IDX(nh0, ST_HITS)] = h;
+            for (int i = lane; i < nw; i += 32) sm.st_bits[IDX(nw0 + i, ST_WORDS)] = i < nwv ? sm.val[IDX(i, BIT_WORDS)] : sm.fpl[IDX(i - nwv, BIT_WORDS)];
         } else if (lane == 0) sm.overflow = 1;
     } else {
         h.bits_off = sm.wbase + nw0;
         if (sm.hbase + nh0 < A.hits_cap && sm.wbase + nw0 + nw <= A.bits_cap) {
             if (lane == 0) A.hits[sm.hbase + nh0] = h;
-            for (int i = lane; i < nw; i += 32) A.bits[sm.wbase + nw0 + i] = i < nwv ? sm.val[i] : sm.fpl[i - nwv];
+            for (int i = lane; i < nw; i += 32) A.bits[sm.wbase + nw0 + i] = i < nwv ? sm.val[IDX(i, BIT_WORDS)] : sm.fpl[IDX(i - nwv, BIT_WORDS)];
         }
     }
     __syncwarp();
@@ -457,7 +473,7 @@ __device__ __noinline__ void run_postdemod(int method, int nb)
     WarpSm &sm = SM();
     if (lane_id() == 0) {
         int no = 0;
-        for (int w = 0; w < BIT_WORDS; w++) sm.tmp[w] = 0;
+        for (int w = 0; w < BIT_WORDS; w++) sm.tmp[IDX(w, BIT_WORDS)] = 0;
         sm.pd_rc = postdemod(method, sm.val, nb, sm.tmp, &no);
         sm.pd_no = no;
     }
@@ -476,7 +492,7 @@ __device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp
     bool has_f = false;
     if (maybe_f) {
         uint32_t fany = 0;
-        for (int i = lane; i < ((nb + 31) >> 5); i += 32) fany |= sm.fpl[i];
+        for (int i = lane; i < ((nb + 31) >> 5); i += 32) fany |= sm.fpl[IDX(i, BIT_WORDS)];
         has_f = __any_sync(FULL, fany != 0);
     }
     if (MS) {
@@ -499,7 +515,7 @@ __device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp
             } else {
                 if (rc < 1) return SDB_ST_OK;
                 if (!MS || no > 0) {              /* MS keeps the old bits when ret_bits is empty (:218) */
-                    for (int w = lane; w < BIT_WORDS; w += 32) sm.val[w] = sm.tmp[w];
+                    for (int w = lane; w < BIT_WORDS; w += 32) sm.val[IDX(w, BIT_WORDS)] = sm.tmp[IDX(w, BIT_WORDS)];
                     nb = no;
                 }
             }
@@ -573,7 +589,7 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
         #pragma unroll 1
         for (int r0 = 0; r0 < nwords; r0 += 32) {
             const int wi = r0 + lane;
-            uint32_t x = sm.dig[min(wi, DIG_WORDS - 2)], nx = sm.dig[min(wi + 1, DIG_WORDS - 1)];
+            uint32_t x = sm.dig[IDX(min(wi, DIG_WORDS - 2), DIG_WORDS)], nx = sm.dig[IDX(min(wi + 1, DIG_WORDS - 1), DIG_WORDS)];
             uint32_t y = __funnelshift_r(x, nx, 4);                /* windows at odd positions */
             uint32_t be = eq_bytes(x, k1) | eq_bytes(x, k0) | eq_bytes(x, kf);
             uint32_t bo = eq_bytes(y, k1) | eq_bytes(y, k0) | eq_bytes(y, kf);
@@ -666,15 +682,15 @@ __device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int
                 else one = true;
             }
             uint32_t vw = __ballot_sync(FULL, one), fw = __ballot_sync(FULL, isf);
-            if (lane == 0) { sm.val[b0 >> 5] = vw; sm.fpl[b0 >> 5] = fw; }
+            if (lane == 0) { sm.val[IDX(b0 >> 5, BIT_WORDS)] = vw; sm.fpl[IDX(b0 >> 5, BIT_WORDS)] = fw; }
         }
         __syncwarp();
         for (int wq = lane; wq < BIT_WORDS; wq += 32)
-            if (wq >= ((n + 31) >> 5)) { sm.val[wq] = 0; sm.fpl[wq] = 0; }
+            if (wq >= ((n + 31) >> 5)) { sm.val[IDX(wq, BIT_WORDS)] = 0; sm.fpl[IDX(wq, BIT_WORDS)] = 0; }
         __syncwarp();
         if (lane == 0) {
-            if (tail == 0) sm.val[n >> 5] |= 1u << (n & 31);
-            else if (tail == 2) sm.fpl[n >> 5] |= 1u << (n & 31);
+            if (tail == 0) sm.val[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
+            else if (tail == 2) sm.fpl[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
         }
         int st = finish_match<false>(A, pp, nch, ordinal, hasf);
         if (st != SDB_ST_OK) return st;
@@ -699,8 +715,8 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
     const int L = k->len, K = k->nuniq;
     const uint32_t uidx = k->uidx, ids = sm.pat_ids;
     /* candidate slots of the (<= 2) distinct values (:73-76): looked up in the per-message mask table */
-    const uint32_t ca = sm.M[k->vidx[0]];
-    const uint32_t cb = K > 1 ? sm.M[k->vidx[1]] : 0u;
+    const uint32_t ca = sm.M[IDX(k->vidx[0], SDB_MAX_VALS)];
+    const uint32_t cb = K > 1 ? sm.M[IDX(k->vidx[1], SDB_MAX_VALS)] : 0u;
     if (!ca || (K > 1 && !cb)) return false;                  /* :78-80 */
     if (!(ca & (ca - 1)) && !(cb & (cb - 1))) {
         /* the common case: one candidate per value -> a single combination, no ordering needed */
@@ -714,11 +730,11 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
             d0 = (uidx & 3) ? db : da; d1 = ((uidx >> 2) & 3) ? db : da;
         }
         if (L == 1) {
-            if (sm.last1[d0] <= (uint32_t)from) return false;
-            code = (uint32_t)d0; pos = (int)sm.first1[d0];
+            if (sm.last1[IDX(d0, 12)] <= (uint32_t)from) return false;
+            code = (uint32_t)d0; pos = (int)sm.first1[IDX(d0, 12)];
         } else {
-            if (sm.last2[d0 * 10 + d1] <= (uint32_t)from) return false;
-            code = (uint32_t)(d0 | (d1 << 4)); pos = (int)sm.first2[d0 * 10 + d1];
+            if (sm.last2[IDX(d0 * 10 + d1, 100)] <= (uint32_t)from) return false;
+            code = (uint32_t)(d0 | (d1 << 4)); pos = (int)sm.first2[IDX(d0 * 10 + d1, 100)];
         }
         return true;
     }
@@ -729,7 +745,7 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
         const uint16_t *__restrict__ rank = sm.rank;
         const int lo0 = k->lo[0], lo1 = K > 1 ? k->lo[1] : 0;
         const uint32_t ro0 = k->rank_off[0], ro1 = K > 1 ? k->rank_off[1] : 0;
-        const int16_t *trow = sm.T[clk_idx];
+        const int16_t *trow = sm.T[IDX(clk_idx, SDB_MAX_CLK)];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int tj = trow[j];
@@ -745,8 +761,8 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
         const int da = (ids >> (4 * sa)) & 0xF;
         if (K == 1) {
             bool ok;
-            if (L == 1) { ok = sm.last1[da] > (uint32_t)from; if (ok) { code = da; pos = (int)sm.first1[da]; } }
-            else { ok = sm.last2[da * 11] > (uint32_t)from; if (ok) { code = da * 0x11; pos = (int)sm.first2[da * 11]; } }
+            if (L == 1) { ok = sm.last1[IDX(da, 12)] > (uint32_t)from; if (ok) { code = da; pos = (int)sm.first1[IDX(da, 12)]; } }
+            else { ok = sm.last2[IDX(da * 11, 100)] > (uint32_t)from; if (ok) { code = da * 0x11; pos = (int)sm.first2[IDX(da * 11, 100)]; } }
             if (ok) return true;
             continue;
         }
@@ -761,9 +777,9 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
             if (sb == sa) continue;                           /* :114 one id for two values */
             const int db = (ids >> (4 * sb)) & 0xF;
             const int d0 = (uidx & 3) ? db : da, d1 = ((uidx >> 2) & 3) ? db : da;   /* :118-127 */
-            if (sm.last2[d0 * 10 + d1] > (uint32_t)from) {    /* :133 */
+            if (sm.last2[IDX(d0 * 10 + d1, 100)] > (uint32_t)from) {    /* :133 */
                 code = (uint32_t)(d0 | (d1 << 4));
-                pos = (int)sm.first2[d0 * 10 + d1];
+                pos = (int)sm.first2[IDX(d0 * 10 + d1, 100)];
                 return true;
             }
         }
@@ -800,9 +816,9 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
     /* a match needs regex_min consecutive symbols, all at positions of one parity: count them (necessary condition) */
     {
         const uint32_t c1 = (acc >> 8) & 0xFF, c0 = (acc >> 16) & 0xFF, cf = acc >> 24;
-        uint32_t cnt = sm.cnt2[(c1 & 15) * 10 + (c1 >> 4)];
-        if (pp->key[2].len && c0 != c1) cnt += sm.cnt2[(c0 & 15) * 10 + (c0 >> 4)];
-        if (hasf && cf != c1 && cf != c0) cnt += sm.cnt2[(cf & 15) * 10 + (cf >> 4)];
+        uint32_t cnt = sm.cnt2[IDX((c1 & 15) * 10 + (c1 >> 4), 100)];
+        if (pp->key[2].len && c0 != c1) cnt += sm.cnt2[IDX((c0 & 15) * 10 + (c0 >> 4), 100)];
+        if (hasf && cf != c1 && cf != c0) cnt += sm.cnt2[IDX((cf & 15) * 10 + (cf >> 4), 100)];
         const int best = max((int)(cnt & 0xFFFF), (int)(cnt >> 16));
         if (best < (int)pp->regex_min) return 0;
     }
@@ -862,7 +878,7 @@ __device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int
 
     /* chunk loop (:174-189): class per chunk = '1' / '0' / 'F' / skip (sync string) / stop */
     __syncwarp();
-    for (int i = lane; i < BIT_WORDS; i += 32) { sm.val[i] = 0; sm.fpl[i] = 0; }
+    for (int i = lane; i < BIT_WORDS; i += 32) { sm.val[IDX(i, BIT_WORDS)] = 0; sm.fpl[IDX(i, BIT_WORDS)] = 0; }
     __syncwarp();
     int nb = 0;
     const int nchunks = (dlen - ms + w - 1) / w;
@@ -904,8 +920,8 @@ __device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int
             bool mine = (emitm >> lane) & 1;
             if (mine) {
                 int idx = nb + __popc(emitm & ((1u << lane) - 1));
-                if ((onem >> lane) & 1) atomicOr(&sm.val[idx >> 5], 1u << (idx & 31));
-                if ((fm >> lane) & 1) atomicOr(&sm.fpl[idx >> 5], 1u << (idx & 31));
+                if ((onem >> lane) & 1) atomicOr(&sm.val[IDX(idx >> 5, BIT_WORDS)], 1u << (idx & 31));
+                if ((fm >> lane) & 1) atomicOr(&sm.fpl[IDX(idx >> 5, BIT_WORDS)], 1u << (idx & 31));
             }
             nb += __popc(emitm);
         }
@@ -926,7 +942,7 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
         uint4 v = __ldg(&src[lane]);
         reinterpret_cast<uint4 *>(sm.dig)[lane] = v;
     }
-    if (lane < 4) sm.dig[4 * nq + lane] = FULL;    /* windows may read 3 words past the last digit */
+    if (lane < 4) sm.dig[IDX(4 * nq + lane, DIG_WORDS)] = FULL;    /* windows may read 3 words past the last digit */
     if (lane < 8) sm.pat[lane] = m->pat[lane];
     if (lane == 0) {
         sm.rank = A.tab.rank; sm.dlen = dlen; sm.npat = m->npat; sm.pat_ids = m->pat_ids; sm.msg = A.msg_base + mi;
@@ -938,8 +954,8 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
 __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
 {
     const int lane = lane_id();
-    for (int i = lane; i < 100; i += 32) { sm.first2[i] = NONE32; sm.last2[i] = 0; sm.cnt2[i] = 0; }
-    if (lane < 12) { sm.first1[lane] = NONE32; sm.last1[lane] = 0; }
+    for (int i = lane; i < 100; i += 32) { sm.first2[IDX(i, 100)] = NONE32; sm.last2[IDX(i, 100)] = 0; sm.cnt2[IDX(i, 100)] = 0; }
+    if (lane < 12) { sm.first1[IDX(lane, 12)] = NONE32; sm.last1[IDX(lane, 12)] = 0; }
     stage_digits(A, sm, m, dlen, mi);
     /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
     for (int base = 0; base < dlen; base += 32) {
@@ -951,17 +967,17 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
         uint32_t ga = __match_any_sync(FULL, va ? a : 16 + lane);
         uint32_t gb = __match_any_sync(FULL, vb ? a * 10 + b : 128 + lane);
         if (va) {
-            if (lane == __ffs(ga) - 1 && sm.first1[a] == NONE32) sm.first1[a] = p;
-            if (lane == 31 - __clz(ga)) sm.last1[a] = p + 1;
+            if (lane == __ffs(ga) - 1 && sm.first1[IDX(a, 12)] == NONE32) sm.first1[IDX(a, 12)] = p;
+            if (lane == 31 - __clz(ga)) sm.last1[IDX(a, 12)] = p + 1;
         }
         if (vb) {
             int code = a * 10 + b;
             if (lane == __ffs(gb) - 1) {
-                if (sm.first2[code] == NONE32) sm.first2[code] = p;
+                if (sm.first2[IDX(code, 100)] == NONE32) sm.first2[IDX(code, 100)] = p;
                 /* base is a multiple of 32, so lane parity == position parity */
-                sm.cnt2[code] += (uint32_t)__popc(gb & 0x55555555u) | ((uint32_t)__popc(gb & 0xAAAAAAAAu) << 16);
+                sm.cnt2[IDX(code, 100)] += (uint32_t)__popc(gb & 0x55555555u) | ((uint32_t)__popc(gb & 0xAAAAAAAAu) << 16);
             }
-            if (lane == 31 - __clz(gb)) sm.last2[code] = p + 1;
+            if (lane == 31 - __clz(gb)) sm.last2[IDX(code, 100)] = p + 1;
         }
         __syncwarp();
     }
@@ -982,7 +998,7 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
 __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &rec)
 {
     WarpSm &sm = SM();
-    const int t_slot = sm.T[pp->clk_idx][lane_id() & 7];
+    const int t_slot = sm.T[IDX(pp->clk_idx, SDB_MAX_CLK)][lane_id() & 7];
     int s0 = 0, dummy;
     uint64_t start_t = 0, t1 = 0, t0 = 0, tf = 0;
     if (pp->key[0].len && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return false;      /* :67-88 */
@@ -1000,7 +1016,7 @@ __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &r
 __device__ __noinline__ bool resolve_ms_warp(const SdbPulseProto *pp, SdbSurv &rec)
 {
     WarpSm &sm = SM();
-    const int t_slot = sm.T[0][lane_id() & 7];
+    const int t_slot = sm.T[IDX(0, SDB_MAX_CLK)][lane_id() & 7];
     const int w = pp->width;
     uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
     int spos = 0, dummy;
@@ -1032,7 +1048,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
         clock_abs = fabs((double)pc);
         /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
         const int t = (lane & 7) < npat ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
-        if (lane < 8) sm.T[0][lane] = (int16_t)t;
+        if (lane < 8) sm.T[IDX(0, SDB_MAX_CLK)][lane] = (int16_t)t;
         v0 = (int)A.tab.n_mu_vals; v1 = (int)A.tab.n_vals;          /* the MS intervals follow the MU pairs */
     } else {
         /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
@@ -1040,7 +1056,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
 #pragma unroll 1
         for (int idx = lane; idx < ncl * 8; idx += 32) {
             int c = idx >> 3, j = idx & 7;
-            sm.T[c][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
+            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
         }
         v0 = 0; v1 = (int)A.tab.n_mu_vals;
     }
@@ -1049,7 +1065,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
 #pragma unroll 1
     for (int v = v0 + lane; v < v1; v += 32) {
         const SdbValRow vr = A.tab.vals[v];
-        const int4 row = *reinterpret_cast<const int4 *>(&sm.T[vr.clk_idx][0]);
+        const int4 row = *reinterpret_cast<const int4 *>(&sm.T[IDX(vr.clk_idx, SDB_MAX_CLK)][0]);
         const int lo = vr.lo, hi = vr.hi;
         int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
         int t4 = (int16_t)(row.z & 0xffff), t5 = row.z >> 16, t6 = (int16_t)(row.w & 0xffff), t7 = row.w >> 16;
@@ -1057,7 +1073,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
                       ((uint32_t)(t2 >= lo && t2 <= hi) << 2) | ((uint32_t)(t3 >= lo && t3 <= hi) << 3) |
                       ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
                       ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
-        sm.M[v] = (uint8_t)mk;                                       /* empty slots hold -32768 and never qualify */
+        sm.M[IDX(v, SDB_MAX_VALS)] = (uint8_t)mk;                                       /* empty slots hold -32768 and never qualify */
     }
     __syncwarp();
     return true;
@@ -1078,7 +1094,10 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
         const SdbPulseMsg *m = &A.msgs[mi];
         const int dlen = m->dlen;
         uint32_t nsurv = 0;
-        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS) {
+        /* records outside the packed domain (ids > 9, > 8 slots, D too long) yield no hits instead of undefined lookups */
+        const bool ids_ok = m->npat <= SDB_MAX_SLOTS &&
+                            !__any_sync(FULL, lane < m->npat && ((m->pat_ids >> (4 * (lane & 7))) & 0xF) > 9);
+        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS && ids_ok) {
             stage_message(A, sm, m, dlen, mi);
             double clock_abs = 0.0;
             if (prepare_tables<MS>(A, sm, m, clock_abs)) {
@@ -1095,14 +1114,14 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                         const SdbPrefilter *pf = &pfs[q];
                         const int nreq = pf->nreq;
                         ok = true;
-                        for (int r = 0; r < nreq; r++) ok = ok && sm.M[pf->vreq[r]] != 0;
+                        for (int r = 0; r < nreq; r++) ok = ok && sm.M[IDX(pf->vreq[r], SDB_MAX_VALS)] != 0;
                         if (MS && ok) {
                             const double pclk = rows[q].clock;
                             ok = !(pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3));
                         }
                     }
                     const uint32_t bal = __ballot_sync(FULL, ok);
-                    if (ok) sm.plist[nalive + __popc(bal & ((1u << lane) - 1))] = (uint8_t)q;
+                    if (ok) sm.plist[IDX(nalive + __popc(bal & ((1u << lane) - 1)), 256)] = (uint8_t)q;
                     nalive += __popc(bal);
                 }
                 __syncwarp();
@@ -1110,7 +1129,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
 #pragma unroll 1
                 for (uint32_t q0 = 0; q0 < nalive; q0 += 32) {
                     const bool have = q0 + lane < nalive;
-                    const uint32_t q = have ? sm.plist[q0 + lane] : 0;
+                    const uint32_t q = have ? sm.plist[IDX(q0 + lane, 256)] : 0;
                     int state = 0;
                     SdbSurv rec;
                     rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
@@ -1135,6 +1154,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                     const uint32_t alive = __ballot_sync(FULL, state == 1);
                     if (state == 1) {                                 /* protocol-table order is the slot order */
                         rec.start |= (uint64_t)q << 56;
+                        SDB_CHK(nsurv + __popc(alive & ((1u << lane) - 1)) < A.surv_stride);
                         slots[nsurv + __popc(alive & ((1u << lane) - 1))] = rec;
                     }
                     nsurv += __popc(alive);
@@ -1209,11 +1229,11 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
                 if (!sm.overflow) {
                     if (hb + nh <= A.hits_cap && wb + nw <= A.bits_cap) {
                         for (uint32_t i = lane; i < nh; i += 32) {
-                            SdbHit h = sm.st_hits[i];
+                            SdbHit h = sm.st_hits[IDX(i, ST_HITS)];
                             h.bits_off += wb;
                             A.hits[hb + i] = h;
                         }
-                        for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[i];
+                        for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[IDX(i, ST_WORDS)];
                     }
                 } else {
                     /* rare: more output than the staging area holds -> scan again, writing in place */
@@ -1267,6 +1287,19 @@ int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_
     if (n_in > (uint32_t)(BIT_WORDS * 32)) return -1;
     unit_postdemod_kernel<<<1, 32, 0, stream>>>(method, d_in, n_in, d_out, out_cap, d_res);
     return (int)cudaGetLastError();
+}
+
+unsigned int debug_violations(bool reset)
+{
+#ifdef SDB_BOUNDS_CHECK
+    unsigned int v = 0, z = 0;
+    cudaMemcpyFromSymbol(&v, g_sdb_oob, sizeof v);
+    if (reset) cudaMemcpyToSymbol(g_sdb_oob, &z, sizeof z);
+    return v;
+#else
+    (void)reset;
+    return 0xFFFFFFFFu;      /* not a checked build */
+#endif
 }
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,

@@ -17,6 +17,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
                  SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream);
 int pulse_blocks_per_sm(int kind);
+unsigned int debug_violations(bool reset);   /* bounds-check build only; 0xFFFFFFFF otherwise */
 size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots handed from mu_resolve_kernel to mu_scan_kernel */
 
 #define SDB_MU_CHUNK 262144u    /* messages per resolve/scan launch pair (bounds the survivor scratch: chunk * n_mu * 16 B) */
