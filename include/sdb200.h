@@ -178,6 +178,19 @@ int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_
                        uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode);
 
 /*
+ * One mcBit2* / mcRaw call (sd_protocols/manchester.py:207-795, helpers.py:90-122) on a bit string given as one
+ * byte per bit, with the length rules of protocol `proto` (table-order index) and the caller's mcbitnum.
+ * proto == 0xFFFFFFFF: an id that is not in the table (every property takes the reference's default; bit 8 of
+ * method_override says the id is 119).  method_override & 0xFF != 0 runs that SDB_M_* decoder instead of the
+ * protocol's own.  rcode: 1 ok, -1 rejected
+ * (`reason` = SDB_MCR_* code), <= -100: the reference raises (-(100 + SDB_ST_*)).  For mcBit2TFA the duplicate
+ * parts are concatenated in bits_out and seg[] holds their lengths.
+ */
+int sdb_unit_mc(SdbHandle *h, uint32_t proto, int method_override, const uint8_t *bits, uint32_t n, int mcbitnum,
+                uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int32_t *seg, uint32_t seg_cap,
+                uint32_t *n_seg, int *rcode, int *reason);
+
+/*
  * Bounds-check build only (libsdb200_chk.so, -DSDB_BOUNDS_CHECK): number of out-of-range shared-memory
  * indices the kernels have seen so far (compute-sanitizer is not available on the GPU pool).
  * Returns 0xFFFFFFFF from the normal build.

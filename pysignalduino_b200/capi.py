@@ -29,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod", "sdb_debug_violations",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations",
 ]
 
 
@@ -75,6 +75,10 @@ def load_library() -> C.CDLL:
     L.sdb_unit_postdemod.restype = C.c_int
     L.sdb_unit_postdemod.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.sdb_unit_mc.restype = C.c_int
+    L.sdb_unit_mc.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32,
+                              C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                              C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
@@ -190,6 +194,27 @@ class Engine:
             if rc != SDB_OK:
                 raise self._err(rc, "sdb_format_hits")
             return pool[: used.value].tobytes(), off
+
+    def unit_mc(self, proto_index: int, bits: str, mcbitnum: int, method_override: int = 0):
+        """One mcBit2* call on the device: -> (rcode, reason, [bit strings])."""
+        a = np.frombuffer(bits.encode("ascii"), dtype=np.uint8) - ord("0")
+        a = np.ascontiguousarray(a.astype(np.uint8))
+        out = np.zeros(4096, dtype=np.uint8)
+        seg = np.zeros(64, dtype=np.int32)
+        n_out, n_seg, rcode, reason = C.c_uint32(0), C.c_uint32(0), C.c_int(0), C.c_int(0)
+        rc = self.lib.sdb_unit_mc(self.h, proto_index, method_override, a.ctypes.data if len(a) else None, len(a), mcbitnum,
+                                  out.ctypes.data, len(out), C.byref(n_out), seg.ctypes.data, len(seg), C.byref(n_seg),
+                                  C.byref(rcode), C.byref(reason))
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_unit_mc")
+        s = "".join("01"[v] for v in out[: n_out.value])
+        if n_seg.value:
+            parts, o = [], 0
+            for ln in seg[: n_seg.value]:
+                parts.append(s[o : o + int(ln)])
+                o += int(ln)
+            return rcode.value, reason.value, parts
+        return rcode.value, reason.value, [s]
 
     def debug_violations(self, reset: bool = False) -> int:
         """Out-of-range index count of the bounds-check build (0xFFFFFFFF from the normal build)."""

@@ -409,3 +409,27 @@ extern "C" int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_
     if (no && bits_out) { CK(cudaMemcpy(bits_out, d_out, no, cudaMemcpyDeviceToHost)); }
     return SDB_OK;
 }
+
+extern "C" int sdb_unit_mc(SdbHandle *h, uint32_t proto, int method_override, const uint8_t *bits, uint32_t n, int mcbitnum,
+                           uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int32_t *seg, uint32_t seg_cap,
+                           uint32_t *n_seg, int *rcode, int *reason)
+{
+    if (!h || !n_out || !n_seg || !rcode || !reason || (n && !bits)) return SDB_E_ARG;
+    if (n > SDB_MAX_HEX * 4 || out_cap > 4096 || (proto >= h->tab.nproto && proto != 0xFFFFFFFFu)) return set_err(h, SDB_E_ARG, "sdb_unit_mc: bad argument");
+    CK(cudaSetDevice(h->device));
+    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 4096;
+    int32_t *d_seg = reinterpret_cast<int32_t *>(h->d_unit + 8192);      /* <= 48 segments */
+    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 12288);
+    if (n) CK(cudaMemcpyAsync(d_in, bits, n, cudaMemcpyHostToDevice, h->stream));
+    int rc = sdb::launch_unit_mc(h->tab, proto, method_override, d_in, (int)n, mcbitnum, d_out, (int)out_cap, d_seg, d_res, h->stream);
+    if (rc != 0) return set_err(h, rc < 0 ? SDB_E_ARG : SDB_E_CUDA, "unit mc launch", rc > 0 ? static_cast<cudaError_t>(rc) : cudaSuccess);
+    int32_t res[4];
+    CK(cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *rcode = res[0]; *reason = res[1];
+    uint32_t no = res[2] > 0 ? (uint32_t)res[2] : 0, ns = res[3] > 0 ? (uint32_t)res[3] : 0;
+    *n_out = no; *n_seg = ns;
+    if (no && bits_out) CK(cudaMemcpy(bits_out, d_out, no < out_cap ? no : out_cap, cudaMemcpyDeviceToHost));
+    if (ns && seg) CK(cudaMemcpy(seg, d_seg, sizeof(int32_t) * (ns < seg_cap ? ns : seg_cap), cudaMemcpyDeviceToHost));
+    return SDB_OK;
+}

@@ -52,18 +52,6 @@ struct McBits {
     bool inv;
     __device__ __forceinline__ int nib(int i) const { int x = h.at(lead + i); return inv ? 15 - x : x; }
     __device__ __forceinline__ int bit(int i) const { return (nib(i >> 2) >> (3 - (i & 3))) & 1; }
-    /* str.find(pattern of m bits MSB-first, from) */
-    __device__ int find(uint32_t pat, int m, int from) const
-    {
-        if (from < 0) from = 0;
-        uint32_t acc = 0, mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1);
-        int have = 0;
-        for (int i = from; i < n; i++) {
-            acc = ((acc << 1) | (uint32_t)bit(i)) & mask;
-            if (++have >= m && acc == pat) return i - m + 1;
-        }
-        return -1;
-    }
 };
 
 struct Res {
@@ -97,13 +85,225 @@ __device__ void emit_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, uint16_t pr
 /* helpers.length_in_range — helpers.py:124-166 */
 __device__ __forceinline__ bool in_range(const SdbHexProto &p, int n)
 {
+    if (!(p.flags & SDB_HF_EXISTS)) return false;                        /* 'protocol does not exists' */
     int mn = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : -1;
     if (mn != -1 && n < mn) return false;
     if ((p.flags & SDB_HF_HAS_MAX) && n > p.length_max) return false;
     return true;
 }
 
-/* ---- MC: returns SDB_ST_* ---------------------------------------------------------------- */
+/* ---- MC decoders, generic over the bit source (hex nibbles in the batch path, bytes in the unit-op path) ----
+ * Reason codes of a rejected frame; the host turns them into the reference's message strings. */
+#define SDB_MCR_NONE 0
+#define SDB_MCR_TOO_SHORT 1        /* 'message is too short' */
+#define SDB_MCR_TOO_LONG 2         /* 'message is too long' */
+#define SDB_MCR_WRONG_BEGIN 3      /* 'wrong bits at begin' */
+#define SDB_MCR_PARITY 4           /* 'parity error' */
+#define SDB_MCR_CHECKSUM 5         /* 'checksum error' */
+#define SDB_MCR_NO_START 6         /* '<name>: lib/mcBit2Sainlogic, start 010100 not found' */
+#define SDB_MCR_NOT_32 7           /* 'message must be 32 bits, got <n>' */
+#define SDB_MCR_NOT_56 8           /* 'message must be 56 bits, got <n>' */
+#define SDB_MCR_NO_SYNC 9          /* 'sync not found' */
+#define SDB_MCR_NO_DUP 10          /* ' no duplicate found' (+ SDB_MCR_DUP_SHORT / _LONG: ', message is too short/long') */
+#define SDB_MCR_LOOP 11            /* 'loop error, please report this data <bits>' */
+#define SDB_MCR_DUP_SHORT 0x100
+#define SDB_MCR_DUP_LONG 0x200
+#define SDB_MCR_DUP_NOPROTO 0x400
+
+/* bit string given as one byte per bit (unit-op path: mcBit2*(name, bit_data, protocol_id, mcbitnum)) */
+struct ByteBits {
+    const uint8_t *b;
+    int n;
+    __device__ __forceinline__ int bit(int i) const { return b[i] & 1; }
+};
+
+/* str.find(pattern of m bits MSB-first, from) */
+template <class Bits>
+__device__ int find_bits(const Bits &B, uint32_t pat, int m, int from)
+{
+    if (from < 0) from = 0;
+    uint32_t acc = 0, mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1);
+    int have = 0;
+    for (int i = from; i < B.n; i++) {
+        acc = ((acc << 1) | (uint32_t)B.bit(i)) & mask;
+        if (++have >= m && acc == pat) return i - m + 1;
+    }
+    return -1;
+}
+
+#define SDB_TFA_MAX 48
+struct TfaOut { int start[SDB_TFA_MAX], len[SDB_TFA_MAX], n; };
+
+/*
+ * One mcBit2* / mcRaw call (manchester.py:207-795, helpers.py:90-122) on bit string B with the caller's mcbitnum.
+ * Returns 1 (R = result bits, or T = list of duplicate parts for TFA), -1 (reason set), or -(100 + SDB_ST_*)
+ * when the reference raises.
+ */
+template <class Bits>
+__device__ int mc_decode(const SdbHexProto &p, const Bits &B, int mcbitnum, Res &R, TfaOut &T, int &reason)
+{
+    const int n = B.n;                                                   /* len(bit_data) */
+    const int lmin = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : -1;
+    const int lmax = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 9999;
+    reason = SDB_MCR_NONE;
+    T.n = 0;
+    R.clear();
+    switch (p.method) {
+    case SDB_M_HIDEKI: case SDB_M_MAVERICK: case SDB_M_OSV1: case SDB_M_OSV2O3: case SDB_M_OSPIR:   /* :418-586 */
+        if (mcbitnum < lmin) { reason = SDB_MCR_TOO_SHORT; return -1; }
+        if (mcbitnum > lmax) { reason = SDB_MCR_TOO_LONG; return -1; }
+        for (int i = 0; i < n; i++) R.push(B.bit(i));
+        return 1;
+    case SDB_M_MCRAW_MANCHESTER: {                                       /* :588-613 */
+        int mx = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 0;
+        if (mcbitnum > mx) { reason = SDB_MCR_TOO_LONG; return -1; }
+        for (int i = 0; i < n; i++) R.push(B.bit(i));
+        return 1;
+    }
+    case SDB_M_MCRAW_HELPERS:                                            /* helpers.py:90-122 */
+        if (p.flags & SDB_HF_HAS_MAX) {
+            if (p.flags & SDB_HF_MAX_IS_STR) return -(100 + SDB_ST_TYPEERROR);   /* int > str */
+            if (mcbitnum > p.length_max) { reason = SDB_MCR_TOO_LONG; return -1; }
+        }
+        for (int i = 0; i < n; i++) R.push(B.bit(i));
+        return 1;
+    case SDB_M_GROTHE:                                                   /* :721-754 */
+        if (mcbitnum != 32) { reason = SDB_MCR_NOT_32; return -1; }
+        for (int i = 0; i < n; i++) R.push(B.bit(i));
+        return 1;
+    case SDB_M_SOMFY: {                                                  /* :756-795 */
+        int from = 0, len = n;
+        if (mcbitnum == 57) { from = n > 0 ? 1 : 0; len = n > 57 ? 56 : (n > 0 ? n - 1 : 0); }   /* bit_data[1:57] */
+        if (len != 56) { reason = SDB_MCR_NOT_56; return -1; }
+        for (int i = 0; i < 56; i++) R.push(B.bit(from + i));
+        return 1;
+    }
+    case SDB_M_AS: {                                                     /* :356-416 */
+        int sp = n >= 16 ? find_bits(B, 0xC, 4, 16) : -1;
+        if (sp >= 0) {
+            int ep = find_bits(B, 0xC, 4, sp + 16);
+            if (ep < 0) ep = n;
+            int ml = ep - sp;
+            if (ml < lmin) { reason = SDB_MCR_TOO_SHORT; return -1; }
+            if (ml > lmax) { reason = SDB_MCR_TOO_LONG; return -1; }
+            for (int i = sp; i < n; i++) R.push(B.bit(i));
+        } else {
+            if (mcbitnum < lmin) { reason = SDB_MCR_TOO_SHORT; return -1; }
+            if (mcbitnum > lmax) { reason = SDB_MCR_TOO_LONG; return -1; }
+            for (int i = 0; i < n; i++) R.push(B.bit(i));
+        }
+        return 1;
+    }
+    case SDB_M_SAINLOGIC: {                                              /* :302-354 */
+        int mx = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 0;
+        if (mcbitnum > mx) { reason = SDB_MCR_TOO_LONG; return -1; }
+        int ones = 0, total = n, mb = mcbitnum;
+        if (mcbitnum < 128) {
+            int start = find_bits(B, 0x14, 6, 0);                        /* '010100' */
+            if (start < 0 || start > 10) { reason = SDB_MCR_NO_START; return -1; }
+            ones = 10 - start;                                           /* prepend '1' until the sync sits at 10 */
+            total = min(128, n + ones);
+            mb = total;                                                  /* mcbitnum = len(bit_data) */
+        }
+        int mn = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : 0;
+        if (mb < mn) { reason = SDB_MCR_TOO_SHORT; return -1; }
+        for (int i = 0; i < total; i++) R.push(i < ones ? 1 : B.bit(i - ones));
+        return 1;
+    }
+    case SDB_M_FUNKBUS: {                                                /* :207-300 */
+        if (mcbitnum < lmin) { reason = SDB_MCR_TOO_SHORT; return -1; }
+        if ((p.flags & SDB_HF_HAS_MAX) && mcbitnum > p.length_max) { reason = SDB_MCR_TOO_LONG; return -1; }
+        /* differential manchester (helpers.py:6-26): s[k] = (b[k] == b[k+1]), k < n-1 */
+        const int ns = n > 0 ? n - 1 : 0;
+        int tl, off, plen;     /* t = prefix + s[off:], prefix '001' (119) or '0' */
+        if (p.flags & SDB_HF_IS_119) {
+            int pos = -1;
+            uint32_t acc = 0;
+            for (int k = 0; k < ns && k < 9; k++) {                      /* '01100' must start at 0..4 */
+                acc = ((acc << 1) | (uint32_t)(B.bit(k) == B.bit(k + 1))) & 0x1F;
+                if (k >= 4 && acc == 0x0C) { pos = k - 4; break; }
+            }
+            if (pos < 0) { reason = SDB_MCR_WRONG_BEGIN; return -1; }
+            off = pos; plen = 3; tl = 3 + ns - pos;
+            if (tl < 48) { reason = SDB_MCR_WRONG_BEGIN; return -1; }
+        } else { off = 0; plen = 1; tl = 1 + ns; }
+        int xorv = 0, chk = 0, parity = 0;
+        for (int i = 0; i < 6; i++) {
+            int from = i * 8, to = min(from + 8, tl);
+            if (from >= to) return -(100 + SDB_ST_VALUEERROR);           /* int('', 2) */
+            int data = 0;
+            for (int k = from; k < to; k++) {
+                int b;
+                if (k < plen) b = (plen == 3 && k == 2) ? 1 : 0;
+                else { int si = off + (k - plen); b = (B.bit(si) == B.bit(si + 1)); }
+                data = (data << 1) | b;
+            }
+            for (int k = 7; k >= 0; k--) R.push((data >> k) & 1);        /* f"{data:02X}" */
+            if (i < 5) xorv ^= data;
+            else { chk = data & 0x0F; xorv ^= data & 0xE0; data &= 0xF0; }
+            parity ^= __popc(data) & 1;
+        }
+        if (parity) { reason = SDB_MCR_PARITY; return -1; }
+        int xn = ((xorv & 0xF0) >> 4) ^ (xorv & 0x0F), r = 0;
+        if (xn & 8) r ^= 0xC;
+        if (xn & 4) r ^= 0x2;
+        if (xn & 2) r ^= 0x8;
+        if (xn & 1) r ^= 0x3;
+        if (r != chk) { reason = SDB_MCR_CHECKSUM; return -1; }
+        return 1;
+    }
+    case SDB_M_TFA: {                                                    /* :615-719 */
+        int f = find_bits(B, 0xFFD, 12, 0);                              /* '111111111101' */
+        if (f < 0) { reason = SDB_MCR_NO_SYNC; return -1; }
+        int pre = f + 12, mend = -1, it = 1, nm = 0, last_fail = 0;
+        int ps[SDB_TFA_MAX], pl[SDB_TFA_MAX];
+        while (mend < mcbitnum) {
+            mend = (pre >= 0 && pre <= n) ? find_bits(B, 0x1FFD, 13, pre) : -1;   /* '1111111111101' */
+            if (mend < pre) mend = mcbitnum;
+            int ml = mend - pre;
+            if (in_range(p, ml)) {
+                /* bit_data[pre:mend] is clipped to the data that exists */
+                int e = mend < n ? mend : n, s = pre < n ? pre : n;
+                if (nm < SDB_TFA_MAX) { ps[nm] = s; pl[nm] = e > s ? e - s : 0; nm++; }
+            } else {
+                int mn = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : -1;
+                last_fail = !(p.flags & SDB_HF_EXISTS) ? SDB_MCR_DUP_NOPROTO
+                            : (mn != -1 && ml < mn) ? SDB_MCR_DUP_SHORT : SDB_MCR_DUP_LONG;
+            }
+            int q = mend <= n ? find_bits(B, 0xD, 4, mend) : -1;         /* '1101' */
+            if (q >= 0) pre = q + 4; else { pre = -1; mend = mcbitnum; }
+            it++;
+        }
+        if (it == 10) { reason = SDB_MCR_LOOP; return -1; }
+        /* :706-711: every element whose hex string was seen exactly once before */
+        int seen[SDB_TFA_MAX];
+        for (int a = 0; a < nm; a++) {
+            int first = a;
+            for (int b = 0; b < a; b++) {
+                /* hex strings equal <=> same digit count and same right-aligned value */
+                if (((pl[a] + 3) >> 2) != ((pl[b] + 3) >> 2)) continue;
+                int la = pl[a], lb = pl[b], L = max(la, lb);
+                bool eq = true;
+                for (int k = 0; k < L && eq; k++) {
+                    int ia = la - 1 - k, ib = lb - 1 - k;
+                    int ba = ia >= 0 ? B.bit(ps[a] + ia) : 0, bb = ib >= 0 ? B.bit(ps[b] + ib) : 0;
+                    eq = ba == bb;
+                }
+                if (eq) { first = b; break; }
+            }
+            seen[a] = 0;
+            if (seen[first] == 1) { T.start[T.n] = ps[a]; T.len[T.n] = pl[a]; T.n++; }
+            seen[first]++;
+        }
+        if (T.n == 0) { reason = SDB_MCR_NO_DUP | last_fail; return -1; }
+        return 1;
+    }
+    default:
+        return -1;
+    }
+}
+
+/* ---- MC batch path: returns SDB_ST_* ------------------------------------------------------- */
 __device__ int mc_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMsg &m)
 {
     const SdbHexProto p = A.tab.hex[m.proto];
@@ -126,166 +326,64 @@ __device__ int mc_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMs
 
     McBits B;
     B.h.d = A.digits + (size_t)m.doff * 16; B.h.n = m.hlen; B.inv = inv; B.lead = 0;
-    while (B.lead < m.hlen - 1 && B.nib(0) == 0) B.lead++;               /* helpers.py:183-186 */
-    /* note: nib(0) is relative to lead, so the loop above re-reads the new first nibble each time */
+    while (B.lead < m.hlen - 1 && B.nib(0) == 0) B.lead++;               /* helpers.py:183-186; nib(0) is relative to lead */
     B.n = 4 * (m.hlen - B.lead);
-    const int n = B.n;
 
     Res R;
-    R.clear();
-    const int dmin = lmin, dmax = lmax;
-    switch (p.method) {
-    case SDB_M_HIDEKI: case SDB_M_MAVERICK: case SDB_M_OSV1: case SDB_M_OSV2O3: case SDB_M_OSPIR:   /* :418-586 */
-        if (n < dmin || n > dmax) return SDB_ST_OK;
-        for (int i = 0; i < n; i++) R.push(B.bit(i));
-        break;
-    case SDB_M_MCRAW_MANCHESTER: {                                       /* :588-613 */
-        int mx = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 0;
-        if (n > mx) return SDB_ST_OK;
-        for (int i = 0; i < n; i++) R.push(B.bit(i));
-        break;
-    }
-    case SDB_M_MCRAW_HELPERS:                                            /* helpers.py:90-122 */
-        if (p.flags & SDB_HF_HAS_MAX) {
-            if (p.flags & SDB_HF_MAX_IS_STR) return SDB_ST_TYPEERROR;    /* int > str */
-            if (n > p.length_max) return SDB_ST_OK;
-        }
-        for (int i = 0; i < n; i++) R.push(B.bit(i));
-        break;
-    case SDB_M_GROTHE:                                                   /* :721-754 */
-        if (n != 32) return SDB_ST_OK;
-        for (int i = 0; i < n; i++) R.push(B.bit(i));
-        break;
-    case SDB_M_SOMFY: {                                                  /* :756-795 */
-        int from = 0, len = n;
-        if (n == 57) { from = 1; len = 56; }
-        if (len != 56) return SDB_ST_OK;
-        for (int i = 0; i < 56; i++) R.push(B.bit(from + i));
-        break;
-    }
-    case SDB_M_AS: {                                                     /* :356-416 */
-        int sp = n >= 16 ? B.find(0xC, 4, 16) : -1;
-        if (sp >= 0) {
-            int ep = B.find(0xC, 4, sp + 16);
-            if (ep < 0) ep = n;
-            int ml = ep - sp;
-            if (ml < dmin || ml > dmax) return SDB_ST_OK;
-            for (int i = sp; i < n; i++) R.push(B.bit(i));
-        } else {
-            if (n < dmin || n > dmax) return SDB_ST_OK;
-            for (int i = 0; i < n; i++) R.push(B.bit(i));
-        }
-        break;
-    }
-    case SDB_M_SAINLOGIC: {                                              /* :302-354 */
-        int mx = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 0;
-        if (n > mx) return SDB_ST_OK;
-        int ones = 0, total = n;
-        if (n < 128) {
-            int start = B.find(0x14, 6, 0);                              /* '010100' */
-            if (start < 0 || start > 10) return SDB_ST_OK;
-            ones = 10 - start;                                           /* prepend '1' until the sync sits at 10 */
-            total = min(128, n + ones);
-        }
-        int mn = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : 0;
-        if (total < mn) return SDB_ST_OK;
-        for (int i = 0; i < total; i++) R.push(i < ones ? 1 : B.bit(i - ones));
-        break;
-    }
-    case SDB_M_FUNKBUS: {                                                /* :207-300 */
-        if (n < dmin) return SDB_ST_OK;
-        if ((p.flags & SDB_HF_HAS_MAX) && n > p.length_max) return SDB_ST_OK;
-        /* differential manchester (helpers.py:6-26): s[k] = (b[k] == b[k+1]), k < n-1 */
-        const int ns = n - 1;
-        int tl, off;       /* t = prefix + s[off:] */
-        int plen;          /* prefix: '001' (119) or '0' */
-        if (p.flags & SDB_HF_IS_119) {
-            int pos = -1;
-            uint32_t acc = 0;
-            for (int k = 0; k < ns && k < 9; k++) {                      /* '01100' must start at 0..4 */
-                acc = ((acc << 1) | (uint32_t)(B.bit(k) == B.bit(k + 1))) & 0x1F;
-                if (k >= 4 && acc == 0x0C) { pos = k - 4; break; }
-            }
-            if (pos < 0) return SDB_ST_OK;
-            off = pos; plen = 3; tl = 3 + ns - pos;
-            if (tl < 48) return SDB_ST_OK;
-        } else { off = 0; plen = 1; tl = 1 + ns; }
-        int xorv = 0, chk = 0, parity = 0;
-        for (int i = 0; i < 6; i++) {
-            int from = i * 8, to = min(from + 8, tl);
-            if (from >= to) return SDB_ST_VALUEERROR;                    /* int('', 2) */
-            int data = 0;
-            for (int k = from; k < to; k++) {
-                int b;
-                if (k < plen) b = (plen == 3 && k == 2) ? 1 : 0;
-                else { int si = off + (k - plen); b = (B.bit(si) == B.bit(si + 1)); }
-                data = (data << 1) | b;
-            }
-            for (int k = 7; k >= 0; k--) R.push((data >> k) & 1);        /* f"{data:02X}" */
-            if (i < 5) xorv ^= data;
-            else { chk = data & 0x0F; xorv ^= data & 0xE0; data &= 0xF0; }
-            parity ^= __popc(data) & 1;
-        }
-        if (parity) return SDB_ST_OK;
-        int xn = ((xorv & 0xF0) >> 4) ^ (xorv & 0x0F), r = 0;
-        if (xn & 8) r ^= 0xC;
-        if (xn & 4) r ^= 0x2;
-        if (xn & 2) r ^= 0x8;
-        if (xn & 1) r ^= 0x3;
-        if (r != chk) return SDB_ST_OK;
-        break;
-    }
-    case SDB_M_TFA: {                                                    /* :615-719 */
-        int f = B.find(0xFFD, 12, 0);                                    /* '111111111101' */
-        if (f < 0) return SDB_ST_OK;
-        int pre = f + 12, mend = -1, it = 1, nm = 0;
-        int ps[48], pl[48];
-        while (mend < n) {
-            mend = (pre >= 0 && pre <= n) ? B.find(0x1FFD, 13, pre) : -1;   /* '1111111111101' */
-            if (mend < pre) mend = n;
-            int ml = mend - pre;
-            if (in_range(p, ml) && nm < 48) { ps[nm] = pre; pl[nm] = ml; nm++; }
-            int q = mend <= n ? B.find(0xD, 4, mend) : -1;              /* '1101' */
-            if (q >= 0) pre = q + 4; else { pre = -1; mend = n; }
-            it++;
-        }
-        if (it == 10) return SDB_ST_OK;
-        /* :706-711: every element whose hex string was seen exactly once before */
-        int dupi[48], nd = 0, seen[48];
-        for (int a = 0; a < nm; a++) {
-            int first = a;
-            for (int b = 0; b < a; b++) {
-                /* hex strings equal <=> same digit count and same right-aligned value */
-                if (((pl[a] + 3) >> 2) != ((pl[b] + 3) >> 2)) continue;
-                int la = pl[a], lb = pl[b], L = max(la, lb);
-                bool eq = true;
-                for (int k = 0; k < L && eq; k++) {
-                    int ia = la - 1 - k, ib = lb - 1 - k;
-                    int ba = ia >= 0 ? B.bit(ps[a] + ia) : 0, bb = ib >= 0 ? B.bit(ps[b] + ib) : 0;
-                    eq = ba == bb;
-                }
-                if (eq) { first = b; break; }
-            }
-            seen[a] = 0;
-            if (seen[first] == 1) dupi[nd++] = a;
-            seen[first]++;
-        }
-        if (nd == 0) return SDB_ST_OK;
-        uint32_t hb = atomicAdd(&A.ctr->hits, (uint32_t)nd);
-        mo.hit_off = hb; mo.nhits = (uint16_t)nd;
-        for (int e = 0; e < nd; e++) {
+    TfaOut T;
+    int reason;
+    const int rc = mc_decode(p, B, B.n, R, T, reason);                   /* :120 mcbitnum = len(bit_data) */
+    if (rc <= -100) return -rc - 100;
+    if (rc != 1) return SDB_ST_OK;
+    if (p.method == SDB_M_TFA) {
+        uint32_t hb = atomicAdd(&A.ctr->hits, (uint32_t)T.n);
+        mo.hit_off = hb; mo.nhits = (uint16_t)T.n;
+        for (int e = 0; e < T.n; e++) {
             R.clear();
-            int a = dupi[e];
-            for (int k = 0; k < pl[a]; k++) R.push(B.bit(ps[a] + k));
+            for (int k = 0; k < T.len[e]; k++) R.push(B.bit(T.start[e] + k));
             publish(A, mo, mi, m.proto, R.w, R.n, (R.n + 31) >> 5, SDB_HIT_LIST, (uint16_t)e, hb, (uint32_t)e);
         }
         return SDB_ST_OK;
     }
-    default:
-        return SDB_ST_OK;
-    }
     emit_one(A, mo, mi, m.proto, R.w, R.n, (R.n + 31) >> 5, 0, 0);       /* sd_protocols.py:102-109 */
     return SDB_ST_OK;
+}
+
+/* unit op: one mcBit2* call on a byte-per-bit string.  out = result bits (bytes); for TFA the parts are
+ * concatenated and seg[] holds their lengths.  res = {rc, reason, n_out, nseg}. */
+__global__ void unit_mc_kernel(SdbDevTable tab, uint32_t proto, int method_override, const uint8_t *bits, int n, int mcbitnum,
+                               uint8_t *out, int out_cap, int32_t *seg, int32_t *res)
+{
+    if (threadIdx.x != 0) return;
+    SdbHexProto p;
+    if (proto < tab.nproto) p = tab.hex[proto];
+    else { p = SdbHexProto{}; if (method_override & 0x100) p.flags = SDB_HF_IS_119; }   /* id not in the table: defaults only */
+    if (method_override & 0xFF) p.method = (uint8_t)(method_override & 0xFF);
+    ByteBits B;
+    B.b = bits; B.n = n;
+    Res R;
+    TfaOut T;
+    int reason = 0, nout = 0, nseg = 0;
+    int rc = mc_decode(p, B, mcbitnum, R, T, reason);
+    if (rc == 1) {
+        if (p.method == SDB_M_TFA) {
+            for (int e = 0; e < T.n; e++) {
+                seg[nseg++] = T.len[e];
+                for (int k = 0; k < T.len[e] && nout < out_cap; k++) out[nout++] = (uint8_t)B.bit(T.start[e] + k);
+            }
+        } else {
+            for (int i = 0; i < R.n && nout < out_cap; i++) out[nout++] = (uint8_t)((R.w[i >> 5] >> (i & 31)) & 1);
+        }
+    }
+    res[0] = rc; res[1] = reason; res[2] = nout; res[3] = nseg;
+}
+
+int launch_unit_mc(const SdbDevTable &tab, uint32_t proto, int method_override, const uint8_t *d_bits, int n, int mcbitnum,
+                   uint8_t *d_out, int out_cap, int32_t *d_seg, int32_t *d_res, cudaStream_t stream)
+{
+    if (n > SDB_MAX_HEX * 4) return -1;
+    unit_mc_kernel<<<1, 32, 0, stream>>>(tab, proto, method_override, d_bits, n, mcbitnum, d_out, out_cap, d_seg, d_res);
+    return (int)cudaGetLastError();
 }
 
 /* ---- MN ------------------------------------------------------------------------------------ */

@@ -26,6 +26,9 @@ int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMs
                uint32_t n, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
                SdbCounters *d_ctr, int grid, cudaStream_t stream);
 
+int launch_unit_mc(const SdbDevTable &tab, uint32_t proto, int method_override, const uint8_t *d_bits, int n, int mcbitnum,
+                   uint8_t *d_out, int out_cap, int32_t *d_seg, int32_t *d_res, cudaStream_t stream);
+
 int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_t *d_out, uint32_t out_cap,
                           int32_t *d_res /* [rc, n_out] */, cudaStream_t stream);
 

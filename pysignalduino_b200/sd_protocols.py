@@ -19,6 +19,11 @@ from .capi import (HIT_LIST, ST_OK, STATUS_EXC, STATUS_NAMES, Engine, Result)
 from .protocol_data import load_protocol_table
 from .table import PD_IDS, compile_table
 
+# SDB_M_* ids of the manchester.py decoders (csrc/sdb_table.h)
+MC_METHODS = {"mcBit2Funkbus": 1, "mcBit2Sainlogic": 2, "mcBit2AS": 3, "mcBit2Hideki": 4, "mcBit2Maverick": 5,
+              "mcBit2OSV1": 6, "mcBit2OSV2o3": 7, "mcBit2OSPIR": 8, "mcRaw": 9, "mcBit2TFA": 11, "mcBit2Grothe": 12,
+              "mcBit2SomfyRTS": 13}
+
 
 class SDProtocols:
     """Protocol handling class: same API as the reference, demodulation on the GPU.
@@ -273,6 +278,109 @@ class SDProtocols:
     def postDemo_lengtnPrefix(self, name, bit_msg_array):
         """postdemodulation.py:708-730"""
         return self._postdemo("postDemo_lengtnPrefix", bit_msg_array)
+
+    # ------------------------------------------------------------------ mcBit2* / mcRaw (unit ops on the device)
+    _MC_REASONS = {1: "message is too short", 2: "message is too long", 3: "wrong bits at begin", 4: "parity error",
+                   5: "checksum error", 9: "sync not found"}
+
+    def _mc_unit(self, method: int, name, bit_data, protocol_id, mcbitnum):
+        """One manchester.py decoder call through sdb_unit_mc; the host only renders hex and message strings."""
+        if mcbitnum is None:
+            mcbitnum = len(bit_data)
+        if any(c not in "01" for c in bit_data):
+            raise pack.DomainError("mcBit2*: bit_data must be a string of 0/1")
+        eng = self.engine()
+        try:
+            index = eng.table.ids.index(protocol_id)
+        except ValueError:
+            index = 0xFFFFFFFF                                   # check_property falls back to its defaults
+        try:
+            is119 = int(protocol_id) == 119                      # manchester.py:242
+        except (TypeError, ValueError):
+            is119 = False
+        if index != 0xFFFFFFFF:
+            is119 = False                                        # the table row carries it
+        rc, reason, parts = eng.unit_mc(index, bit_data, int(mcbitnum), method | (0x100 if is119 else 0))
+        if rc <= -100:
+            raise STATUS_EXC[-rc - 100](f"reference raises in the MC decoder ({method})")
+        if rc == 1:
+            if method == MC_METHODS["mcBit2TFA"]:
+                return (1, [self.bin_str_2_hex_str(x) for x in parts])
+            return (1, self.bin_str_2_hex_str(parts[0]))
+        base = reason & 0xFF
+        if base in self._MC_REASONS:
+            return (-1, self._MC_REASONS[base])
+        if base == 6:
+            return (-1, f"{name}: lib/mcBit2Sainlogic, start 010100 not found")
+        if base == 7:
+            return (-1, f"message must be 32 bits, got {mcbitnum}")
+        if base == 8:
+            n = len(bit_data[1:57]) if mcbitnum == 57 else len(bit_data)         # manchester.py:783-789
+            return (-1, f"message must be 56 bits, got {n}")
+        if base == 10:
+            tail = {0: "", 0x100: ", message is too short", 0x200: ", message is too long",
+                    0x400: ", protocol does not exists"}[reason & 0x700]
+            return (-1, f" no duplicate found{tail}")
+        if base == 11:
+            return (-1, f"loop error, please report this data {bit_data}")
+        raise RuntimeError(f"sdb_unit_mc: unknown reason code {reason}")
+
+    def mcBit2Funkbus(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:207-300"""
+        return self._mc_unit(MC_METHODS["mcBit2Funkbus"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2Sainlogic(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:302-354"""
+        return self._mc_unit(MC_METHODS["mcBit2Sainlogic"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2AS(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:356-416"""
+        return self._mc_unit(MC_METHODS["mcBit2AS"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2Hideki(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:418-450"""
+        return self._mc_unit(MC_METHODS["mcBit2Hideki"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2Maverick(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:452-484"""
+        return self._mc_unit(MC_METHODS["mcBit2Maverick"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2OSV1(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:486-518"""
+        return self._mc_unit(MC_METHODS["mcBit2OSV1"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2OSV2o3(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:520-552"""
+        return self._mc_unit(MC_METHODS["mcBit2OSV2o3"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2OSPIR(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:554-586"""
+        return self._mc_unit(MC_METHODS["mcBit2OSPIR"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcRaw(self, name, bit_data, protocol_id, mcbitnum, other_arg=None):
+        """manchester.py:588-613 (the ManchesterMixin definition wins over helpers.mcraw in the MRO)"""
+        return self._mc_unit(MC_METHODS["mcRaw"], name, bit_data, protocol_id, int(mcbitnum))    # :608 int(None) raises
+
+    def mcraw(self, name="anonymous", bit_data=None, protocol_id=None, mcbitnum=None):
+        """helpers.py:90-122 (lower case: the rfmode-less '57' table entry names it; note its own message text)"""
+        if bit_data is None:
+            return (-1, "no bitData provided")
+        if protocol_id is None:
+            return (-1, "no protocolId provided")
+        rc, msg = self._mc_unit(10, name, bit_data, protocol_id, mcbitnum)
+        return (rc, "message is to long") if rc == -1 else (rc, msg)
+
+    def mcBit2TFA(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:615-719 (returns the LIST of duplicated parts)"""
+        return self._mc_unit(MC_METHODS["mcBit2TFA"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2Grothe(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:721-754"""
+        return self._mc_unit(MC_METHODS["mcBit2Grothe"], name, bit_data, protocol_id, mcbitnum)
+
+    def mcBit2SomfyRTS(self, name, bit_data, protocol_id, mcbitnum=None):
+        """manchester.py:756-795"""
+        return self._mc_unit(MC_METHODS["mcBit2SomfyRTS"], name, bit_data, protocol_id, mcbitnum)
 
     # ------------------------------------------------------------------ small pure helpers (API surface)
     def bin_str_2_hex_str(self, num):
