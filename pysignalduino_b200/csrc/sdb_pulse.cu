@@ -86,14 +86,29 @@ struct KArgs {
     uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
 };
 
+/* MU scan kernel: symbol / start bitmaps of the distinct id-string sets of up to 32 survivors */
+#define MU_NB 6                       /* symbol bitmap triples resident at a time             */
+#define MU_NS 6                       /* start bitmaps resident at a time                     */
+#define MU_BW 34                      /* words per bitmap: 1024 positions + 2 zero words      */
+#define MU_K 4                        /* matches a lane records before the warp emits them    */
+
 struct __align__(16) WarpSm {
     uint32_t dig[DIG_WORDS];          /* nibble-packed digits, 0xF beyond dlen               */
-    uint32_t first2[100], last2[100]; /* digram ab: first position / last position + 1       */
-    uint32_t first1[12], last1[12];   /* digit a                                             */
-    uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
-    int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
-    uint8_t  M[SDB_MAX_VALS];         /* candidate-slot mask per (clock, interval) pair      */
-    uint8_t  plist[256];              /* table rows that passed the prefilter, in table order */
+    union {
+        struct {                      /* resolve kernels */
+            uint32_t first2[100], last2[100]; /* digram ab: first position / last position + 1       */
+            uint32_t first1[12], last1[12];   /* digit a                                             */
+            uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
+            int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
+            uint8_t  M[SDB_MAX_VALS];         /* candidate-slot mask per (clock, interval) pair      */
+            uint8_t  plist[256];              /* table rows that passed the prefilter, in table order */
+        };
+        struct {                      /* scan_kernel<MU> */
+            uint32_t Bm[MU_NB][3][MU_BW];     /* [0] bit p: a symbol of the set starts at position p; [1] / [2]: 8 / 16
+                                               * consecutive symbols (p, p + w, ...) start at p      */
+            uint32_t Sm[MU_NS][MU_BW];        /* bit p: the start string occurs at position p        */
+        };
+    };
     int32_t  pat[8];
     uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
     uint32_t fpl[BIT_WORDS];          /* 'F' plane                                           */
@@ -558,143 +573,357 @@ __device__ __forceinline__ uint32_t eq_nibbles8(uint32_t x, uint32_t c8)
 }
 
 /*
- * The regex scan of one (message x MU protocol) task once the templates are resolved:
- * message_unsynced.py:146-290.  start_t / t1 / t0 / tf = id strings (nibble-packed) of start, one,
- * zero, float; s0 = where D' begins.
+ * The regex scan of the MU survivors of one message: message_unsynced.py:146-290.
+ *
+ * re.finditer("START((?:S1|S2|S3){MIN,}(?:E1|..)?)", D') is backtracking-free because all symbol alternatives have
+ * the same width w: a match at i needs START at i and a run of n >= MIN symbols at p = i + len(START),
+ * p, p + w, ... (greedy: up to the first non-symbol of that residue class), then an optional tail.  Two bitmaps
+ * describe everything: B (a symbol of the set starts here) and S (the start string occurs here).  Survivors of one
+ * message share them heavily (most resolve to the same two id strings), so the warp builds each DISTINCT bitmap once
+ * (SWAR compares, 8 windows per lane) and then every LANE walks the matches of its own survivor with word scans over
+ * the shared bitmaps; the warp only cooperates again to turn a match into bits (ballots), post-demodulate and emit.
  */
-__device__ __noinline__ int scan_mu(const KArgs &A, const SdbPulseProto *pp, int s0, uint64_t start_t,
-                                    uint32_t t1, uint32_t t0, uint32_t tf, bool hasf)
+/* warp: bitmap of the positions where a w-digit symbol of {c1, c0, cf} starts -> dst[0 .. nw + 1] */
+__device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint32_t c0, uint32_t cf, int nw)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
     const int dlen = sm.dlen;
-    const int w = pp->width;
-    const int flags = pp->flags;
-    const int Ls = pp->key[0].len;
-    const bool has0 = pp->key[2].len != 0;
-
-    const uint32_t wm = nibmask32(w);
-    const uint32_t c1 = t1, c0 = has0 ? t0 : t1, cf = hasf ? tf : t1;
-    const bool use_tail = (flags & SDB_PF_RECONSTRUCT) && w > 1;   /* w == 1: the tail key is '' and matches nothing extra */
-    const uint32_t em = nibmask32(w - 1);
-
-    /* symbol bitmap B and start bitmap S over the positions of D (lane r = positions 32r..32r+31) */
-    uint32_t myB = 0, myS = Ls ? 0u : FULL;
-    if (w == 2 && Ls <= 2) {
-        /* SWAR: each lane compares the 8 two-digit windows of one digit word against the symbol bytes.
-         * Windows reaching past dlen contain 0xF padding and never equal a symbol (digits <= 9). */
+    if (w == 2) {
+        /* each lane compares the 8 two-digit windows of one digit word against the symbol bytes; windows reaching
+         * past dlen contain 0xF padding and never equal a symbol (digits <= 9) */
         const uint32_t k1 = c1 * 0x01010101u, k0 = c0 * 0x01010101u, kf = cf * 0x01010101u;
+        const int nwords = (dlen + 7) >> 3;
+        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
+        const int nbytes = 4 * (nw + 2);
+#pragma unroll 1
+        for (int wi = lane; wi < nbytes; wi += 32) {
+            uint32_t b8 = 0;
+            if (wi < nwords) {
+                uint32_t x = sm.dig[IDX(wi, DIG_WORDS)], nx = sm.dig[IDX(wi + 1, DIG_WORDS)];
+                uint32_t y = __funnelshift_r(x, nx, 4);                /* windows at odd positions */
+                uint32_t be = eq_bytes(x, k1) | eq_bytes(x, k0) | eq_bytes(x, kf);
+                uint32_t bo = eq_bytes(y, k1) | eq_bytes(y, k0) | eq_bytes(y, kf);
+                b8 = spread_even(be) | (spread_even(bo) << 1);
+            }
+            d8[IDX(wi, 4 * MU_BW)] = (uint8_t)b8;
+        }
+    } else {
+        const uint32_t wm = nibmask32(w);
+#pragma unroll 1
+        for (int r = 0; r <= nw + 1; r++) {
+            int p = r * 32 + lane;
+            uint32_t x = p < dlen ? win32(sm.dig, p) & wm : 0xFFFFFFFFu;
+            bool sym = (p + w <= dlen) && (x == c1 || x == c0 || x == cf);
+            uint32_t bw = __ballot_sync(FULL, sym);
+            if (lane == 0) dst[IDX(r, MU_BW)] = bw;
+        }
+    }
+    __syncwarp();
+    /* "8 / 16 symbols in a row start here" by shifted-AND doubling on the words (lane j = word j; word 32 is all zero):
+     * the per-lane scans take their candidates from these, so the many short accidental runs cost nothing */
+    uint32_t x = lane <= nw + 1 ? dst[IDX(lane, MU_BW)] : 0u;
+    uint32_t x8 = 0;
+#pragma unroll
+    for (int lv = 0; lv < 4; lv++) {
+        const int sh = w << lv;                                        /* w, 2w, 4w, 8w <= 32 */
+        uint32_t nx = __shfl_down_sync(FULL, x, 1);
+        if (lane == 31) nx = 0;
+        x &= sh < 32 ? __funnelshift_r(x, nx, sh) : nx;
+        if (lv == 2) x8 = x;
+    }
+    dst[IDX(MU_BW + lane, 3 * MU_BW)] = x8;
+    dst[IDX(2 * MU_BW + lane, 3 * MU_BW)] = x;
+    if (lane < 2) { dst[IDX(MU_BW + 32 + lane, 3 * MU_BW)] = 0; dst[IDX(2 * MU_BW + 32 + lane, 3 * MU_BW)] = 0; }
+    __syncwarp();
+}
+
+/* warp: bitmap of the occurrences of the Ls-digit start string -> dst[0 .. nw + 1] */
+__device__ __noinline__ void mu_build_S(uint32_t *dst, int Ls, uint64_t start_t, int nw)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const int dlen = sm.dlen;
+    if (Ls <= 2) {
         const uint32_t ks = Ls == 2 ? (uint32_t)start_t * 0x01010101u : ((uint32_t)start_t & 0xF) * 0x11111111u;
         const int nwords = (dlen + 7) >> 3;
-        #pragma unroll 1
-        for (int r0 = 0; r0 < nwords; r0 += 32) {
-            const int wi = r0 + lane;
-            uint32_t x = sm.dig[IDX(min(wi, DIG_WORDS - 2), DIG_WORDS)], nx = sm.dig[IDX(min(wi + 1, DIG_WORDS - 1), DIG_WORDS)];
-            uint32_t y = __funnelshift_r(x, nx, 4);                /* windows at odd positions */
-            uint32_t be = eq_bytes(x, k1) | eq_bytes(x, k0) | eq_bytes(x, kf);
-            uint32_t bo = eq_bytes(y, k1) | eq_bytes(y, k0) | eq_bytes(y, kf);
-            uint32_t b8 = spread_even(be) | (spread_even(bo) << 1);
-            if (wi >= nwords) b8 = 0;
-            uint32_t v = b8 << (8 * (lane & 3));
-            v |= __shfl_xor_sync(FULL, v, 1);
-            v |= __shfl_xor_sync(FULL, v, 2);
-            uint32_t got = __shfl_sync(FULL, v, (lane & 7) * 4);   /* mask word (r0/4 + lane&7) */
-            if ((lane >> 3) == (r0 >> 5)) myB = got;
-            if (Ls) {
-                uint32_t s8 = Ls == 2 ? (spread_even(eq_bytes(x, ks)) | (spread_even(eq_bytes(y, ks)) << 1))
-                                      : eq_nibbles8(x, ks);        /* one-pulse start: plain digit compare */
-                if (wi >= nwords) s8 = 0;
-                uint32_t sv = s8 << (8 * (lane & 3));
-                sv |= __shfl_xor_sync(FULL, sv, 1);
-                sv |= __shfl_xor_sync(FULL, sv, 2);
-                uint32_t sgot = __shfl_sync(FULL, sv, (lane & 7) * 4);
-                if ((lane >> 3) == (r0 >> 5)) myS = sgot;
+        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
+        const int nbytes = 4 * (nw + 2);
+#pragma unroll 1
+        for (int wi = lane; wi < nbytes; wi += 32) {
+            uint32_t s8 = 0;
+            if (wi < nwords) {
+                uint32_t x = sm.dig[IDX(wi, DIG_WORDS)];
+                if (Ls == 2) {
+                    uint32_t y = __funnelshift_r(x, sm.dig[IDX(wi + 1, DIG_WORDS)], 4);
+                    s8 = spread_even(eq_bytes(x, ks)) | (spread_even(eq_bytes(y, ks)) << 1);
+                } else s8 = eq_nibbles8(x, ks);                        /* one-pulse start: plain digit compare */
             }
+            d8[IDX(wi, 4 * MU_BW)] = (uint8_t)s8;
         }
     } else {
         const uint64_t lm = nibmask64(Ls);
-        const int nr = (dlen + 31) >> 5;          /* an empty START at p == dlen needs MIN == 0, which the table compiler rejects */
-        #pragma unroll 1
-        for (int r = 0; r < nr; r++) {
+#pragma unroll 1
+        for (int r = 0; r <= nw + 1; r++) {
             int p = r * 32 + lane;
-            uint32_t x = win32(sm.dig, p) & wm;
-            bool sym = (p + w <= dlen) && (x == c1 || x == c0 || x == cf);
-            uint32_t bw = __ballot_sync(FULL, sym);
-            if (lane == r) myB = bw;
-            if (Ls) {
-                bool st = (p + Ls <= dlen) && ((win64(sm.dig, p) & lm) == start_t);
-                uint32_t sw = __ballot_sync(FULL, st);
-                if (lane == r) myS = sw;
-            }
+            bool st = (p + Ls <= dlen) && ((win64(sm.dig, p) & lm) == start_t);
+            uint32_t sw = __ballot_sync(FULL, st);
+            if (lane == 0) dst[IDX(r, MU_BW)] = sw;
         }
     }
-    const int MIN = pp->regex_min;
-    /* Candidate match positions.  With a start string that occurs only a few times, every occurrence is simply
-     * tried in turn (the run length is needed anyway); otherwise R[p] = B[p] & B[p+w] & ... (MIN terms) is built by
-     * binary doubling so that the leftmost feasible position is one find-first-set away. */
-    const bool direct = Ls && __reduce_add_sync(FULL, __popc(myS)) <= 8u;
-    uint32_t myC = myS;
-    if (!direct) {
-        uint32_t R = FULL, Acc = myB;
-        int rl = 0, al = 1;
-        #pragma unroll 1
-        for (int m = MIN; m > 0; m >>= 1) {
-            if (m & 1) { R &= rl ? shr_dist(Acc, rl * w) : Acc; rl += al; }
-            if (m > 1) { Acc &= shr_dist(Acc, al * w); al <<= 1; }
-        }
-        myC = myS & (Ls ? shr_dist(R, Ls) : R);
-    }
+    __syncwarp();
+}
 
-    /* re.finditer (:192): leftmost match from pos, then continue at its end */
-    int pos = s0, ordinal = 0;
-    for (;;) {
-        int i = first_set_from(myC, pos);
-        if (i < 0) break;
-        int p = i + Ls;
-        /* greedy run: first position q >= p, q = p (mod w), that is not a symbol */
-        uint32_t cls = w == 1 ? FULL : (w == 2 ? 0x55555555u << (p & 1) : 0x11111111u << (p & 3));
-        int ns = first_set_from(~myB & cls, p);
-        int n = ns >= 0 ? (ns - p) / w : (SDB_MAX_DIGITS - p + w - 1) / w;
-        if (direct && n < MIN) { pos = i + 1; continue; }   /* {MIN,} not met here: the regex retries one position later */
-        int end = p + n * w;
-        int tail = -1;                             /* 0/1/2 = bit '1'/'0'/'F' of the reconstructed chunk */
-        if (use_tail) {
-            uint32_t x = win32(sm.dig, end) & em;  /* beyond dlen the 0xF padding never matches */
-            if (x == (c1 & em)) tail = 0;
-            else if (has0 && x == (c0 & em)) tail = 1;
-            else if (hasf && x == (cf & em)) tail = 2;
-            if (tail >= 0) end += w - 1;
-        }
-        pos = end > i ? end : i + 1;
-        int nch = n + (tail >= 0 ? 1 : 0);
-        if (nch == 0) return SDB_ST_INDEXERROR;   /* :212 chunks[-1] on an empty capture */
-        if (pp->mu_len_max >= 0 && nch > pp->mu_len_max) continue;   /* :217 */
-        /* chunks -> bits (:220-228): later keys overwrite earlier ones on identical strings */
-        __syncwarp();
-        #pragma unroll 1
-        for (int b0 = 0; b0 < n; b0 += 32) {
-            int c = b0 + lane;
-            bool isf = false, one = false;
-            if (c < n) {
-                uint32_t x = win32(sm.dig, p + c * w) & wm;
-                if (hasf && x == cf) isf = true;
-                else if (has0 && x == c0) one = false;
-                else one = true;
+/* per-lane description and progress of one survivor, packed so that the whole scan state stays in registers */
+#define MU_NONE 0xFFFE
+struct MuLane {
+    const uint32_t *B, *Bx, *S;  /* Bx: B, or its 8- / 16-in-a-row level when MIN allows; S == nullptr: no start string */
+    uint32_t sym;                /* id strings of one | zero << 8 ... kept as c1, c0, cf below */
+    uint32_t c1, c0, cf;         /* one / zero / float (zero, float = one when absent) */
+    int lw, Ls, MIN, lenmax;
+    uint32_t flags;              /* 1 use_tail, 2 has0, 4 hasf, 8 done */
+    int pos, status, nm;
+    uint32_t m0, m1, m2, m3;     /* recorded matches: p | n << 11 | (tail + 1) << 22 */
+    uint64_t dead;               /* 16 bits per residue class of p: no run of >= MIN symbols starts before this position */
+    uint64_t cand;               /* 16 bits per residue class of p: cached next candidate i + 1 (0 unknown, 0xFFFF none) */
+};
+#define MU_F_TAIL 1u
+#define MU_F_HAS0 2u
+#define MU_F_HASF 4u
+#define MU_F_DONE 8u
+
+__device__ __forceinline__ uint32_t mu_cls_mask(int lw, int p)
+{
+    return lw == 0 ? FULL : (lw == 1 ? 0x55555555u << (p & 1) : 0x11111111u << (p & 3));
+}
+
+/* lane: one step of re.finditer for this survivor = the leftmost remaining candidate, accepted (recorded) or rejected.
+ * A candidate is a position i with S[i] and (MIN == 0 or Bx[i + Ls]). */
+__device__ __forceinline__ void mu_step(const uint32_t *dig, MuLane &L, int nwB)
+{
+    const int w = 1 << L.lw, Ls = L.Ls;
+    const int pos = L.pos;
+    /* leftmost candidate over the residue classes; a class is dead up to the end of a run that was too short.
+     * p = i + Ls in class c  <=>  i in class (c - Ls) mod w */
+    int i = MU_NONE;
+#pragma unroll 1
+    for (int c = 0; c < w; c++) {
+        const int from = max(pos, (int)((uint32_t)(L.dead >> (16 * c)) & 0xFFFFu) - Ls);
+        int cd = (int)((uint32_t)(L.cand >> (16 * c)) & 0xFFFFu) - 1;
+        if (cd < from) {
+            const uint32_t cmask = mu_cls_mask(L.lw, (c - Ls) & 3);
+            int j = from >> 5;
+            uint32_t first = FULL << (from & 31);
+            cd = MU_NONE;
+#pragma unroll 1
+            for (; j <= nwB; j++) {
+                uint32_t cw = cmask & first;
+                first = FULL;
+                if (L.MIN > 0) cw &= Ls ? __funnelshift_r(L.Bx[IDX(j, MU_BW)], L.Bx[IDX(j + 1, MU_BW)], Ls) : L.Bx[IDX(j, MU_BW)];
+                if (L.S) cw &= L.S[IDX(j, MU_BW)];
+                if (cw) { cd = j * 32 + __ffs(cw) - 1; break; }
             }
-            uint32_t vw = __ballot_sync(FULL, one), fw = __ballot_sync(FULL, isf);
-            if (lane == 0) { sm.val[IDX(b0 >> 5, BIT_WORDS)] = vw; sm.fpl[IDX(b0 >> 5, BIT_WORDS)] = fw; }
+            L.cand = (L.cand & ~(0xFFFFull << (16 * c))) | ((uint64_t)(cd + 1) << (16 * c));
         }
-        __syncwarp();
-        for (int wq = lane; wq < BIT_WORDS; wq += 32)
-            if (wq >= ((n + 31) >> 5)) { sm.val[IDX(wq, BIT_WORDS)] = 0; sm.fpl[IDX(wq, BIT_WORDS)] = 0; }
-        __syncwarp();
-        if (lane == 0) {
-            if (tail == 0) sm.val[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
-            else if (tail == 2) sm.fpl[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
+        i = min(i, cd);
+    }
+    if (i == MU_NONE) { L.flags |= MU_F_DONE; return; }
+    const int p = i + Ls;
+    /* greedy run: first position q >= p, q = p (mod w), that is not a symbol (B is zero from dlen on) */
+    const uint32_t cls = mu_cls_mask(L.lw, p);
+    int ns;
+    {
+        int j = p >> 5;
+        uint32_t z = ~L.B[IDX(j, MU_BW)] & cls & (FULL << (p & 31));
+        while (!z) { j++; z = ~L.B[IDX(j, MU_BW)] & cls; }           /* ends at word (dlen >> 5) <= nwB + 1 at the latest */
+        ns = j * 32 + __ffs(z) - 1;
+    }
+    const int n = (ns - p) >> L.lw;
+    if (n < L.MIN) {                                                    /* {MIN,} not met: every start inside this run fails too */
+        const int sh = 16 * (p & (w - 1));
+        L.dead = (L.dead & ~(0xFFFFull << sh)) | ((uint64_t)ns << sh);
+        L.pos = i + 1;
+        return;
+    }
+    int end = p + n * w;
+    int tail = -1;                                                      /* 0/1/2 = bit '1'/'0'/'F' of the reconstructed chunk */
+    if (L.flags & MU_F_TAIL) {
+        const uint32_t em = nibmask32(w - 1);
+        uint32_t x = win32(dig, end) & em;                              /* beyond dlen the 0xF padding never matches */
+        if (x == (L.c1 & em)) tail = 0;
+        else if ((L.flags & MU_F_HAS0) && x == (L.c0 & em)) tail = 1;
+        else if ((L.flags & MU_F_HASF) && x == (L.cf & em)) tail = 2;
+        if (tail >= 0) end += w - 1;
+    }
+    L.pos = end > i ? end : i + 1;
+    const int nch = n + (tail >= 0 ? 1 : 0);
+    if (nch == 0) { L.status = SDB_ST_INDEXERROR; L.flags |= MU_F_DONE; return; }   /* :212 chunks[-1] on an empty capture */
+    if (L.lenmax >= 0 && nch > L.lenmax) return;                        /* :217 */
+    const uint32_t rec = (uint32_t)p | ((uint32_t)n << 11) | ((uint32_t)(tail + 1) << 22);
+    if (L.nm == 0) L.m0 = rec; else if (L.nm == 1) L.m1 = rec; else if (L.nm == 2) L.m2 = rec; else L.m3 = rec;
+    L.nm++;
+}
+
+/* warp: one match -> bits (:220-228: later keys overwrite earlier ones on identical strings) -> finish_match */
+__device__ __noinline__ int mu_emit_match(const KArgs &A, const SdbPulseProto *pp, uint32_t rec, uint32_t c1, uint32_t c0,
+                                          uint32_t cf, bool hasf, int ordinal)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const int w = pp->width;
+    const bool has0 = pp->key[2].len != 0;
+    const uint32_t wm = nibmask32(w);
+    const int p = rec & 0x7FF, n = (rec >> 11) & 0x7FF, tail = (int)(rec >> 22) - 1;
+    __syncwarp();
+#pragma unroll 1
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        int c = b0 + lane;
+        bool isf = false, one = false;
+        if (c < n) {
+            uint32_t x = win32(sm.dig, p + c * w) & wm;
+            if (hasf && x == cf) isf = true;
+            else if (has0 && x == c0) one = false;
+            else one = true;
         }
-        int st = finish_match<false>(A, pp, nch, ordinal, hasf);
-        if (st != SDB_ST_OK) return st;
-        ordinal++;
+        uint32_t vw = __ballot_sync(FULL, one), fw = __ballot_sync(FULL, isf);
+        if (lane == 0) { sm.val[IDX(b0 >> 5, BIT_WORDS)] = vw; sm.fpl[IDX(b0 >> 5, BIT_WORDS)] = fw; }
+    }
+    __syncwarp();
+    for (int wq = lane; wq < BIT_WORDS; wq += 32)
+        if (wq >= ((n + 31) >> 5)) { sm.val[IDX(wq, BIT_WORDS)] = 0; sm.fpl[IDX(wq, BIT_WORDS)] = 0; }
+    __syncwarp();
+    if (lane == 0) {
+        if (tail == 0) sm.val[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
+        else if (tail == 2) sm.fpl[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
+    }
+    return finish_match<false>(A, pp, n + (tail >= 0 ? 1 : 0), ordinal, hasf);
+}
+
+__device__ __forceinline__ uint64_t mu_sort3_key(uint32_t a, uint32_t b, uint32_t c, int w)
+{
+    uint32_t lo = min(a, min(b, c)), hi = max(a, max(b, c));
+    uint32_t mid = a + b + c - lo - hi;
+    return ((uint64_t)w << 48) | ((uint64_t)lo << 32) | ((uint64_t)mid << 16) | hi;
+}
+
+__device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const SdbPulseProto *rows = A.tab.mu;
+    const int nwB = (sm.dlen - 1) >> 5;                                /* candidates live in words 0 .. nwB; words 0 .. nwB + 1 are valid */
+#pragma unroll 1
+    for (uint32_t s0i = 0; s0i < nsurv; s0i += 32) {
+        const bool have = s0i + lane < nsurv;
+        SdbSurv mine;
+        mine.start = 0; mine.c1 = mine.c0 = mine.cf = 0; mine.meta = 0;
+        if (have) mine = slots[s0i + lane];                            /* coalesced 16-byte loads */
+        const int cnt = min(32u, nsurv - s0i);
+        const uint32_t row = have ? (uint32_t)(mine.start >> 56) : 0u;
+        const uint64_t start_t = mine.start & 0x00FFFFFFFFFFFFFFull;
+        MuLane L;
+        int w, lvl;
+        {
+            const SdbPulseProto *pp = &rows[row];
+            w = pp->width;
+            L.lw = w == 1 ? 0 : (w == 2 ? 1 : 2);
+            L.Ls = pp->key[0].len;
+            const bool has0 = pp->key[2].len != 0, hasf = (mine.meta & 0x800) != 0;
+            L.c1 = mine.c1; L.c0 = has0 ? mine.c0 : mine.c1; L.cf = hasf ? mine.cf : mine.c1;
+            L.MIN = pp->regex_min; L.lenmax = pp->mu_len_max;
+            /* w == 1: the tail key is '' and matches nothing extra */
+            L.flags = (((pp->flags & SDB_PF_RECONSTRUCT) && w > 1) ? MU_F_TAIL : 0u) | (has0 ? MU_F_HAS0 : 0u) | (hasf ? MU_F_HASF : 0u) |
+                      (have ? 0u : MU_F_DONE);
+            lvl = L.MIN >= 16 ? 2 : (L.MIN >= 8 ? 1 : 0);
+        }
+        L.sym = 0;
+        L.B = nullptr; L.Bx = nullptr; L.S = nullptr;
+        L.pos = mine.meta & 0x7FF; L.status = SDB_ST_OK; L.nm = 0; L.m0 = L.m1 = L.m2 = L.m3 = 0;
+        L.dead = 0; L.cand = 0;
+        int ordbase = 0;
+        const uint64_t keyB = mu_sort3_key(L.c1, L.c0, L.cf, w);
+        const uint64_t keyS = ((uint64_t)L.Ls << 56) | start_t;
+
+        /* Rounds: build the distinct bitmaps of the pending lanes (at most MU_NB / MU_NS per round) and let the lanes whose
+         * bitmaps are resident scan until they are done or hold MU_K unread matches; once nothing is pending, emit in survivor
+         * order.  A survivor with more than MU_K matches becomes the only pending lane of a further round. */
+        uint32_t pending = __ballot_sync(FULL, have);
+        int k = 0, rounds = 0;
+        bool cont = false;
+#pragma unroll 1
+        for (;;) {
+            const bool pend = (pending >> lane) & 1;
+            bool now = pend;
+            if (!(cont && rounds == 1)) {                               /* (a continuation after a single round finds every bitmap still resident) */
+            const uint32_t gB = __match_any_sync(FULL, pend ? keyB : (0xF000000000000000ull | lane));
+            const bool needS = pend && L.Ls != 0;
+            const uint32_t gS = __match_any_sync(FULL, needS ? keyS : (0xF000000000000000ull | lane));
+            const uint32_t leadB = __ballot_sync(FULL, pend && lane == __ffs(gB) - 1);
+            const uint32_t leadS = __ballot_sync(FULL, needS && lane == __ffs(gS) - 1);
+            const int slotB = __popc(leadB & ((1u << (__ffs(gB) - 1)) - 1));
+            const int slotS = needS ? __popc(leadS & ((1u << (__ffs(gS) - 1)) - 1)) : 0;
+            now = pend && slotB < MU_NB && slotS < MU_NS;
+            __syncwarp();
+            uint32_t lb = leadB;
+#pragma unroll 1
+            for (int sl = 0; lb && sl < MU_NB; sl++) {
+                const int src = __ffs(lb) - 1;
+                lb &= lb - 1;
+                mu_build_B(sm.Bm[sl][0], __shfl_sync(FULL, w, src), __shfl_sync(FULL, L.c1, src), __shfl_sync(FULL, L.c0, src),
+                           __shfl_sync(FULL, L.cf, src), nwB);
+            }
+            uint32_t ls = leadS;
+#pragma unroll 1
+            for (int sl = 0; ls && sl < MU_NS; sl++) {
+                const int src = __ffs(ls) - 1;
+                ls &= ls - 1;
+                const uint32_t lo = __shfl_sync(FULL, (uint32_t)start_t, src), hi = __shfl_sync(FULL, (uint32_t)(start_t >> 32), src);
+                mu_build_S(sm.Sm[sl], __shfl_sync(FULL, L.Ls, src), ((uint64_t)hi << 32) | lo, nwB);
+            }
+            if (now) {
+                L.B = sm.Bm[IDX(slotB, MU_NB)][0];
+                L.Bx = sm.Bm[IDX(slotB, MU_NB)][lvl];
+                L.S = L.Ls ? sm.Sm[IDX(slotS, MU_NS)] : nullptr;
+            }
+            rounds += rounds < 2;
+            }
+            /* warp-synchronous on purpose: one step per lane per trip, reconverged at every trip, so the cost is the LONGEST
+             * lane's step count and not the sum over lanes */
+            bool run = now && !(L.flags & MU_F_DONE) && L.nm < MU_K;
+#pragma unroll 1
+            while (__any_sync(FULL, run)) {
+                if (run) {
+                    mu_step(sm.dig, L, nwB);
+                    run = !(L.flags & MU_F_DONE) && L.nm < MU_K;
+                }
+                __syncwarp();
+            }
+            pending &= ~__ballot_sync(FULL, now);
+            if (pending) continue;
+            /* an exception anywhere loses every hit of the message (it escapes demodulate_mu): no need to emit first */
+            if (__any_sync(FULL, L.status != SDB_ST_OK)) return SDB_ST_INDEXERROR;
+#pragma unroll 1
+            for (; k < cnt; k++) {
+                const int nmk = __shfl_sync(FULL, L.nm, k);
+                if (nmk) {
+                    const SdbPulseProto *pk = &rows[__shfl_sync(FULL, row, k)];
+                    const uint32_t c1k = __shfl_sync(FULL, L.c1, k), c0k = __shfl_sync(FULL, L.c0, k), cfk = __shfl_sync(FULL, L.cf, k);
+                    const bool hasfk = (__shfl_sync(FULL, L.flags, k) & MU_F_HASF) != 0;
+                    const int ob = __shfl_sync(FULL, ordbase, k);
+#pragma unroll 1
+                    for (int j = 0; j < nmk; j++) {
+                        const uint32_t rec = __shfl_sync(FULL, j == 0 ? L.m0 : (j == 1 ? L.m1 : (j == 2 ? L.m2 : L.m3)), k);
+                        const int st = mu_emit_match(A, pk, rec, c1k, c0k, cfk, hasfk, ob + j);
+                        if (st != SDB_ST_OK) return st;
+                    }
+                    if (lane == k) { ordbase += L.nm; L.nm = 0; }
+                }
+                if (!(__shfl_sync(FULL, L.flags, k) & MU_F_DONE)) break;
+            }
+            if (k >= cnt) break;
+            cont = true;
+            pending = 1u << k;                                         /* more than MU_K matches: this survivor continues alone */
+        }
     }
     return SDB_ST_OK;
 }
@@ -1187,8 +1416,7 @@ __device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots,
             const uint64_t start_t = (((uint64_t)(shi & 0x00FFFFFFu)) << 32) | slo;
             const int pos0 = (int)((cfm >> 16) & 0x7FF);
             const bool hasf = ((cfm >> 16) & 0x800) != 0;
-            const int st = MS ? scan_ms(A, pp, pos0, (uint32_t)start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf)
-                              : scan_mu(A, pp, pos0, start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf);
+            const int st = scan_ms(A, pp, pos0, (uint32_t)start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf);
             if (st != SDB_ST_OK) return st;
         }
     }
@@ -1211,7 +1439,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
         if (nsurv) {
             const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
             stage_digits(A, sm, m, m->dlen, mi);
-            int status = scan_survivors<MS>(A, slots, nsurv);
+            int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu(A, slots, nsurv);
             __syncwarp();
             const uint32_t nh = sm.nh, nw = sm.nw;
             if (status != SDB_ST_OK) {
@@ -1240,7 +1468,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
                     __syncwarp();
                     if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
                     __syncwarp();
-                    scan_survivors<MS>(A, slots, nsurv);
+                    if (MS) scan_survivors<MS>(A, slots, nsurv); else scan_survivors_mu(A, slots, nsurv);
                 }
             }
         }
