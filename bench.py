@@ -247,7 +247,8 @@ def run_ours(args):
 
     # our kernels per step: MS and MU = (resolve + scan) per 262144-message chunk, MC 1, MN 1
     CHUNK = 262144
-    launches_per_step = sum((2 * ((s["n"] + CHUNK - 1) // CHUNK)) if s["kind"] <= 1 else 1 for s in slots)
+    # per chunk: MS = resolve + scan, MU = resolve + match + emit + fused fallback (sdb_pulse.cu launch_pulse)
+    launches_per_step = sum(((2 if s["kind"] == 0 else 4) * ((s["n"] + CHUNK - 1) // CHUNK)) if s["kind"] <= 1 else 1 for s in slots)
 
     def barrier():
         if world > 1:

@@ -641,7 +641,6 @@ static int demod_mu_one(const OraProto *tab, int np, const regex_t *mm, const Ms
             } else if (key != 2) { failed = 1; break; }
         }
         if (failed || nparts == 0) continue;                 /* :143 */
-        if (getenv("ORA_DUMP")) fprintf(stderr, "SURV %d %d [%s] %s %s %s %d %d\n", mi, pi, start_str, parts[0], nparts>1?parts[1]:"-", nparts>2?parts[2]:"-", p->has_length_min ? p->length_min : 0, (int)strlen(D));
 
         int use_tail = p->reconstruct && el.n > 0;           /* :175 */
         int length_min = p->has_length_min ? p->length_min : 0;   /* :178 */

@@ -84,6 +84,8 @@ struct KArgs {
     SdbSurv *surv;             /* n x surv_stride survivor slots (resolve -> scan) */
     uint32_t *surv_cnt;        /* survivors per message */
     uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
+    uint32_t *match;           /* MU: n x MU_MCAP match records (match kernel -> emit kernel) */
+    uint32_t *match_cnt;       /* MU: records per message, or MU_MARK = left to the fused fallback kernel */
 };
 
 /* MU scan kernel: symbol / start bitmaps of the distinct id-string sets of up to 32 survivors */
@@ -91,6 +93,8 @@ struct KArgs {
 #define MU_NS 6                       /* start bitmaps resident at a time                     */
 #define MU_BW 34                      /* words per bitmap: 1024 positions + 2 zero words      */
 #define MU_K 4                        /* matches a lane records before the warp emits them    */
+#define MU_MCAP 64                    /* match records per message handed to the emit kernel  */
+#define MU_MARK 0xFFFFFFFFu           /* more than that: the fused fallback kernel takes the message */
 
 struct __align__(16) WarpSm {
     uint32_t dig[DIG_WORDS];          /* nibble-packed digits, 0xF beyond dlen               */
@@ -806,7 +810,11 @@ __device__ __forceinline__ uint64_t mu_sort3_key(uint32_t a, uint32_t b, uint32_
     return ((uint64_t)w << 48) | ((uint64_t)lo << 32) | ((uint64_t)mid << 16) | hi;
 }
 
-__device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
+/* REC = true: matches are appended to `recs` (survivor index << 24 | p | n << 11 | (tail + 1) << 22) for the emit kernel and
+ * nrec counts them (SDB_ST_MU_OVERFLOW when they do not fit); REC = false: every match is emitted on the spot. */
+#define SDB_ST_MU_OVERFLOW 0x7F
+template <bool REC>
+__device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slots, uint32_t nsurv, uint32_t *recs, uint32_t &nrec)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -902,6 +910,31 @@ __device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slo
             if (pending) continue;
             /* an exception anywhere loses every hit of the message (it escapes demodulate_mu): no need to emit first */
             if (__any_sync(FULL, L.status != SDB_ST_OK)) return SDB_ST_INDEXERROR;
+            if (REC) {
+                /* lanes k .. q flush their recorded matches, q = the first lane that is not done yet (it continues alone) */
+                const uint32_t notdone = __ballot_sync(FULL, !(L.flags & MU_F_DONE)) & (FULL << k);
+                const int q = notdone ? __ffs(notdone) - 1 : cnt;
+                const int mine_n = (lane >= k && lane <= q && lane < cnt) ? L.nm : 0;
+                int incl = mine_n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const uint32_t total = (uint32_t)__shfl_sync(FULL, incl, 31);
+                if (nrec + total > MU_MCAP) return SDB_ST_MU_OVERFLOW;
+                if (mine_n) {
+                    uint32_t *dst = recs + nrec + (incl - mine_n);
+                    const uint32_t tag = (s0i + lane) << 24;
+                    dst[0] = L.m0 | tag;
+                    if (mine_n > 1) dst[1] = L.m1 | tag;
+                    if (mine_n > 2) dst[2] = L.m2 | tag;
+                    if (mine_n > 3) dst[3] = L.m3 | tag;
+                    L.nm = 0;
+                }
+                nrec += total;
+                k = q;
+            } else
 #pragma unroll 1
             for (; k < cnt; k++) {
                 const int nmk = __shfl_sync(FULL, L.nm, k);
@@ -1435,11 +1468,13 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
         const SdbPulseMsg *m = &A.msgs[mi];
         SdbMsgOut mo;
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        if (!MS && A.match_cnt[mi] != MU_MARK) continue;         /* MU: only what the match kernel could not hand over */
         const uint32_t nsurv = A.surv_cnt[mi];
         if (nsurv) {
             const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
             stage_digits(A, sm, m, m->dlen, mi);
-            int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu(A, slots, nsurv);
+            uint32_t unused = 0;
+            int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu<false>(A, slots, nsurv, nullptr, unused);
             __syncwarp();
             const uint32_t nh = sm.nh, nw = sm.nw;
             if (status != SDB_ST_OK) {
@@ -1468,8 +1503,124 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
                     __syncwarp();
                     if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
                     __syncwarp();
-                    if (MS) scan_survivors<MS>(A, slots, nsurv); else scan_survivors_mu(A, slots, nsurv);
+                    if (MS) scan_survivors<MS>(A, slots, nsurv); else scan_survivors_mu<false>(A, slots, nsurv, nullptr, unused);
                 }
+            }
+        }
+        if (lane == 0) A.out[mi] = mo;
+        __syncwarp();
+    }
+}
+
+/* MU, kernel 2 of 3: every survivor's regex matches -> match records (message_unsynced.py:146-217) */
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_match_kernel(KArgs A)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+        const SdbPulseMsg *m = &A.msgs[mi];
+        const uint32_t nsurv = A.surv_cnt[mi];
+        uint32_t nrec = 0;
+        int status = SDB_ST_OK;
+        if (nsurv) {
+            stage_digits(A, sm, m, m->dlen, mi);
+            status = scan_survivors_mu<true>(A, A.surv + (size_t)mi * A.surv_stride, nsurv, A.match + (size_t)mi * MU_MCAP, nrec);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (status == SDB_ST_MU_OVERFLOW) A.match_cnt[mi] = MU_MARK;
+            else {
+                const bool raised = status != SDB_ST_OK;
+                A.match_cnt[mi] = raised ? 0u : nrec;
+                if (raised || nrec == 0) {                       /* nothing left to do for the emit kernel */
+                    SdbMsgOut mo;
+                    mo.hit_off = 0; mo.nhits = 0; mo.status = (uint8_t)status; mo.rsv = 0;
+                    A.out[mi] = mo;
+                    if (raised) atomicAdd(&A.ctr->raised, 1u);   /* exception: earlier hits are lost */
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* the records of one message -> bits, post-demodulation, modulematch, staged hits */
+__device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slots, const uint32_t *recs, uint32_t nrec)
+{
+    const int lane = lane_id();
+    int prev = -1, ordinal = 0;
+#pragma unroll 1
+    for (uint32_t r0 = 0; r0 < nrec; r0 += 32) {
+        const bool have = r0 + lane < nrec;
+        const uint32_t rec = have ? recs[r0 + lane] : 0u;             /* coalesced */
+        SdbSurv sv;
+        sv.start = 0; sv.c1 = sv.c0 = sv.cf = 0; sv.meta = 0;
+        if (have) sv = slots[rec >> 24];
+        const int cnt = min(32u, nrec - r0);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const uint32_t rk = __shfl_sync(FULL, rec, k);
+            const uint32_t row = __shfl_sync(FULL, (uint32_t)(sv.start >> 56), k);
+            const uint32_t c10 = __shfl_sync(FULL, (uint32_t)sv.c1 | ((uint32_t)sv.c0 << 16), k);
+            const uint32_t cfm = __shfl_sync(FULL, (uint32_t)sv.cf | ((uint32_t)sv.meta << 16), k);
+            const SdbPulseProto *pp = &A.tab.mu[row];
+            const bool has0 = pp->key[2].len != 0, hasf = ((cfm >> 16) & 0x800) != 0;
+            const uint32_t c1 = c10 & 0xFFFF, c0 = has0 ? c10 >> 16 : c1, cf = hasf ? cfm & 0xFFFF : c1;
+            const int si = (int)(rk >> 24);
+            ordinal = si == prev ? ordinal + 1 : 0;                   /* records of one survivor are consecutive, in match order */
+            prev = si;
+            mu_emit_match(A, pp, rk & 0x00FFFFFFu, c1, c0, cf, hasf, ordinal);
+        }
+    }
+}
+
+/* MU, kernel 3 of 3: match records -> hits (message_unsynced.py:220-290) */
+__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_emit_kernel(KArgs A)
+{
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+        const uint32_t nrec = A.match_cnt[mi];
+        if (nrec == 0 || nrec == MU_MARK) continue;
+        const SdbPulseMsg *m = &A.msgs[mi];
+        const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
+        const uint32_t *recs = A.match + (size_t)mi * MU_MCAP;
+        SdbMsgOut mo;
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        stage_digits(A, sm, m, m->dlen, mi);
+        mu_emit_records(A, slots, recs, nrec);
+        __syncwarp();
+        const uint32_t nh = sm.nh, nw = sm.nw;
+        if (nh) {
+            uint32_t hb = 0, wb = 0;
+            if (lane == 0) {
+                hb = atomicAdd(&A.ctr->hits, nh);
+                wb = atomicAdd(&A.ctr->words, nw);
+            }
+            hb = __shfl_sync(FULL, hb, 0);
+            wb = __shfl_sync(FULL, wb, 0);
+            mo.hit_off = hb; mo.nhits = (uint16_t)nh;
+            if (!sm.overflow) {
+                if (hb + nh <= A.hits_cap && wb + nw <= A.bits_cap) {
+                    for (uint32_t i = lane; i < nh; i += 32) {
+                        SdbHit h = sm.st_hits[IDX(i, ST_HITS)];
+                        h.bits_off += wb;
+                        A.hits[hb + i] = h;
+                    }
+                    for (uint32_t i = lane; i < nw; i += 32) A.bits[wb + i] = sm.st_bits[IDX(i, ST_WORDS)];
+                }
+            } else {
+                /* rare: more output than the staging area holds -> emit again, writing in place */
+                __syncwarp();
+                if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
+                __syncwarp();
+                mu_emit_records(A, slots, recs, nrec);
             }
         }
         if (lane == 0) A.out[mi] = mo;
@@ -1485,7 +1636,10 @@ int pulse_blocks_per_sm(int kind)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, SDB_PULSE_THREADS, 0);
     } else {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false>, SDB_PULSE_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<false>, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mu_match_kernel, SDB_PULSE_THREADS, 0);
+        int c = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, mu_emit_kernel, SDB_PULSE_THREADS, 0);
+        if (c < b) b = c;
     }
     int nb = a < b ? a : b;
     return nb > 0 ? nb : 1;
@@ -1493,7 +1647,8 @@ int pulse_blocks_per_sm(int kind)
 
 size_t mu_scratch_bytes(uint32_t stride, uint32_t chunk)
 {
-    return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t);
+    return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t)        /* survivor slots + counts */
+           + (size_t)chunk * MU_MCAP * sizeof(uint32_t) + (size_t)chunk * sizeof(uint32_t);   /* MU match records + counts */
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
@@ -1546,6 +1701,8 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     A.surv = static_cast<SdbSurv *>(mu_scratch);
     A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * stride * sizeof(SdbSurv));
     A.surv_stride = ms ? tab.n_ms : tab.n_mu;
+    A.match = A.surv_cnt + mu_chunk;
+    A.match_cnt = A.match + (size_t)mu_chunk * MU_MCAP;
     for (uint32_t off = 0; off < n; off += mu_chunk) {
         A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
@@ -1556,7 +1713,9 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
             scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
         } else {
             resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
         }
     }
     return (int)cudaGetLastError();

@@ -5,7 +5,7 @@ from pysignalduino_b200 import pack
 from tests.common import diff_report, golden_expected, load_golden
 
 PULSE = [("reference_vectors.json.gz", None), ("corpus_ms.json.gz", "MS"), ("corpus_mu.json.gz", "MU"),
-         ("fuzz_ms.json.gz", "MS"), ("fuzz_mu.json.gz", "MU")]
+         ("fuzz_ms.json.gz", "MS"), ("fuzz_mu.json.gz", "MU"), ("crafted_mu.json.gz", "MU")]
 
 
 @pytest.mark.parametrize("name,_typ", PULSE)
@@ -38,6 +38,9 @@ def test_golden_has_raised_and_multi_hit_cases():
     mu = load_golden("corpus_mu.json.gz")
     assert any(r["status"] == "IndexError" for r in mu)
     assert any(len(r["results"]) >= 4 for r in mu)
+    crafted = load_golden("crafted_mu.json.gz")          # > 4 matches per survivor, > 64 per message, empty captures
+    assert sum(1 for r in crafted if len(r["results"]) > 64) >= 5
+    assert any(r["status"] == "IndexError" for r in crafted)
     mc = load_golden("corpus_mc_strict.json.gz")
     assert all(r["status"] in ("ok", "TypeError") and not r["results"] for r in mc)
     assert any(r["status"] == "TypeError" for r in mc)
