@@ -107,6 +107,7 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     h->tab.clk = reinterpret_cast<const double *>(b + hd->off_clk);
     h->tab.rank = reinterpret_cast<const uint16_t *>(b + hd->off_rank);
     h->tab.vals = reinterpret_cast<const SdbValRow *>(b + hd->off_vals);
+    h->tab.kill = reinterpret_cast<const uint32_t *>(b + hd->off_kill);
     h->tab.n_vals = hd->n_vals; h->tab.n_mu_vals = hd->n_mu_vals;
     h->tab.mm = reinterpret_cast<const SdbMmItem *>(b + hd->off_mm);
     h->tab.hex = reinterpret_cast<const SdbHexProto *>(b + hd->off_hex);

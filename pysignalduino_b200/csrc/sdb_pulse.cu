@@ -106,6 +106,7 @@ struct __align__(16) WarpSm {
             int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
             uint8_t  M[SDB_MAX_VALS];         /* candidate-slot mask per (clock, interval) pair      */
             uint8_t  plist[256];              /* table rows that passed the prefilter, in table order */
+            uint32_t dead[SDB_KILL_WORDS];    /* bit r: protocol row r lacks a candidate slot for a mandatory value */
         };
         struct {                      /* scan_kernel<MU> */
             uint32_t Bm[MU_NB][3][MU_BW];     /* [0] bit p: a symbol of the set starts at position p; [1] / [2]: 8 / 16
@@ -1051,17 +1052,18 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
 
 /* Thread-level resolution of one MU protocol (2-digit symbols, start of <= 2 pulses).
  * Returns 0 dead, 1 resolved (codes = start | one<<8 | zero<<16 | float<<24, s0f = s0 | hasf<<16),
- * 2 = needs the warp-level path. */
+ * 2 = needs the warp-level path (for a long start: after one / zero passed a pre-screen on the whole D).
+ * after_start: the warp has resolved a long start meanwhile (D' begins at s0_in); one / zero / float follow here. */
 __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
-                                                 uint32_t &codes, uint32_t &s0f)
+                                                 uint32_t &codes, uint32_t &s0f, bool after_start, int s0_in)
 {
-    if (pp->width != 2) return 2;
+    if (pp->width != 2) return 2;                              /* 1- / 4-digit symbols: warp-level path */
     const int clk_idx = pp->clk_idx;
-    const bool long_start = pp->key[0].len > 2;               /* needs a warp-wide search: only pre-screen one / zero here */
+    const bool long_start = !after_start && pp->key[0].len > 2;   /* needs a warp-wide search: only pre-screen one / zero here */
     uint32_t acc = 0, hasf = 0;
-    int s0 = 0;
+    int s0 = after_start ? s0_in : 0;
 #pragma unroll 1
-    for (int kk = long_start ? 1 : 0; kk < 4; kk++) {         /* start (:67-88), then one / zero / float (:99-141) */
+    for (int kk = (long_start || after_start) ? 1 : 0; kk < 4; kk++) {   /* start (:67-88), then one / zero / float (:99-141) */
         const SdbKeyTpl *k = &pp->key[kk];
         if (!k->len) continue;
         uint32_t code = 0;
@@ -1323,7 +1325,9 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
         v0 = 0; v1 = (int)A.tab.n_mu_vals;
     }
     __syncwarp();
-    /* candidate-slot mask of every distinct (clock, accept interval) pair: one lane per pair */
+    /* candidate-slot mask of every distinct (clock, accept interval) pair: one lane per pair; a pair without any
+     * candidate kills every protocol that needs it (pattern_utils.py:78-80) */
+    uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
     for (int v = v0 + lane; v < v1; v += 32) {
         const SdbValRow vr = A.tab.vals[v];
@@ -1336,6 +1340,22 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
                       ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
                       ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
         sm.M[IDX(v, SDB_MAX_VALS)] = (uint8_t)mk;                                       /* empty slots hold -32768 and never qualify */
+        if (!mk) {
+            const uint4 *kr = reinterpret_cast<const uint4 *>(A.tab.kill + (size_t)v * SDB_KILL_WORDS);
+            const uint4 k0 = __ldg(&kr[0]);
+            ka.x |= k0.x; ka.y |= k0.y; ka.z |= k0.z; ka.w |= k0.w;
+            if (!MS) { const uint4 k1 = __ldg(&kr[1]); kb.x |= k1.x; kb.y |= k1.y; kb.z |= k1.z; kb.w |= k1.w; }
+        }
+    }
+    {
+        const uint32_t d0 = __reduce_or_sync(FULL, ka.x), d1 = __reduce_or_sync(FULL, ka.y), d2 = __reduce_or_sync(FULL, ka.z),
+                       d3 = __reduce_or_sync(FULL, ka.w);
+        uint32_t d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+        if (!MS) { d4 = __reduce_or_sync(FULL, kb.x); d5 = __reduce_or_sync(FULL, kb.y); d6 = __reduce_or_sync(FULL, kb.z); d7 = __reduce_or_sync(FULL, kb.w); }
+        if (lane == 0) {
+            sm.dead[0] = d0; sm.dead[1] = d1; sm.dead[2] = d2; sm.dead[3] = d3;
+            sm.dead[4] = d4; sm.dead[5] = d5; sm.dead[6] = d6; sm.dead[7] = d7;
+        }
     }
     __syncwarp();
     return true;
@@ -1350,7 +1370,6 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
     const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
-    const SdbPrefilter *pfs = MS ? A.tab.ms_pf : A.tab.mu_pf;
 
     for (uint32_t mi = wid; mi < A.n; mi += warps) {
         const SdbPulseMsg *m = &A.msgs[mi];
@@ -1373,10 +1392,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                     const uint32_t q = q0 + lane;
                     bool ok = false;
                     if (q < nrows) {
-                        const SdbPrefilter *pf = &pfs[q];
-                        const int nreq = pf->nreq;
-                        ok = true;
-                        for (int r = 0; r < nreq; r++) ok = ok && sm.M[IDX(pf->vreq[r], SDB_MAX_VALS)] != 0;
+                        ok = !((sm.dead[IDX(q >> 5, SDB_KILL_WORDS)] >> (q & 31)) & 1);
                         if (MS && ok) {
                             const double pclk = rows[q].clock;
                             ok = !(pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3));
@@ -1392,26 +1408,43 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                 for (uint32_t q0 = 0; q0 < nalive; q0 += 32) {
                     const bool have = q0 + lane < nalive;
                     const uint32_t q = have ? sm.plist[IDX(q0 + lane, 256)] : 0;
-                    int state = 0;
+                    int state = have ? 4 : 0;                         /* 4 = to be resolved by this lane */
                     SdbSurv rec;
                     rec.start = 0; rec.c1 = rec.c0 = rec.cf = 0; rec.meta = 0;
-                    if (have) {
-                        const SdbPulseProto *pq = &rows[q];
-                        uint32_t codes = 0, sf = 0;
-                        state = MS ? thread_resolve_ms(pq, sm, codes, sf) : thread_resolve_mu(pq, sm, codes, sf);
-                        rec.start = codes & 0xFF;
-                        rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
-                        rec.meta = (uint16_t)((sf & 0x7FF) | ((sf >> 16) ? 0x800 : 0));
-                    }
-                    /* the few protocols that need warp-wide searches are resolved one after the other */
-                    uint32_t cx = __ballot_sync(FULL, state == 2);
-                    while (cx) {
-                        const int b = __ffs(cx) - 1;
-                        cx &= cx - 1;
-                        const uint32_t qb = __shfl_sync(FULL, q, b);
-                        SdbSurv r2;
-                        const bool ok = MS ? resolve_ms_warp(&rows[qb], r2) : resolve_mu_warp(&rows[qb], r2);
-                        if (lane == b) { state = ok ? 1 : 0; rec = r2; }
+                    uint64_t long_start = 0;
+                    int s0w = 0;
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; pass++) {
+                        if (state == 4) {
+                            const SdbPulseProto *pq = &rows[q];
+                            uint32_t codes = 0, sf = 0;
+                            state = MS ? thread_resolve_ms(pq, sm, codes, sf) : thread_resolve_mu(pq, sm, codes, sf, pass == 1, s0w);
+                            rec.start = pass == 1 ? long_start : (uint64_t)(codes & 0xFF);
+                            rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
+                            rec.meta = (uint16_t)((sf & 0x7FF) | ((sf >> 16) ? 0x800 : 0));
+                        }
+                        if (pass == 1) break;
+                        /* the few protocols that need warp-wide searches are resolved one after the other: an MU protocol with
+                         * 2-digit symbols only needs its long start found by the warp, its lane does the rest in pass 1 */
+                        uint32_t cx = __ballot_sync(FULL, state == 2);
+                        while (cx) {
+                            const int b = __ffs(cx) - 1;
+                            cx &= cx - 1;
+                            const uint32_t qb = __shfl_sync(FULL, q, b);
+                            const SdbPulseProto *pb = &rows[qb];
+                            if (!MS && pb->width == 2) {
+                                uint64_t st = 0;
+                                int sp = 0;
+                                const int t_slot = sm.T[IDX(pb->clk_idx, SDB_MAX_CLK)][lane & 7];
+                                const bool ok = resolve_key(&pb->key[0], t_slot, 0, true, st, sp);     /* :67-88 */
+                                if (lane == b) { state = ok ? 4 : 0; long_start = st; s0w = sp; }
+                            } else {
+                                SdbSurv r2;
+                                const bool ok = MS ? resolve_ms_warp(&rows[qb], r2) : resolve_mu_warp(&rows[qb], r2);
+                                if (lane == b) { state = ok ? 1 : 0; rec = r2; }
+                            }
+                        }
+                        if (!__any_sync(FULL, state == 4)) break;
                     }
                     const uint32_t alive = __ballot_sync(FULL, state == 1);
                     if (state == 1) {                                 /* protocol-table order is the slot order */

@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 8u
+#define SDB_TBL_VERSION 9u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -87,6 +87,7 @@ typedef struct SdbValRow {
     uint16_t rsv;
 } SdbValRow;
 #define SDB_MAX_VALS 512
+#define SDB_KILL_WORDS 8
 
 /* One MS or MU protocol, 248 bytes. key[0] = sync (MS) / start (MU), [1] one, [2] zero, [3] float. */
 typedef struct SdbPulseProto {
@@ -141,6 +142,8 @@ typedef struct SdbTblHeader {
     uint32_t total;
     uint32_t n_vals, off_vals;   /* SdbValRow[]: MU pairs first, then the MS intervals (clock slot 0) */
     uint32_t n_mu_vals;
+    uint32_t off_kill;           /* uint32[n_vals][SDB_KILL_WORDS]: protocol rows (of the pair's class) that need pair v */
+    uint32_t rsv[3];
 } SdbTblHeader;
 
 #ifdef __cplusplus
@@ -150,7 +153,7 @@ static_assert(sizeof(SdbPulseProto) == 248, "SdbPulseProto layout");
 static_assert(sizeof(SdbPrefilter) == 28, "SdbPrefilter layout");
 static_assert(sizeof(SdbMmItem) == 20, "SdbMmItem layout");
 static_assert(sizeof(SdbHexProto) == 36, "SdbHexProto layout");
-static_assert(sizeof(SdbTblHeader) == 80, "SdbTblHeader layout");
+static_assert(sizeof(SdbTblHeader) == 96, "SdbTblHeader layout");
 #endif
 
 /* Device-side view of the table (pointers into the device copy of the blob). */
@@ -160,6 +163,7 @@ typedef struct SdbDevTable {
     const double        *clk;   uint32_t n_clk;     /* clk[0..n_clk) clocks, clk[n_clk..2n_clk) = 10/clock */
     const uint16_t      *rank;
     const SdbValRow     *vals;  uint32_t n_vals, n_mu_vals;
+    const uint32_t      *kill;
     const SdbMmItem     *mm;
     const SdbHexProto   *hex;   uint32_t nproto;
 } SdbDevTable;

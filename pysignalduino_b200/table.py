@@ -30,11 +30,12 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 8
+TBL_VERSION = 9
 
 MAX_UNIQ = 4
 MAX_TPL = 14
 MAX_REQ = 12
+KILL_WORDS = 8        # 32-byte kill-mask rows: up to 256 protocols per class
 
 # flags of SdbPulseProto
 PF_RECONSTRUCT = 0x01
@@ -117,9 +118,10 @@ HEADER_DTYPE = np.dtype(
         ("off_ms", "<u4"), ("off_mu", "<u4"), ("off_ms_pf", "<u4"), ("off_mu_pf", "<u4"),
         ("off_clk", "<u4"), ("off_rank", "<u4"), ("off_mm", "<u4"), ("off_hex", "<u4"),
         ("total", "<u4"), ("n_vals", "<u4"), ("off_vals", "<u4"), ("n_mu_vals", "<u4"),
+        ("off_kill", "<u4"), ("rsv0", "<u4"), ("rsv1", "<u4"), ("rsv2", "<u4"),
     ]
 )
-assert HEADER_DTYPE.itemsize == 80
+assert HEADER_DTYPE.itemsize == 96
 
 
 # --------------------------------------------------------------------------------------------
@@ -529,6 +531,16 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
     hdr["n_vals"] = len(val_arr)
     hdr["n_mu_vals"] = len(mu_vals)
     hdr["off_vals"] = add(val_arr)
+    # kill masks: bit r of row v = protocol row r (of its class) needs pair v to have a candidate slot
+    # (the transposed prefilter: one lane per pair ORs the rows of the pairs without a candidate)
+    kill = np.zeros((len(val_arr), KILL_WORDS), dtype="<u4")
+    for pf_arr in (mu_pf_arr, ms_pf_arr):
+        if len(pf_arr) > 32 * KILL_WORDS:
+            raise NotImplementedError(f"{len(pf_arr)} protocols in one class (max {32 * KILL_WORDS})")
+        for r, pf in enumerate(pf_arr):
+            for i in range(int(pf["nreq"])):
+                kill[int(pf["vreq"][i]), r >> 5] |= np.uint32(1 << (r & 31))
+    hdr["off_kill"] = add(kill)
     total = (off + 15) // 16 * 16
     hdr["total"] = total
     blob = bytearray(total)
