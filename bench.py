@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[4]): a mixed corpus, 40
 15 % MC / 5 % MN, M messages per GPU (default 10 M), each message decoded against EVERY protocol of
 its class (47 MS / 129 MU protocols; MC / MN name their protocol).  The corpus is partitioned by
 message type when it is packed (the type is the first two characters of a firmware line); one
-"step" = one pass of the hot path over the whole per-GPU shard = four kernel launches.
+"step" = one pass of the hot path over the whole per-GPU shard (per 262 144-message chunk: MS = resolve + scan,
+MU = resolve + match + emit + fused fallback; MC and MN one launch each).
 Rank r of N decodes messages [r*M, (r+1)*M) of the N*M-message corpus: weak scaling, replicated
 protocol table, no collective on the decode path.
 
@@ -359,16 +360,24 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     achieved = alg_bytes / (kern_ms[dom] / 1e3) / 1e9
     traffic = None
+    issue = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         tj = json.loads(tp.read_text()).get(s["name"])
         if tj and tj.get("messages"):
             traffic = tj["dram_bytes_per_message"] * s["n"]
+            if tj.get("warp_instructions_per_message") and clocks.get("sm_mhz"):
+                # second roofline, the one that binds: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock)
+                wi = tj["warp_instructions_per_message"] * s["n"] / (kern_ms[dom] / 1e3)
+                pk = 148 * 4 * clocks["sm_mhz"] * 1e6
+                issue = {"warp_instructions_per_message": tj["warp_instructions_per_message"], "achieved": wi, "peak": pk,
+                         "unit": "warp-instructions/s", "frac": wi / pk, "source": tj.get("source")}
     roofline = {
-        "bound": "hbm", "kernel": {0: "resolve_kernel<MS> + scan_kernel<MS> (one MS pass)", 1: "resolve_kernel<MU> + scan_kernel<MU> (one MU pass)"}.get(s["kind"], "hex_kernel"),
+        "bound": "hbm", "kernel": {0: "resolve_kernel<MS> + scan_kernel<MS> (one MS pass)",
+                                   1: "resolve_kernel<MU> + mu_match_kernel + mu_emit_kernel (one MU pass)"}.get(s["kind"], "hex_kernel"),
         "achieved": achieved,
         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kern_ms[dom],
+        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kern_ms[dom], "issue": issue,
         "note": "integer-issue bound scan/codec work: see profiles/ for issue-slot utilisation; HBM fraction is low by construction",
     }
     per_kernel = {sl["name"]: {"messages": sl["n"], "ms": kern_ms[i], "msgs_per_s": sl["n"] / (kern_ms[i] / 1e3),
