@@ -77,7 +77,7 @@ typedef struct SdbHexMsg {
     int32_t  clock;              /* MC: C=                                                       */
     int16_t  bitlen;             /* MC: L= (clamped to int16)                                    */
     uint8_t  flags;              /* SDB_MSG_VALID | SDB_HEX_* */
-    uint8_t  rsv;
+    uint8_t  rsv;                /* MN: != 0 runs that converter instead of the protocol's own (direct Conv* call) */
 } SdbHexMsg;
 
 #define SDB_HEX_TOGGLE_POLARITY 0x02  /* messagetype 'Mc' or firmware "V 3.2." (manchester.py:94-96)          */

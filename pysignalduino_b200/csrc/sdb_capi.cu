@@ -340,7 +340,7 @@ extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
                     put_hex(w, ht.nbits, false);
                 }
             } else if (ht.flags & SDB_HIT_FIELDS) {
-                if (p.method == SDB_M_PCA301) {
+                if (ht.aux == SDB_M_PCA301) {              /* MN hits carry the converter that produced them in aux */
                     snprintf(num, sizeof num, "OK 24 %u %u %u %u %u %u %u %u %u %u %04X", w[0], w[1], w[2], w[3], w[4],
                              w[5], w[6], w[7], w[8], w[9], w[10]);
                     put_str(num);
@@ -349,7 +349,7 @@ extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
                     put_str(num);
                 }
             } else {
-                if (p.method == SDB_M_KOPP) put_str("kr");
+                if (ht.aux == SDB_M_KOPP) put_str("kr");
                 put_hex(w, ht.nbits, false);
             }
         }

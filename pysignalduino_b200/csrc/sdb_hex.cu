@@ -413,7 +413,8 @@ __device__ int crc16(const Nibs &h, int first_byte, int nbytes, int poly)
 
 __device__ int mn_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMsg &m)
 {
-    const SdbHexProto p = A.tab.hex[m.proto];
+    SdbHexProto p = A.tab.hex[m.proto];
+    if (m.rsv) p.method = m.rsv;                                         /* a direct Conv*(msg_data) call names the converter */
     if (p.method < SDB_M_BRESSER_LIGHTNING || p.method == SDB_M_UNKNOWN) return SDB_ST_OK;   /* sd_protocols.py:125-149 */
     Nibs h;
     h.d = A.digits + (size_t)m.doff * 16; h.n = m.hlen;

@@ -249,7 +249,7 @@ class HexBatch:
 
 
 def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, int],
-             toggle_polarity: bool = False) -> HexBatch:
+             toggle_polarity: bool = False, method_override: int = 0) -> HexBatch:
     """Pack MC (kind 2) or MN (kind 3) dicts: protocol_id, data (hex), clock, bit_length.
 
     D must be upper-case hex (what the firmware emits): the reference's polarity inversion is an
@@ -271,10 +271,13 @@ def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, i
         ok = pid in proto_index if isinstance(pid, str) else False
         if kind == KIND_MN and "protocol_id" not in m:
             ok = False
+        if method_override:                            # direct Conv*(msg_data): the converter never looks at the table
+            ok = True
         if not ok:
             streams.append(empty)
             continue
-        rec["proto"][i] = proto_index[pid]
+        rec["proto"][i] = proto_index[pid] if not method_override else 0
+        rec["rsv"][i] = method_override
         rec["flags"][i] = MSG_VALID | (HEX_TOGGLE_POLARITY if toggle_polarity else 0)
         if data is None:
             data = ""

@@ -234,6 +234,44 @@ class SDProtocols:
             return []
         return self._one(msg_data, "MN")
 
+    # ------------------------------------------------------------------ Conv* (MN converters, batch of one on the device)
+    def _conv(self, method: int, msg_data: Dict[str, Any]) -> list:
+        eng = self.engine()
+        batch = pack.pack_hex([msg_data], pack.KIND_MN, {}, method_override=method)
+        res = eng.demod_host(batch, mc_repaired=self.mc_repaired)
+        statuses, results = self.format_results(batch, res)
+        if statuses[0] != "ok":
+            raise STATUS_EXC[int(res.out["status"][0])](f"reference converter raises {statuses[0]} on this message")
+        return results[0]
+
+    def ConvBresser_lightning(self, msg_data, msg_type="MN"):
+        """helpers.py:223-279"""
+        return self._conv(14, msg_data)
+
+    def ConvBresser_5in1(self, msg_data, msg_type="MN"):
+        """helpers.py:382-425"""
+        return self._conv(15, msg_data)
+
+    def ConvBresser_6in1(self, msg_data, msg_type="MN"):
+        """helpers.py:427-471"""
+        return self._conv(16, msg_data)
+
+    def ConvBresser_7in1(self, msg_data, msg_type="MN"):
+        """helpers.py:473-523"""
+        return self._conv(17, msg_data)
+
+    def ConvPCA301(self, msg_data, msg_type="MN"):
+        """helpers.py:525-579"""
+        return self._conv(18, msg_data)
+
+    def ConvKoppFreeControl(self, msg_data, msg_type="MN"):
+        """helpers.py:581-628"""
+        return self._conv(19, msg_data)
+
+    def ConvLaCrosse(self, msg_data, msg_type="MN"):
+        """helpers.py:630-716"""
+        return self._conv(20, msg_data)
+
     # ------------------------------------------------------------------ postDemo_* (unit ops on the device)
     def _postdemo(self, method: str, bit_msg_array):
         rc, out = self.engine().unit_postdemod(PD_IDS[method], bit_msg_array)

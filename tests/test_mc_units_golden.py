@@ -38,3 +38,21 @@ def test_device_mc_units_match_reference():
                 bad.append((m, pid, mcbitnum, len(bits), got, (rc, out)))
         sdp.engine().close()
     assert not bad, (len(bad), total, bad[:8])
+
+
+def test_conv_goldens_cover_every_converter():
+    seen = {}
+    for m, msg, st, out in load_golden("conv_units.json.gz"):
+        seen.setdefault(m, set()).add(bool(out))
+    assert len(seen) == 7 and all(v == {True, False} for v in seen.values()), seen
+
+
+@pytest.mark.gpu
+def test_device_conv_units_match_reference(sdp):
+    """Direct Conv*(msg_data) calls (helpers.py:223-716), as the reference's tests/test_helpers.py makes them."""
+    bad = []
+    for m, msg, st, out in load_golden("conv_units.json.gz"):
+        got = getattr(sdp, m)(dict(msg))
+        if got != out:
+            bad.append((m, msg, got, out))
+    assert not bad, (len(bad), bad[:5])
