@@ -169,6 +169,34 @@ int sdb_format_hits(const SdbHandle *h, int kind,
                     char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used);
 
 /*
+ * Firmware text lines -> hits (signalduino/parser/ms.py:26-69, mu.py:26-82 without the
+ * per-line Python work).  `text` holds payload lines of ONE message type (MS or MU), already stripped of the
+ * STX/ETX framing (base.py:174-193); line i is text[line_off[i] .. +line_len[i]), offsets ascending, lines disjoint.
+ * A tokenizer kernel replaces _parse_to_dict (ms.py:71-84), the MU validity regex (mu.py:48-52) and the input gates
+ * of demodulate_ms / _mu (message_synced.py:21-66, message_unsynced.py:22-35); the demodulation kernels follow.
+ * Results are indexed by line.  info[i].status: SDB_LINE_INVALID = the reference yields [] for the line,
+ * SDB_LINE_OK = decoded here, SDB_LINE_HOSTPATH = outside the canonical grammar (non-ASCII, duplicate / multi-digit
+ * pattern ids, values float() reads differently, D > 1024 digits): the caller packs that line itself.
+ * All pointers are HOST pointers.
+ */
+typedef struct SdbLineInfo {
+    uint8_t  status;             /* SDB_LINE_*                                                   */
+    uint8_t  has_r;              /* the line has an R= field (meta.rssi = its text)               */
+    uint16_t r_len;
+    uint32_t r_off;              /* offset of the R value inside the line                         */
+    int32_t  clock;              /* MS: abs(P[CP]) (meta.clock, message_synced.py:239)            */
+} SdbLineInfo;
+#define SDB_LINE_INVALID  0
+#define SDB_LINE_OK       1
+#define SDB_LINE_HOSTPATH 2
+
+int sdb_demod_lines_host(SdbHandle *h, int kind,
+                         const uint8_t *text, size_t text_len,
+                         const uint32_t *line_off, const uint32_t *line_len, uint32_t n,
+                         SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                         uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info);
+
+/*
  * Unit-op entry points: run ONE device function on ONE input (a 1-warp launch).  They back
  * the scalar helper methods of the drop-in class so that the reference's own unit tests
  * (tests/test_postdemodulation.py, tests/test_manchester_protocols.py, tests/test_helpers.py)

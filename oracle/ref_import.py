@@ -80,3 +80,18 @@ def repaired_class():
 
     _REPAIRED = SDProtocolsRepaired
     return _REPAIRED
+
+
+def reference_parser_module():
+    """signalduino.parser of the reference WITHOUT running signalduino/__init__.py (it imports the asyncio controller
+    and its third-party dependencies: aiomqtt, serial, ... — SURVEY App. D).  A bare package object with the right
+    __path__ lets `signalduino.parser`, `.types` and `.exceptions` import normally."""
+    import importlib
+    import types
+
+    reference_class()                                   # sd_protocols on sys.path
+    if "signalduino" not in sys.modules:
+        pkg = types.ModuleType("signalduino")
+        pkg.__path__ = [str(REFERENCE_ROOT / "signalduino")]
+        sys.modules["signalduino"] = pkg
+    return importlib.import_module("signalduino.parser")

@@ -29,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host",
 ]
 
 
@@ -79,12 +79,19 @@ def load_library() -> C.CDLL:
     L.sdb_unit_mc.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32,
                               C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.sdb_demod_lines_host.restype = C.c_int
+    L.sdb_demod_lines_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
         raise SdbError("libsdb200.so ABI version mismatch")
     _lib = L
     return L
+
+
+LINEINFO_DTYPE = np.dtype([("status", "u1"), ("has_r", "u1"), ("r_len", "<u2"), ("r_off", "<u4"), ("clock", "<i4")])
+LINE_INVALID, LINE_OK, LINE_HOSTPATH = 0, 1, 2
 
 
 class Result:
@@ -159,6 +166,34 @@ class Engine:
         if rc not in (SDB_OK, SDB_E_OVERFLOW):
             raise self._err(rc, "sdb_demod_host")
         return rc
+
+    # ---- text lines (tokenizer kernel + demodulation) ---------------------------------------
+    def demod_lines(self, kind: int, text: np.ndarray, line_off: np.ndarray, line_len: np.ndarray,
+                    hits_cap: int = 0, bits_cap: int = 0):
+        """Payload lines of one type (MS / MU) -> (Result indexed by line, SdbLineInfo array)."""
+        n = len(line_off)
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        line_off = np.ascontiguousarray(line_off, dtype=np.uint32)
+        line_len = np.ascontiguousarray(line_len, dtype=np.uint32)
+        out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
+        info = np.zeros(n, dtype=LINEINFO_DTYPE)
+        hits_cap = hits_cap or max(1024, 4 * n)
+        bits_cap = bits_cap or max(4096, 16 * n)
+        ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
+        while True:
+            hits = np.empty(hits_cap, dtype=pack.HIT_DTYPE)
+            bits = np.empty(bits_cap, dtype=np.uint32)
+            rc = self.lib.sdb_demod_lines_host(self.h, kind, text.ctypes.data, text.nbytes, line_off.ctypes.data,
+                                               line_len.ctypes.data, n, out.ctypes.data, hits.ctypes.data, hits_cap,
+                                               bits.ctypes.data, bits_cap, ctr.ctypes.data, info.ctypes.data)
+            if rc == SDB_E_OVERFLOW:
+                hits_cap = max(hits_cap, int(ctr["hits"][0]) + 16)
+                bits_cap = max(bits_cap, int(ctr["words"][0]) + 16)
+                continue
+            if rc != SDB_OK:
+                raise self._err(rc, "sdb_demod_lines_host")
+            nh, nw = int(ctr["hits"][0]), int(ctr["words"][0])
+            return Result(kind, out, hits[:nh], bits[:nw], ctr[0]), info
 
     # ---- device-pointer call (pointers are ints, e.g. torch tensor.data_ptr()) ---------------
     def demod_pulse_device(self, kind: int, d_msgs: int, d_digits: int, n: int, d_out: int, d_hits: int, hits_cap: int,

@@ -33,6 +33,8 @@ struct SdbHandle {
     uint32_t *d_bits = nullptr;  size_t cap_bits = 0;
     SdbCounters *d_ctr = nullptr;
     uint8_t *d_unit = nullptr;          /* unit-op scratch */
+    uint8_t *d_text = nullptr;  size_t cap_text = 0;     /* sdb_demod_lines_host: line text */
+    uint8_t *d_lines = nullptr; size_t cap_lines = 0;    /* line offsets, lengths, SdbLineInfo */
     void *d_mu_scratch = nullptr;       /* MU survivor slots (resolve kernel -> scan kernel), allocated on first MU call */
     uint32_t mu_chunk = 0;
     cudaStream_t stream = nullptr;      /* compute + final copies of the host-buffer path */
@@ -125,7 +127,7 @@ extern "C" void sdb_destroy(SdbHandle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch);
+    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch); cudaFree(h->d_text); cudaFree(h->d_lines);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
@@ -275,6 +277,54 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
         CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
+    if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
+    if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
+    if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SDB_OK;
+}
+
+extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
+                                    const uint8_t *text, size_t text_len,
+                                    const uint32_t *line_off, const uint32_t *line_len, uint32_t n,
+                                    SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                                    uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info)
+{
+    if (!h) return SDB_E_ARG;
+    if (kind != SDB_KIND_MS && kind != SDB_KIND_MU) return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: kind must be MS or MU");
+    if (!counters || (n && (!text || !line_off || !line_len || !out || !info))) return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: null pointer");
+    CK(cudaSetDevice(h->device));
+    memset(counters, 0, sizeof *counters);
+    if (n == 0) return SDB_OK;
+    if (text_len >= (1ull << 32)) return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: text larger than 4 GiB");
+    for (uint32_t i = 0; i < n; i++) {
+        if ((size_t)line_off[i] + line_len[i] > text_len || (i && line_off[i] < line_off[i - 1] + line_len[i - 1]))
+            return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: lines must be ascending, disjoint and inside the text");
+    }
+    int rc;
+    const size_t pool_bytes = sdb::lines_pool_bytes(text_len, n);
+    if ((rc = grow(h, reinterpret_cast<uint8_t *&>(h->d_msgs), h->cap_msgs, sizeof(SdbPulseMsg) * (size_t)n))) return rc;
+    if ((rc = grow(h, h->d_digits, h->cap_digits, pool_bytes + 64))) return rc;
+    if ((rc = grow(h, h->d_out, h->cap_out, sizeof(SdbMsgOut) * (size_t)n))) return rc;
+    if ((rc = grow(h, h->d_hits, h->cap_hits, sizeof(SdbHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
+    if ((rc = grow(h, h->d_bits, h->cap_bits, sizeof(uint32_t) * (size_t)(bits_cap ? bits_cap : 1)))) return rc;
+    if ((rc = grow(h, h->d_text, h->cap_text, text_len + 16))) return rc;
+    if ((rc = grow(h, h->d_lines, h->cap_lines, (2 * sizeof(uint32_t) + sizeof(SdbLineInfo)) * (size_t)n))) return rc;
+    cudaStream_t st = h->stream;
+    uint32_t *d_off = reinterpret_cast<uint32_t *>(h->d_lines), *d_len = d_off + n;
+    SdbLineInfo *d_info = reinterpret_cast<SdbLineInfo *>(d_len + n);
+    CK(cudaMemcpyAsync(h->d_text, text, text_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, line_off, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_len, line_len, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
+    rc = sdb::launch_tokenize(kind, h->d_text, d_off, d_len, n, dm, h->d_digits, d_info, h->sm_count, st);
+    if (rc != 0) return set_err(h, SDB_E_CUDA, "tokenize kernel launch", static_cast<cudaError_t>(rc));
+    rc = sdb_demod_pulse_device(h, kind, dm, h->d_digits, n, h->d_out, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+    if (rc != SDB_OK) return rc;
+    CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(info, d_info, sizeof(SdbLineInfo) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
     if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
     if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
