@@ -191,6 +191,7 @@ def run_ours(args):
 
     from corpus.corpus import Corpus
     from pysignalduino_b200 import SDProtocols, pack
+    from pysignalduino_b200.capi import LINEINFO_DTYPE
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,6 +338,45 @@ def run_ours(args):
         c = ctrs[s["name"]]
         assert int(hs["ctr"]["hits"][0]) == int(c[0]) and int(hs["ctr"]["words"][0]) == int(c[1]), "device / host-path results differ"
 
+    # ---- line-parser row: firmware TEXT lines of the MS / MU shards through sdb_demod_lines_host
+    #      (tokenizer kernel + demodulation kernels, pinned host text in, results out), rank 0 only ----
+    lines_info = None
+    if rank == 0 and not args.no_lines:
+        import ctypes as C
+
+        legs, n_lines, text_bytes, t_lines, ok_lines, lines_hits = [], 0, 0, 0.0, 0, 0
+        for s, hs in zip(slots, host):
+            if s["kind"] > 1:
+                continue
+            text, off, ln = corp.render_lines(s["batch"])
+            t_text = torch.from_numpy(text.copy()).pin_memory()
+            info = np.zeros(s["n"], dtype=LINEINFO_DTYPE)
+            legs.append((s, hs, t_text, off, ln, info))
+            n_lines += s["n"]
+            text_bytes += int(text.nbytes)
+
+        def lines_step():
+            for s, hs, t_text, off, ln, info in legs:
+                rc = eng.lib.sdb_demod_lines_host(eng.h, s["kind"], t_text.data_ptr(), t_text.numel(), off.ctypes.data, ln.ctypes.data,
+                                                  s["n"], hs["out"].ctypes.data, hs["hits"].ctypes.data, len(hs["hits"]),
+                                                  hs["bits"].ctypes.data, len(hs["bits"]), hs["ctr"].ctypes.data, info.ctypes.data)
+                if rc != 0:
+                    raise SystemExit(f"bench.py: sdb_demod_lines_host failed ({rc})")
+
+        if legs:
+            lines_step()
+            nrep = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                lines_step()
+            t_lines = (time.perf_counter() - t0) / nrep
+            for s, hs, t_text, off, ln, info in legs:
+                ok_lines += int((info["status"] == 1).sum())
+                lines_hits += int(hs["ctr"]["hits"][0])
+            lines_info = {"value": n_lines / t_lines, "unit": "lines/s", "lines": n_lines, "text_bytes_per_step": text_bytes,
+                          "decoded_on_device": ok_lines, "hits": lines_hits,
+                          "note": "MS + MU shards rendered as firmware payload lines; tokenizer + demodulation kernels, host text in / results out"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -400,7 +440,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "per_kernel": per_kernel,
-        "corpus_gen_s": t_gen,
+        "corpus_gen_s": t_gen, "lines": lines_info,
     }
     emit(line)
     if world > 1:
@@ -415,6 +455,7 @@ def main():
     ap.add_argument("--messages", type=int, default=10_000_000, help="messages per GPU (mixed corpus)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-lines", action="store_true", help="skip the text-line (tokenizer) leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

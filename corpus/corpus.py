@@ -160,6 +160,26 @@ class Corpus:
         return pack.PulseBatch(kind, msgs, digits, RssiCodes(rssi), clock)
 
 
+    def render_lines(self, batch: pack.PulseBatch):
+        """Payload lines of a packed MS / MU batch: (text uint8, line_off uint32, line_len uint32), '\\n'-separated."""
+        L = lib()
+        L.sdc_render_lines.restype = C.c_int64
+        n = batch.n
+        rssi = np.ascontiguousarray(batch.rssi.codes if isinstance(batch.rssi, RssiCodes) else np.full(n, -1), dtype=np.int16)
+        msgs = np.ascontiguousarray(batch.msgs)
+        digits = np.ascontiguousarray(batch.digits)
+        off = np.zeros(n, dtype=np.uint32)
+        ln = np.zeros(n, dtype=np.uint32)
+        cap = int(64 * n + 2 * int(batch.msgs["dlen"].astype(np.int64).sum()) + 64)
+        while True:
+            text = np.empty(cap, dtype=np.uint8)
+            used = L.sdc_render_lines(C.c_int(batch.kind), C.c_void_p(msgs.ctypes.data), C.c_void_p(digits.ctypes.data),
+                                      C.c_void_p(rssi.ctypes.data), C.c_int64(n), C.c_void_p(text.ctypes.data), C.c_int64(cap),
+                                      C.c_void_p(off.ctypes.data), C.c_void_p(ln.ctypes.data))
+            if used <= cap:
+                return text[:used], off, ln
+            cap = int(used) + 64
+
     def hexmsgs(self, kind: int, n: int, seed: int | None = None, lo: int = 0, hi: int | None = None) -> pack.HexBatch:
         """Messages [lo, hi) of an n-message MC (kind 2) or MN (kind 3) corpus."""
         if hi is None:

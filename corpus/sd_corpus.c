@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "../include/sdb200.h"
@@ -295,3 +296,45 @@ int sdc_gen_pulse(const GenProto *tab, int ntab, const int32_t *ids, int nids, i
 }
 
 void sdc_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------------------------
+ * Packed MS / MU batch -> firmware payload lines ("MS;P0=-3886;...;D=1310...;CP=1;SP=3;R=33;"), one per message,
+ * '\n'-separated: the input of the line-parser row (signalduino/parser/ms.py, mu.py).  A record without
+ * SDB_MSG_VALID is rendered with an empty D (the parser drops it just the same).  Returns the bytes needed
+ * (render again with a larger buffer when > cap).
+ * ------------------------------------------------------------------------------------------ */
+int64_t sdc_render_lines(int kind, const SdbPulseMsg *msgs, const uint8_t *digits, const int16_t *rssi, int64_t n,
+                         char *text, int64_t cap, uint32_t *off, uint32_t *len)
+{
+    int64_t used = 0;
+    char buf[SDB_MAX_DIGITS + 256];
+    for (int64_t i = 0; i < n; i++) {
+        const SdbPulseMsg *m = &msgs[i];
+        int k = 0;
+        k += sprintf(buf + k, kind == SDB_KIND_MS ? "MS;" : "MU;");
+        const int valid = (m->flags & SDB_MSG_VALID) != 0;
+        if (valid)
+            for (int s = 0; s < m->npat; s++) k += sprintf(buf + k, "P%u=%d;", (m->pat_ids >> (4 * s)) & 0xF, m->pat[s]);
+        else
+            k += sprintf(buf + k, "P0=1;P1=-1;");
+        buf[k++] = 'D'; buf[k++] = '=';
+        if (valid) {
+            const uint8_t *d = digits + (size_t)m->doff * 16;
+            for (int j = 0; j < m->dlen; j++) {
+                int nib = (d[j >> 1] >> ((j & 1) * 4)) & 0xF;
+                buf[k++] = nib <= 9 ? (char)('0' + nib) : 'x';
+            }
+        }
+        buf[k++] = ';';
+        if (kind == SDB_KIND_MS) {
+            int cpid = m->cp != 0xFF ? (int)((m->pat_ids >> (4 * m->cp)) & 0xF) : 9;
+            k += sprintf(buf + k, "CP=%d;SP=0;", cpid);
+        }
+        if (rssi && rssi[i] >= 0) k += sprintf(buf + k, "R=%d;", (int)rssi[i]);
+        if (off) off[i] = (uint32_t)used;
+        if (len) len[i] = (uint32_t)k;
+        if (used + k + 1 <= cap) { memcpy(text + used, buf, (size_t)k); text[used + k] = '\n'; }
+        used += k + 1;
+    }
+    return used;
+}

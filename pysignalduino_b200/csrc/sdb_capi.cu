@@ -313,18 +313,39 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
     cudaStream_t st = h->stream;
     uint32_t *d_off = reinterpret_cast<uint32_t *>(h->d_lines), *d_len = d_off + n;
     SdbLineInfo *d_info = reinterpret_cast<SdbLineInfo *>(d_len + n);
-    CK(cudaMemcpyAsync(h->d_text, text, text_len, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_off, line_off, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_len, line_len, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
-    rc = sdb::launch_tokenize(kind, h->d_text, d_off, d_len, n, dm, h->d_digits, d_info, h->sm_count, st);
-    if (rc != 0) return set_err(h, SDB_E_CUDA, "tokenize kernel launch", static_cast<cudaError_t>(rc));
-    rc = sdb_demod_pulse_device(h, kind, dm, h->d_digits, n, h->d_out, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
-    if (rc != SDB_OK) return rc;
+    /* per chunk of SDB_MU_CHUNK lines: H2D of the chunk's text / offsets (copy stream) -> tokenizer + demodulation kernels
+     * (compute stream) -> D2H of the result slots and line infos (d2h stream); chunk k+1's copy overlaps chunk k's kernels.
+     * Device offsets are the caller's own (global) offsets, so digit-pool units and hit.msg need no rebasing. */
+    const uint32_t C = SDB_MU_CHUNK;
+    const uint32_t nchunks = (n + C - 1) / C;
+    while (h->ev_h2d.size() < nchunks) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_h2d.push_back(a); h->ev_done.push_back(b);
+    }
+    CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
+        const size_t t0 = line_off[lo], t1 = (size_t)line_off[lo + cnt - 1] + line_len[lo + cnt - 1];
+        CK(cudaMemcpyAsync(h->d_text + t0, text + t0, t1 - t0, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(d_off + lo, line_off + lo, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaMemcpyAsync(d_len + lo, line_len + lo, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_h2d[k], h->copy_stream));
+        CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
+        rc = sdb::launch_tokenize(kind, h->d_text, d_off + lo, d_len + lo, cnt, lo, dm + lo, h->d_digits, d_info + lo, h->sm_count, st);
+        if (rc != 0) return set_err(h, SDB_E_CUDA, "tokenize kernel launch", static_cast<cudaError_t>(rc));
+        rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
+        if (rc != SDB_OK) return rc;
+        CK(cudaEventRecord(h->ev_done[k], st));
+        CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
+        CK(cudaMemcpyAsync(out + lo, h->d_out + lo, sizeof(SdbMsgOut) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CK(cudaMemcpyAsync(info + lo, d_info + lo, sizeof(SdbLineInfo) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
     CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(info, d_info, sizeof(SdbLineInfo) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(h->d2h_stream));
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
     if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
     if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));

@@ -9,16 +9,22 @@
  *                                                          sd_protocols/message_unsynced.py:22-35
  * i.e. everything between extract_payload() (base.py:174-193, host) and the demodulation kernels.
  *
- * One THREAD per line: the work is a byte-serial field scan (100-900 bytes per line, ~10 instructions per
- * byte) and 32 lines per warp keep the issue slots busy; the per-line cost is ~1 % of the MU demodulation
- * of the same line, so there is nothing to gain from a warp-cooperative scan.  Each line's digit stream goes to
- * the digit pool at unit (line_off >> 5) + i (16-byte units): D is shorter than the line, so the regions never
- * overlap and no prefix sum is needed.
+ * One WARP per line (a first version with one thread per line diverged on every byte loop and cost 6-11 k warp
+ * instructions per line — as much as demodulating it):
+ *   1. the line is staged in shared memory with coalesced 16-byte loads;
+ *   2. 32 bytes per step: __ballot_sync finds the ';' separators (and any non-ASCII byte), the lanes holding one
+ *      record the field boundaries;
+ *   3. one LANE per field classifies and parses its (short) field: key, '=' position, canonical integer value;
+ *   4. ballots / shuffles apply the dict semantics across fields: last D / CP / SP / R wins, pattern slots in order
+ *      of first appearance, the MU regex as conditions on the field-class masks;
+ *   5. the warp checks and nibble-packs the D digits, 8 per lane, straight into the digit pool (coalesced), at unit
+ *      (line_off >> 5) + i (16-byte units): D is shorter than the line, so regions never overlap and no prefix
+ *      sum is needed.
  *
  * Exactness: the device accepts the canonical grammar the firmware emits (keys D, CP, SP, R, P<d> with
- * values -?[0-9]{1,10}); every line outside it (non-ASCII bytes, duplicate or multi-digit pattern ids,
- * values float() parses differently, D longer than 1024 digits) is flagged SDB_LINE_HOSTPATH and goes
- * through the host packer (pack.py), never decoded differently.
+ * values -?[0-9]{1,10}); every line outside it (non-ASCII bytes, duplicate or multi-digit pattern ids in MS,
+ * values float() parses differently, D longer than 1024 digits, more than 32 fields, longer than 1280 bytes) is
+ * flagged SDB_LINE_HOSTPATH and goes through the host packer (pack.py), never decoded differently.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,24 +34,31 @@
 
 namespace sdb {
 
+#define FULL 0xffffffffu
+#define LN_MAX 1280                              /* staged bytes per line; longer lines take the host path */
+#define LN_WARPS 8
+
 struct LArgs {
     const uint8_t *text;
     const uint32_t *line_off, *line_len;
     uint32_t n;
+    uint32_t base;            /* index of line 0 of this launch in the caller's batch (digit-pool unit = (off >> 5) + base + i) */
     SdbPulseMsg *msgs;
-    uint8_t *pool;            /* digit pool, ((text_len >> 5) + n + 2) * 16 bytes */
+    uint8_t *pool;            /* digit pool, ((text_len >> 5) + n + 4) * 16 bytes */
     SdbLineInfo *info;
 };
 
-struct Span { int a, b; };                     /* [a, b) inside the line; a < 0 = key absent */
+struct __align__(16) LineSm {
+    uint8_t  buf[LN_MAX + 48];                   /* the line, at the same 16-byte phase as in global memory */
+    uint16_t fend[33];                           /* position of the ';' that ends field k */
+    uint32_t rec[12];                            /* SdbPulseMsg being assembled */
+};
+
+/* field classes (step 3) */
+enum { F_EMPTY = 0, F_IGNORE, F_PAT, F_D, F_CP, F_SP, F_R, F_OTHER_OK, F_HOST, F_BAD };
 
 __device__ __forceinline__ bool is_dig(uint8_t c) { return c >= '0' && c <= '9'; }
-__device__ __forceinline__ bool all_digits(const uint8_t *s, Span v)
-{
-    if (v.a < 0 || v.b <= v.a) return false;   /* "".isdigit() is False */
-    for (int i = v.a; i < v.b; i++) if (!is_dig(s[i])) return false;
-    return true;
-}
+
 /* -?[0-9]{1,10} inside int32 (without INT_MIN): the only value syntax the device packs itself */
 __device__ __forceinline__ bool canon_int(const uint8_t *s, int a, int b, int32_t &out)
 {
@@ -58,174 +71,244 @@ __device__ __forceinline__ bool canon_int(const uint8_t *s, int a, int b, int32_
     out = (int32_t)(neg ? -v : v);
     return true;
 }
-
-struct Pats {
-    int32_t val[SDB_MAX_SLOTS];
-    uint32_t ids;
-    int n;
-    __device__ __forceinline__ int find(int id) const
-    {
-        for (int s = 0; s < n; s++) if ((int)((ids >> (4 * s)) & 0xF) == id) return s;
-        return -1;
-    }
-};
-
-/* nibble-pack D (digits only by construction) into the pool region of this line, 0xF padding to the 16-byte unit */
-__device__ __forceinline__ void pack_digits(const uint8_t *s, Span d, uint8_t *pool, uint32_t unit)
+__device__ __forceinline__ bool short_digits(const uint8_t *s, int a, int b)      /* str.isdigit() on a short value */
 {
-    const int dlen = d.b - d.a;
-    uint32_t *w = reinterpret_cast<uint32_t *>(pool + (size_t)unit * 16);
-    const int nwords = ((dlen + 31) >> 5) * 4;
-    for (int k = 0; k < nwords; k++) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int i = 8 * k + j;
-            const uint32_t nib = i < dlen ? (is_dig(s[d.a + i]) ? (uint32_t)(s[d.a + i] - '0') : 0xEu) : 0xFu;
-            x |= nib << (4 * j);
+    if (b <= a) return false;
+    for (int i = a; i < b; i++) if (!is_dig(s[i])) return false;
+    return true;
+}
+
+/* lane: classify field [a, b).  MS follows _parse_to_dict (key = text before the first '='), MU the alternatives of the
+ * validity regex.  va / vb = value span, id / val = pattern id and value. */
+template <bool MU>
+__device__ __forceinline__ int classify(const uint8_t *s, int a, int b, int &va, int &vb, int &id, int32_t &val)
+{
+    const int fl = b - a;
+    va = vb = b; id = 0; val = 0;
+    if (fl == 0) return MU ? F_BAD : F_EMPTY;
+    const uint8_t c0 = s[a];
+    if (MU) {
+        if (fl >= 4 && c0 == 'P' && s[a + 1] >= '0' && s[a + 1] <= '7' && s[a + 2] == '=') {
+            int p = a + 3;
+            if (s[p] == '-') p++;
+            const int nd = b - p;
+            if (nd >= 1 && nd <= 5 && short_digits(s, p, b)) { canon_int(s, a + 3, b, val); id = s[a + 1] - '0'; return F_PAT; }
+            return F_BAD;
         }
-        w[k] = x;
+        if (fl >= 4 && c0 == 'D' && s[a + 1] == '=') { va = a + 2; vb = b; return F_D; }     /* \d{2,}: checked by the warp */
+        if (fl == 4 && c0 == 'C' && s[a + 1] == 'P' && s[a + 2] == '=' && is_dig(s[a + 3])) return F_OTHER_OK;
+        if (fl >= 3 && c0 == 'R' && s[a + 1] == '=') { va = a + 2; vb = b; return short_digits(s, va, vb) ? F_R : F_BAD; }
+        if (fl == 1 && (c0 == 'O' || c0 == 'e' || c0 == 'p')) return F_OTHER_OK;
+        if (fl == 3 && c0 == 'w' && s[a + 1] == '=' && is_dig(s[a + 2])) return F_OTHER_OK;
+        return F_BAD;
     }
+    if (c0 == 'D' && (fl == 1 || s[a + 1] == '=')) { va = fl == 1 ? b : a + 2; return F_D; }
+    if (c0 == 'R' && (fl == 1 || s[a + 1] == '=')) { va = fl == 1 ? b : a + 2; return F_R; }
+    if (fl >= 2 && (c0 == 'C' || c0 == 'S') && s[a + 1] == 'P' && (fl == 2 || s[a + 2] == '=')) {
+        va = fl == 2 ? b : a + 3;
+        return c0 == 'C' ? F_CP : F_SP;
+    }
+    if (c0 == 'P' && fl >= 2 && is_dig(s[a + 1])) {
+        int e = a + 1, pid = 0;
+        while (e < b && is_dig(s[e])) { pid = pid * 10 + (s[e] - '0'); if (pid > 1000) pid = 1000; e++; }
+        if (e < b && s[e] != '=') return F_IGNORE;                      /* key with other characters: not a pattern key */
+        /* a pattern key (message_synced.py:50-57): canonical single-digit id and canonical value, or the host decides */
+        if (e == b || pid > 9 || !canon_int(s, e + 1, b, val)) return F_HOST;
+        id = pid;
+        return F_PAT;
+    }
+    return F_IGNORE;
 }
 
 template <bool MU>
-__device__ void tokenize_one(const uint8_t *s, int len, uint32_t unit, uint8_t *pool, SdbPulseMsg &rec, SdbLineInfo &info)
+__global__ void __launch_bounds__(LN_WARPS * 32) tokenize_kernel(LArgs A)
 {
-    info.status = SDB_LINE_INVALID; info.has_r = 0; info.r_len = 0; info.r_off = 0; info.clock = 0;
-    for (int i = 0; i < SDB_MAX_SLOTS; i++) rec.pat[i] = 0;
-    rec.doff = unit; rec.dlen = 0; rec.npat = 0; rec.cp = 0xFF; rec.pat_ids = 0; rec.flags = 0;
-    rec.rsv[0] = rec.rsv[1] = rec.rsv[2] = 0;
-    if (len > 8191) { info.status = SDB_LINE_HOSTPATH; return; }
-    for (int i = 0; i < len; i++)
-        if (s[i] >= 0x80) { info.status = SDB_LINE_HOSTPATH; return; }      /* str.isdigit() / \d know more digits than ASCII */
+    __shared__ LineSm g_ls[LN_WARPS];
+    LineSm &sm = g_ls[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    Span D = {-1, -1}, CP = {-1, -1}, SP = {-1, -1}, R = {-1, -1};
-    Pats P;
-    P.ids = 0; P.n = 0;
-    bool host = false;
+    for (uint32_t li = wid; li < A.n; li += warps) {
+        const uint32_t off = A.line_off[li];
+        const int len = (int)A.line_len[li];
+        const uint32_t unit = (off >> 5) + A.base + li;
+        int status = SDB_LINE_INVALID;
+        /* record defaults: everything zero, cp = 0xFF */
+        if (lane < 12) sm.rec[lane] = lane == 8 ? unit : (lane == 9 ? 0xFF000000u : 0u);
+        int32_t clock = 0;
+        int r_off = 0, r_len = 0, has_r = 0;
+        __syncwarp();
 
-    if (MU) {
-        /* ^(?=.*D=\d+)(?:MU;(?:P[0-7]=-?[0-9]{1,5};){2,8}((?:D=\d{2,};)|(?:CP=\d;)|(?:R=\d+;)|(?:O;)|(?:e;)|(?:p;)|(?:w=\d;))*)$
-         * (mu.py:48): no alternative of the second group matches a pattern field and vice versa, so the split is unique */
-        if (len < 3 || s[0] != 'M' || s[1] != 'U' || s[2] != ';') return;
-        int p = 3, npf = 0;
-        bool tail = false;
-        while (p < len) {
-            int q = p;
-            while (q < len && s[q] != ';') q++;
-            if (q >= len) return;                                           /* every field ends with ';' */
-            const int fl = q - p;
-            bool is_pat = false;
-            if (fl >= 4 && s[p] == 'P' && s[p + 1] >= '0' && s[p + 1] <= '7' && s[p + 2] == '=') {
-                int a = p + 3;
-                if (s[a] == '-') a++;
-                const int nd = q - a;
-                is_pat = nd >= 1 && nd <= 5;
-                for (int i = a; i < q && is_pat; i++) is_pat = is_dig(s[i]);
+        if (len > LN_MAX) status = SDB_LINE_HOSTPATH;
+        else if (len > 0) {
+            /* 1. stage (16-byte loads from the aligned address below the line start) */
+            const uint32_t ph = off & 15u;
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.text + (off - ph));
+            const int nq = (int)((ph + (uint32_t)len + 15u) >> 4);
+            for (int q = lane; q < nq; q += 32) reinterpret_cast<uint4 *>(sm.buf)[q] = __ldg(&src[q]);
+            __syncwarp();
+            const uint8_t *s = sm.buf + ph;
+
+            /* 2. separators; a trailing part without ';' is a field too (str.split) */
+            int nf = 0;
+            bool nonascii = false;
+            for (int w0 = 0; w0 < len; w0 += 32) {
+                const int p = w0 + lane;
+                const uint8_t c = p < len ? s[p] : 0;
+                const uint32_t semi = __ballot_sync(FULL, c == ';');
+                nonascii |= __any_sync(FULL, c >= 0x80);
+                if (c == ';') {
+                    const int k = nf + __popc(semi & ((1u << lane) - 1));
+                    if (k < 33) sm.fend[k] = (uint16_t)p;
+                }
+                nf += __popc(semi);
             }
-            if (is_pat) {
-                if (tail) return;
-                if (++npf > 8) return;
-                int32_t v = 0;
-                canon_int(s, p + 3, q, v);
-                const int id = s[p + 1] - '0';
-                const int slot = P.find(id);                                /* same dict key: the value is overwritten in place */
-                if (slot >= 0) P.val[slot] = v;
-                else { P.val[P.n] = v; P.ids |= (uint32_t)id << (4 * P.n); P.n++; }
-            } else {
-                if (!tail) { if (npf < 2) return; tail = true; }
-                bool ok = false;
-                if (fl >= 4 && s[p] == 'D' && s[p + 1] == '=') {
-                    ok = true;
-                    for (int i = p + 2; i < q && ok; i++) ok = is_dig(s[i]);
-                    if (ok) { D.a = p + 2; D.b = q; }
-                } else if (fl == 4 && s[p] == 'C' && s[p + 1] == 'P' && s[p + 2] == '=' && is_dig(s[p + 3])) ok = true;
-                else if (fl >= 3 && s[p] == 'R' && s[p + 1] == '=') {
-                    ok = true;
-                    for (int i = p + 2; i < q && ok; i++) ok = is_dig(s[i]);
-                    if (ok) { R.a = p + 2; R.b = q; }
-                } else if (fl == 1 && (s[p] == 'O' || s[p] == 'e' || s[p] == 'p')) ok = true;
-                else if (fl == 3 && s[p] == 'w' && s[p + 1] == '=' && is_dig(s[p + 2])) ok = true;
-                if (!ok) return;
-            }
-            p = q + 1;
-        }
-        if (npf < 2 || D.a < 0) return;                                     /* {2,8} and the D=\d+ look-ahead */
-    } else {
-        /* _parse_to_dict (ms.py:71-84): split on ';', key = text before the first '=', later keys overwrite */
-        int p = 0;
-        while (p < len) {
-            int q = p, eq = -1;
-            while (q < len && s[q] != ';') { if (s[q] == '=' && eq < 0) eq = q; q++; }
-            if (q > p) {
-                const int ke = eq >= 0 ? eq : q;                            /* key = [p, ke) */
-                const Span v = {eq >= 0 ? eq + 1 : q, q};
-                const int kl = ke - p;
-                if (kl == 1 && s[p] == 'D') D = v;
-                else if (kl == 2 && s[p] == 'C' && s[p + 1] == 'P') CP = v;
-                else if (kl == 2 && s[p] == 'S' && s[p + 1] == 'P') SP = v;
-                else if (kl == 1 && s[p] == 'R') R = v;
-                else if (kl >= 2 && s[p] == 'P') {
-                    bool kd = true;
-                    int id = 0;
-                    for (int i = p + 1; i < ke; i++) { kd = kd && is_dig(s[i]); id = id * 10 + (s[i] - '0'); if (id > 1000) id = 1000; }
-                    if (kd) {                                                /* a pattern key (message_synced.py:50-57) */
-                        int32_t val = 0;
-                        if (id > 9 || !canon_int(s, v.a, v.b, val) || P.find(id) >= 0 || P.n >= SDB_MAX_SLOTS) host = true;
-                        else { P.val[P.n] = val; P.ids |= (uint32_t)id << (4 * P.n); P.n++; }
+            const bool open_tail = s[len - 1] != ';';
+            if (open_tail) { if (lane == 0 && nf < 33) sm.fend[nf] = (uint16_t)len; nf++; }
+            __syncwarp();
+
+            if (nonascii || nf > 32) status = SDB_LINE_HOSTPATH;      /* str.isdigit() / \d know more digits than ASCII */
+            else {
+                /* 3. one lane per field */
+                const bool have = lane < nf;
+                const int a = have ? (lane ? sm.fend[lane - 1] + 1 : 0) : 0, b = have ? sm.fend[lane] : 0;
+                int va = 0, vb = 0, id = 0;
+                int32_t val = 0;
+                int cls = have ? classify<MU>(s, a, b, va, vb, id, val) : F_EMPTY;
+                if (MU && have && lane == 0) cls = (b == 2 && s[0] == 'M' && s[1] == 'U') ? F_OTHER_OK : F_BAD;
+
+                /* 4. dict semantics across the fields */
+                const uint32_t m_pat = __ballot_sync(FULL, cls == F_PAT), m_d = __ballot_sync(FULL, cls == F_D);
+                const uint32_t m_r = __ballot_sync(FULL, cls == F_R);
+                bool host = __any_sync(FULL, cls == F_HOST);
+                bool ok = true;
+                if (MU) {
+                    /* ^(?=.*D=\d+)(?:MU;(?:P[0-7]=-?[0-9]{1,5};){2,8}((?:D=\d{2,};)|(?:CP=\d;)|(?:R=\d+;)|(?:O;)|(?:e;)|(?:p;)|(?:w=\d;))*)$
+                     * no alternative of the tail matches a pattern field and vice versa, so the split is unique */
+                    const int k = __ffs(~(m_pat >> 1)) - 1;                /* leading pattern fields after "MU" */
+                    ok = !open_tail && !__any_sync(FULL, have && cls == F_BAD) && k >= 2 && k <= 8 &&
+                         (k + 1 >= 32 || (m_pat >> (k + 1)) == 0) && m_d != 0;
+                } else {
+                    ok = m_d != 0;                                         /* ms.py:41-43: no D, nothing to demodulate */
+                }
+                /* the D fields: digits only (MU: every D field, \d{2,}; MS: the last one, non-empty); pack the last */
+                const int d_lane = m_d ? 31 - __clz(m_d) : 0;
+                int dlen = 0;
+                if (ok) {
+                    uint32_t todo = MU ? m_d : (1u << d_lane);
+                    while (todo && ok) {
+                        const int dl = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int da = __shfl_sync(FULL, va, dl), db = __shfl_sync(FULL, vb, dl);
+                        const int n = db - da;
+                        const bool last = dl == d_lane;
+                        if (n < (MU ? 2 : 1)) { ok = false; break; }
+                        if (last && n > SDB_MAX_DIGITS) { host = true; }
+                        bool good = true;
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(A.pool + (size_t)unit * 16);
+                        const int nwords = ((n + 31) >> 5) * 4;
+                        for (int w = lane; w * 8 < n || (last && !host && w < nwords); w += 32) {
+                            uint32_t x = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int i = 8 * w + j;
+                                uint32_t nib = 0xFu;
+                                if (i < n) { const uint8_t c = s[da + i]; good = good && is_dig(c); nib = (uint32_t)(c - '0') & 0xFu; }
+                                x |= nib << (4 * j);
+                            }
+                            if (last && !host && w < nwords) dst[w] = x;
+                        }
+                        if (!__all_sync(FULL, good)) ok = false;
+                        if (last) dlen = n;
                     }
                 }
+                int cp_slot = -1;
+                if (ok && !MU) {
+                    /* message_synced.py:21-47: CP and SP non-empty digit strings, R too when present (the last of each wins) */
+                    const uint32_t m_cp = __ballot_sync(FULL, cls == F_CP), m_sp = __ballot_sync(FULL, cls == F_SP);
+                    const bool vdig = (cls == F_CP || cls == F_SP || cls == F_R) && short_digits(s, va, vb);
+                    const uint32_t m_vd = __ballot_sync(FULL, vdig);
+                    if (!m_cp || !m_sp) ok = false;
+                    else {
+                        const int lc = 31 - __clz(m_cp), lsp = 31 - __clz(m_sp);
+                        if (!((m_vd >> lc) & 1) || !((m_vd >> lsp) & 1)) ok = false;
+                        if (m_r && !((m_vd >> (31 - __clz(m_r))) & 1)) ok = false;
+                        if (ok) {
+                            int cpv = 0;                                    /* str(int(CP)) (message_synced.py:33,59) */
+                            if (lane == lc) for (int i = va; i < vb; i++) { cpv = cpv * 10 + (s[i] - '0'); if (cpv > 1000) cpv = 1000; }
+                            cpv = __shfl_sync(FULL, cpv, lc);
+                            cp_slot = cpv <= 9 ? cpv + 100 : -1;             /* resolved to a slot below */
+                        }
+                    }
+                }
+                if (ok) {
+                    /* pattern slots in order of first appearance; the same key again overwrites the value in place
+                     * (MU: keys are P0..P7; MS: any duplicate id goes to the host, "P1" and "P01" are different keys) */
+                    const uint32_t grp = __match_any_sync(FULL, cls == F_PAT ? id : 64 + lane);
+                    const bool leader = cls == F_PAT && lane == __ffs(grp) - 1;
+                    const uint32_t m_lead = __ballot_sync(FULL, leader);
+                    if (!MU && m_lead != m_pat) host = true;
+                    const int npat = __popc(m_lead);
+                    if (npat > SDB_MAX_SLOTS) host = true;
+                    if (!host) {
+                        const int32_t v_last = __shfl_sync(FULL, val, 31 - __clz(grp));     /* value of the last field of the group */
+                        uint32_t ids_part = 0;
+                        if (leader) {
+                            const int slot = __popc(m_lead & ((1u << lane) - 1));
+                            sm.rec[slot] = (uint32_t)v_last;
+                            ids_part = (uint32_t)id << (4 * slot);
+                            if (cp_slot == id + 100) cp_slot = slot;
+                        }
+                        const uint32_t ids = __reduce_or_sync(FULL, ids_part);
+                        const int cps = __reduce_max_sync(FULL, (leader && cp_slot < 100) ? cp_slot : -1);
+                        __syncwarp();
+                        if (lane == 0) {
+                            sm.rec[9] = (uint32_t)dlen | ((uint32_t)npat << 16) | ((uint32_t)(cps >= 0 ? cps : 0xFF) << 24);
+                            sm.rec[10] = ids;
+                            sm.rec[11] = SDB_MSG_VALID;
+                        }
+                        __syncwarp();
+                        if (cps >= 0) { const int32_t pv = (int32_t)sm.rec[cps]; clock = pv < 0 ? -pv : pv; }
+                        if (m_r) {
+                            const int lr = 31 - __clz(m_r);
+                            r_off = __shfl_sync(FULL, va, lr); r_len = __shfl_sync(FULL, vb, lr) - r_off; has_r = 1;
+                        }
+                        status = SDB_LINE_OK;
+                    }
+                }
+                if (host && (MU ? ok : true)) status = status == SDB_LINE_OK ? SDB_LINE_OK : SDB_LINE_HOSTPATH;
+                if (!ok && !MU) status = SDB_LINE_INVALID;               /* the gates fail before any pattern is looked at */
             }
-            p = q + 1;
         }
-        if (D.a < 0) return;                                                /* ms.py:41-43: no D, nothing to demodulate */
-        /* message_synced.py:21-47 */
-        if (!all_digits(s, D) || !all_digits(s, CP) || !all_digits(s, SP)) return;
-        if (R.a >= 0 && !all_digits(s, R)) return;
-    }
-    if (host || D.b - D.a > SDB_MAX_DIGITS) { info.status = SDB_LINE_HOSTPATH; return; }
-
-    for (int i = 0; i < P.n; i++) rec.pat[i] = P.val[i];
-    rec.npat = (uint8_t)P.n; rec.pat_ids = P.ids;
-    rec.dlen = (uint16_t)(D.b - D.a);
-    rec.flags = SDB_MSG_VALID;
-    if (!MU) {
-        int cpv = 0;                                                         /* str(int(CP)) (message_synced.py:33,59) */
-        for (int i = CP.a; i < CP.b; i++) { cpv = cpv * 10 + (s[i] - '0'); if (cpv > 1000) cpv = 1000; }
-        const int slot = cpv <= 9 ? P.find(cpv) : -1;
-        if (slot >= 0) { rec.cp = (uint8_t)slot; info.clock = P.val[slot] < 0 ? -P.val[slot] : P.val[slot]; }
-    }
-    if (R.a >= 0) { info.r_off = (uint32_t)R.a; info.r_len = (uint16_t)(R.b - R.a); info.has_r = 1; }
-    pack_digits(s, D, pool, unit);
-    info.status = SDB_LINE_OK;
-}
-
-template <bool MU>
-__global__ void __launch_bounds__(128) tokenize_kernel(LArgs A)
-{
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
-        const uint32_t off = A.line_off[i], len = A.line_len[i];
-        SdbPulseMsg rec;
-        SdbLineInfo info;
-        tokenize_one<MU>(A.text + off, (int)len, (off >> 5) + i, A.pool, rec, info);
-        A.msgs[i] = rec;
-        A.info[i] = info;
+        __syncwarp();
+        if (status != SDB_LINE_OK && lane < 12) sm.rec[lane] = lane == 8 ? unit : (lane == 9 ? 0xFF000000u : 0u);
+        __syncwarp();
+        if (lane < 12) reinterpret_cast<uint32_t *>(&A.msgs[li])[lane] = sm.rec[lane];
+        if (lane == 0) {
+            SdbLineInfo inf;
+            inf.status = (uint8_t)status; inf.has_r = (uint8_t)(status == SDB_LINE_OK ? has_r : 0);
+            inf.r_len = (uint16_t)(status == SDB_LINE_OK ? r_len : 0); inf.r_off = (uint32_t)(status == SDB_LINE_OK ? r_off : 0);
+            inf.clock = status == SDB_LINE_OK ? clock : 0;
+            A.info[li] = inf;
+        }
+        __syncwarp();
     }
 }
 
 size_t lines_pool_bytes(size_t text_len, uint32_t n) { return ((text_len >> 5) + (size_t)n + 4) * 16; }
 
-int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n,
+int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n, uint32_t base,
                     SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, int sm_count, cudaStream_t stream)
 {
     if (n == 0) return 0;
     LArgs A;
-    A.text = d_text; A.line_off = d_off; A.line_len = d_len; A.n = n; A.msgs = d_msgs; A.pool = d_pool; A.info = d_info;
-    uint32_t need = (n + 127) / 128;
+    A.text = d_text; A.line_off = d_off; A.line_len = d_len; A.n = n; A.base = base; A.msgs = d_msgs; A.pool = d_pool; A.info = d_info;
+    uint32_t need = (n + LN_WARPS - 1) / LN_WARPS;
     uint32_t grid = (uint32_t)sm_count * 8;
     if (need < grid) grid = need;
-    if (kind == SDB_KIND_MU) tokenize_kernel<true><<<grid, 128, 0, stream>>>(A);
-    else tokenize_kernel<false><<<grid, 128, 0, stream>>>(A);
+    if (kind == SDB_KIND_MU) tokenize_kernel<true><<<grid, LN_WARPS * 32, 0, stream>>>(A);
+    else tokenize_kernel<false><<<grid, LN_WARPS * 32, 0, stream>>>(A);
     return (int)cudaGetLastError();
 }
 

@@ -27,7 +27,7 @@ int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMs
                SdbCounters *d_ctr, int grid, cudaStream_t stream);
 
 size_t lines_pool_bytes(size_t text_len, uint32_t n);
-int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n,
+int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n, uint32_t base,
                     SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, int sm_count, cudaStream_t stream);
 
 int launch_unit_mc(const SdbDevTable &tab, uint32_t proto, int method_override, const uint8_t *d_bits, int n, int mcbitnum,
