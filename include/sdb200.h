@@ -197,6 +197,18 @@ int sdb_demod_lines_host(SdbHandle *h, int kind,
                          uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info);
 
 /*
+ * Host-side JSON of the MS / MU hits of an sdb_demod_lines_host call: one string per hit, exactly
+ * MqttPublisher._message_to_json(DecodedMessage) (signalduino/mqtt.py:228-245) = json.dumps({"protocol_id", "payload",
+ * "metadata": {"bit_length", "rssi", "clock"}}, indent=4).  id_pool / id_off[nproto + 1]: the protocol id strings in table
+ * order; text / line_off / info: the arguments / results of the lines call (rssi is the text of the R field).
+ */
+int sdb_format_json(const SdbHandle *h, int kind,
+                    const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
+                    const char *id_pool, const uint32_t *id_off,
+                    const uint8_t *text, const uint32_t *line_off, const SdbLineInfo *info,
+                    char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used);
+
+/*
  * Unit-op entry points: run ONE device function on ONE input (a 1-warp launch).  They back
  * the scalar helper methods of the drop-in class so that the reference's own unit tests
  * (tests/test_postdemodulation.py, tests/test_manchester_protocols.py, tests/test_helpers.py)

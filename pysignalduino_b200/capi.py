@@ -29,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json",
 ]
 
 
@@ -82,6 +82,9 @@ def load_library() -> C.CDLL:
     L.sdb_demod_lines_host.restype = C.c_int
     L.sdb_demod_lines_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.sdb_format_json.restype = C.c_int
+    L.sdb_format_json.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
@@ -228,6 +231,35 @@ class Engine:
                 continue
             if rc != SDB_OK:
                 raise self._err(rc, "sdb_format_hits")
+            return pool[: used.value].tobytes(), off
+
+    def format_json(self, kind: int, hits: np.ndarray, bits: np.ndarray, text: np.ndarray, line_off: np.ndarray,
+                    info: np.ndarray) -> Tuple[bytes, np.ndarray]:
+        """MqttPublisher._message_to_json of every MS / MU hit of a demod_lines call: (pool bytes, offsets[nhits+1])."""
+        nh = len(hits)
+        hits = np.ascontiguousarray(hits)
+        bits = np.ascontiguousarray(bits)
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        line_off = np.ascontiguousarray(line_off, dtype=np.uint32)
+        info = np.ascontiguousarray(info)
+        if not hasattr(self, "_id_pool"):
+            enc = [i.encode("utf-8") for i in self.table.ids]
+            self._id_pool = b"".join(enc) + b"\0"
+            self._id_off = np.zeros(len(enc) + 1, dtype=np.uint32)
+            np.cumsum([len(e) for e in enc], out=self._id_off[1:])
+        off = np.zeros(nh + 1, dtype=np.uint64)
+        cap = max(256, 200 * nh)
+        while True:
+            pool = np.empty(cap, dtype=np.uint8)
+            used = C.c_size_t(0)
+            rc = self.lib.sdb_format_json(self.h, kind, hits.ctypes.data, nh, bits.ctypes.data if len(bits) else None,
+                                          self._id_pool, self._id_off.ctypes.data, text.ctypes.data, line_off.ctypes.data,
+                                          info.ctypes.data, pool.ctypes.data, cap, off.ctypes.data, C.byref(used))
+            if rc == SDB_E_OVERFLOW:
+                cap = used.value + 16
+                continue
+            if rc != SDB_OK:
+                raise self._err(rc, "sdb_format_json")
             return pool[: used.value].tobytes(), off
 
     def unit_mc(self, proto_index: int, bits: str, mcbitnum: int, method_override: int = 0):

@@ -7,6 +7,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -460,6 +461,118 @@ extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
 }
 
 /* ---- unit ops ----------------------------------------------------------------------------- */
+/* Python's repr(float): the shortest digit string that round-trips, fixed notation for 1e-4 <= |v| < 1e16 */
+static void py_float_repr(double v, char *out, size_t cap)
+{
+    if (v != v) { snprintf(out, cap, "nan"); return; }
+    if (v == 0.0) { snprintf(out, cap, "%s", std::signbit(v) ? "-0.0" : "0.0"); return; }
+    if (v - v != 0.0) { snprintf(out, cap, "%s", v < 0 ? "-inf" : "inf"); return; }
+    char e[40];
+    int prec = 1;
+    for (; prec <= 17; prec++) {
+        snprintf(e, sizeof e, "%.*e", prec - 1, v);
+        if (strtod(e, nullptr) == v) break;
+    }
+    /* e = [-]d[.ddd]e[+-]xx */
+    std::string digits;
+    const char *p = e;
+    const bool neg = *p == '-';
+    if (neg) p++;
+    for (; *p && *p != 'e'; p++) if (*p != '.') digits.push_back(*p);
+    const int ex = atoi(p + 1);
+    std::string r = neg ? "-" : "";
+    if (ex >= -4 && ex < 16) {
+        if (ex >= 0) {
+            for (int i = 0; i <= ex; i++) r.push_back(i < (int)digits.size() ? digits[i] : '0');
+            r.push_back('.');
+            if ((int)digits.size() > ex + 1) r.append(digits, ex + 1, std::string::npos); else r.push_back('0');
+        } else {
+            r += "0.";
+            r.append((size_t)(-ex - 1), '0');
+            r += digits;
+        }
+    } else {
+        r.push_back(digits[0]);
+        if (digits.size() > 1) { r.push_back('.'); r.append(digits, 1, std::string::npos); }
+        char x[8];
+        snprintf(x, sizeof x, "e%c%02d", ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+        r += x;
+    }
+    snprintf(out, cap, "%s", r.c_str());
+}
+
+extern "C" int sdb_format_json(const SdbHandle *h, int kind,
+                               const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
+                               const char *id_pool, const uint32_t *id_off,
+                               const uint8_t *text, const uint32_t *line_off, const SdbLineInfo *info,
+                               char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
+{
+    if (!h || !str_off || !pool_used || !id_pool || !id_off || (nhits && (!hits || !info || !line_off || !text))) return SDB_E_ARG;
+    if (kind != SDB_KIND_MS && kind != SDB_KIND_MU) return SDB_E_ARG;
+    const SdbTblHeader *hd = reinterpret_cast<const SdbTblHeader *>(h->blob.data());
+    /* payload strings first (same formatter as sdb_format_hits) */
+    std::vector<uint64_t> poff(nhits + 1, 0);
+    std::vector<char> ppool(64 + 48 * (size_t)nhits);
+    size_t pused = 0;
+    int rc = sdb_format_hits(h, kind, hits, nhits, bits, ppool.data(), ppool.size(), poff.data(), &pused);
+    if (rc == SDB_E_OVERFLOW) { ppool.resize(pused + 16); rc = sdb_format_hits(h, kind, hits, nhits, bits, ppool.data(), ppool.size(), poff.data(), &pused); }
+    if (rc != SDB_OK) return rc;
+    /* MU: meta.clock is the protocol's clockabs (message_unsynced.py:288) */
+    std::vector<std::string> mu_clock(hd->nproto);
+    if (kind == SDB_KIND_MU) {
+        const SdbPulseProto *tab = reinterpret_cast<const SdbPulseProto *>(h->blob.data() + hd->off_mu);
+        char buf[40];
+        for (uint32_t i = 0; i < hd->n_mu; i++) { py_float_repr(tab[i].clock, buf, sizeof buf); mu_clock[tab[i].proto] = buf; }
+    }
+    size_t used = 0;
+    auto put = [&](char c) { if (used < pool_cap) pool[used] = c; used++; };
+    auto put_str = [&](const char *s) { while (*s) put(*s++); };
+    auto put_json_string = [&](const char *s, size_t n) {          /* json.dumps(str), ensure_ascii=True */
+        put('"');
+        for (size_t i = 0; i < n; i++) {
+            const unsigned char c = (unsigned char)s[i];
+            char esc[8];
+            switch (c) {
+            case '"': put_str("\\\""); break;
+            case '\\': put_str("\\\\"); break;
+            case '\n': put_str("\\n"); break;
+            case '\r': put_str("\\r"); break;
+            case '\t': put_str("\\t"); break;
+            case '\b': put_str("\\b"); break;
+            case '\f': put_str("\\f"); break;
+            default:
+                if (c < 0x20 || c >= 0x7f) { snprintf(esc, sizeof esc, "\\u%04x", c); put_str(esc); }
+                else put((char)c);
+            }
+        }
+        put('"');
+    };
+    char num[48];
+    for (uint32_t i = 0; i < nhits; i++) {
+        str_off[i] = used;
+        const SdbHit &ht = hits[i];
+        if (ht.proto >= hd->nproto) return SDB_E_ARG;
+        const SdbLineInfo &li = info[ht.msg];
+        /* MqttPublisher._message_to_json (signalduino/mqtt.py:228-245): asdict(message) without "raw", json.dumps(indent=4) */
+        put_str("{\n    \"protocol_id\": ");
+        put_json_string(id_pool + id_off[ht.proto], id_off[ht.proto + 1] - id_off[ht.proto]);
+        put_str(",\n    \"payload\": ");
+        put_json_string(ppool.data() + poff[i], (size_t)(poff[i + 1] - poff[i]));
+        snprintf(num, sizeof num, "%u", (unsigned)ht.nbits);
+        put_str(",\n    \"metadata\": {\n        \"bit_length\": "); put_str(num);
+        put_str(",\n        \"rssi\": ");
+        if (li.has_r) put_json_string(reinterpret_cast<const char *>(text) + line_off[ht.msg] + li.r_off, li.r_len);
+        else put_str("null");
+        put_str(",\n        \"clock\": ");
+        if (kind == SDB_KIND_MS) { snprintf(num, sizeof num, "%d.0", li.clock); put_str(num); }
+        else put_str(mu_clock[ht.proto].c_str());
+        put_str("\n    }\n}");
+    }
+    str_off[nhits] = used;
+    *pool_used = used;
+    return used > pool_cap ? SDB_E_OVERFLOW : SDB_OK;
+}
+
 extern "C" int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_t n_in,
                                   uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode)
 {

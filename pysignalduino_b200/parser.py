@@ -204,6 +204,61 @@ class SignalParser:
         # MC: demodulate_mc() is called without a protocol_id (mc.py:78) and returns [] (sd_protocols.py:79-83)
         return results
 
+    def parse_lines_json(self, lines: Sequence[str]) -> List[List[str]]:
+        """``[[MqttPublisher._message_to_json(m) for m in parse_line(l)] for l in lines]`` (signalduino/mqtt.py:228-245).
+
+        MS / MU hits of lines the tokenizer takes are serialised natively in one call (``sdb_format_json``), without
+        building ``DecodedMessage`` objects; everything else (host-path lines, MN) goes through ``parse_lines``."""
+        out: List[List[str]] = [[] for _ in lines]
+        rest: List[int] = []
+        by_type: Dict[str, List[int]] = {"MS": [], "MU": []}
+        payloads: List[Optional[str]] = [None] * len(lines)
+        for i, line in enumerate(lines):
+            payload = extract_payload(line)
+            if payload is None:
+                continue
+            payloads[i] = payload
+            mt = payload[:2].upper()
+            if mt in by_type:
+                by_type[mt].append(i)
+            elif mt == "MN":
+                rest.append(i)
+        eng = self.protocols.engine()
+        for mt, idx in by_type.items():
+            if not idx:
+                continue
+            kind = pack.KIND_BY_NAME[mt]
+            blobs, dev = [], []
+            for i in idx:
+                try:
+                    blobs.append(payloads[i].encode("latin-1"))
+                    dev.append(i)
+                except UnicodeEncodeError:
+                    rest.append(i)
+            if not dev:
+                continue
+            lens = np.fromiter((len(b) for b in blobs), dtype=np.int64, count=len(blobs))
+            offs = np.zeros(len(blobs), dtype=np.int64)
+            np.cumsum(lens[:-1] + 1, out=offs[1:])
+            text = np.frombuffer(b"\n".join(blobs) + b"\n", dtype=np.uint8)
+            offs32 = offs.astype(np.uint32)
+            res, info = eng.demod_lines(kind, text, offs32, lens.astype(np.uint32))
+            rest.extend(dev[int(k)] for k in np.nonzero(info["status"] == LINE_HOSTPATH)[0])
+            if len(res.hits):
+                pool, off = eng.format_json(kind, res.hits, res.bits, text, offs32, info)
+                js = pool.decode("ascii")
+                o = res.out
+                for k in np.nonzero((o["nhits"] > 0) & (o["status"] == ST_OK) & (info["status"] == LINE_OK))[0]:
+                    h0, nh = int(o["hit_off"][k]), int(o["nhits"][k])
+                    out[dev[int(k)]] = [js[int(off[h]) : int(off[h + 1])] for h in range(h0, h0 + nh)]
+        if rest:
+            import json
+
+            rest.sort()
+            for i, msgs in zip(rest, self.parse_lines([lines[i] for i in rest])):
+                out[i] = [json.dumps({"protocol_id": m.protocol_id, "payload": m.payload, "metadata": m.metadata}, indent=4) for m in msgs]
+        return out
+
     # ------------------------------------------------------------------ MS / MU
     def _pulse_lines(self, mt: str, idx: List[int], frames, results) -> None:
         kind = pack.KIND_BY_NAME[mt]

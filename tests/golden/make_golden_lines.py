@@ -132,17 +132,38 @@ def reduce_line(line, rng):
     return "\x02" + typ + ";" + ";".join(out) + ";\x03"
 
 
+def message_to_json():
+    """MqttPublisher._message_to_json of the reference (signalduino/mqtt.py:228-245).  mqtt.py imports the MQTT client
+    stack at module level (aiomqtt, paho, jsonschema: not installed here), so only that one function is compiled from
+    the reference file (ast) and executed with the names it uses."""
+    import json as _json
+    from dataclasses import asdict
+
+    types_mod = __import__("signalduino.types", fromlist=["RawFrame"])
+    src = (ref_import.REFERENCE_ROOT / "signalduino" / "mqtt.py").read_text(encoding="utf-8")
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "_message_to_json")
+    fn.decorator_list = []
+    ns = {"json": _json, "asdict": asdict, "RawFrame": types_mod.RawFrame, "DecodedMessage": types_mod.DecodedMessage}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "mqtt_message_to_json", "exec"), ns)
+    return ns["_message_to_json"]
+
+
+TO_JSON = None
+
+
 def snapshot(msgs):
     out = []
     for m in msgs:
         f = m.raw
-        out.append({"protocol_id": m.protocol_id, "payload": m.payload, "metadata": m.metadata,
+        out.append({"protocol_id": m.protocol_id, "payload": m.payload, "metadata": m.metadata, "json": TO_JSON(m),
                     "frame": {"line": f.line, "rssi": f.rssi, "freq_afc": f.freq_afc, "message_type": f.message_type}})
     return out
 
 
 def main():
+    global TO_JSON
     mod = ref_import.reference_parser_module()
+    TO_JSON = message_to_json()
     log = logging.getLogger("golden_lines")
     log.addHandler(logging.NullHandler())
     log.propagate = False
