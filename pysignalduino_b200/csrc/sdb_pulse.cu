@@ -8,25 +8,23 @@
  *   length_in_range / bin_str_2_hex_str   sd_protocols/helpers.py:28-64, :124-166
  *   postDemo_*         sd_protocols/postdemodulation.py (sdb_postdemod.cuh)
  *
- * Work decomposition: ONE WARP PER MESSAGE, persistent warps striding over the batch.
- *   phase 0  the warp stages the message in shared memory: nibble-packed digits (coalesced
- *            128-bit loads), digit / digram first- and last-occurrence tables (so that
- *            "target in D" becomes a table lookup), and for MU the tenths table
- *            T[clock][slot] = 10*round(P/clock, 1) for the distinct protocol clocks.
- *   phase 1  one LANE per protocol: integer interval tests decide which protocols can resolve
- *            all mandatory templates at all; survivors come back as a ballot mask.
- *   phase 2  one WARP per surviving (message x protocol) task, in protocol-table order:
- *            exact pattern_exists (lane = (distinct value, slot), gap ranks, mixed-radix
- *            product enumeration), symbol / start bitmaps (SWAR byte compares on 8 digits per
- *            lane, or __ballot_sync over digit windows), run-length via shifted-AND doubling,
- *            bit emission by ballots, post-demodulation, padding, modulematch, hit staging.
+ * Work decomposition: ONE WARP PER MESSAGE, persistent warps striding over the batch, several SMALL kernels per
+ * message class (each kernel's hot code has to fit the 32 KB L1.5 instruction cache — see DESIGN.md §4.1):
+ *   resolve_kernel<MS|MU>   stage the message (nibble-packed digits by coalesced 128-bit loads; digit / digram first-
+ *                           and last-occurrence tables so that "target in D" is a table lookup; tenths table
+ *                           T[clock][slot] = 10*round(P/clock, 1)), candidate-slot masks per (clock, interval)
+ *                           pair + kill masks = prefilter, then one LANE per surviving protocol: exact
+ *                           pattern_exists at thread level (warp level for long starts / 1- and 4-digit symbols)
+ *                           -> 16-byte survivor records in protocol-table order.
+ *   scan_kernel<MS>         survivors -> chunk classification by ballots -> bits -> finish_match.
+ *   mu_match_kernel         survivors 32 at a time, one per lane: distinct symbol / start bitmaps built once per
+ *                           message (SWAR), each lane walks re.finditer for its own survivor over the shared
+ *                           bitmaps -> 4-byte match records in reference order.
+ *   mu_emit_kernel          match records -> bits (ballots) -> finish_match.
+ *   scan_kernel<MU>         fused match + emit, only for messages with more than MU_MCAP matches.
+ *   finish_match            length rules, padding, post-demodulation, modulematch, hit staging.
  * Hits of one message are staged in shared memory and published with one atomicAdd, so
  * they are contiguous and already in reference order (protocol order, then match order).
- *
- * Code size matters: the first version inlined everything (18 k SASS instructions, 295 KB) and
- * ncu showed 74 % of the stall samples in "no instruction" (instruction-cache misses).  The cold
- * parts (general candidate sort, post-demodulation, modulematch, second pass) are therefore
- * __noinline__ and the hot loop is kept small.
  *
  * Float parity: the only float64 work is x = P/clock and CPython's round(x, 1), done with
  * correctly-rounded division and an FMA residual; every tolerance /
@@ -613,6 +611,21 @@ __device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint3
             }
             d8[IDX(wi, 4 * MU_BW)] = (uint8_t)b8;
         }
+    } else if (w == 1) {
+        /* one-digit symbols: 8 digits per lane, plain nibble compares (0xF padding never equals a digit) */
+        const uint32_t k1 = (c1 & 0xF) * 0x11111111u, k0 = (c0 & 0xF) * 0x11111111u, kf = (cf & 0xF) * 0x11111111u;
+        const int nwords = (dlen + 7) >> 3;
+        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
+        const int nbytes = 4 * (nw + 2);
+#pragma unroll 1
+        for (int wi = lane; wi < nbytes; wi += 32) {
+            uint32_t b8 = 0;
+            if (wi < nwords) {
+                const uint32_t x = sm.dig[IDX(wi, DIG_WORDS)];
+                b8 = eq_nibbles8(x, k1) | eq_nibbles8(x, k0) | eq_nibbles8(x, kf);
+            }
+            d8[IDX(wi, 4 * MU_BW)] = (uint8_t)b8;
+        }
     } else {
         const uint32_t wm = nibmask32(w);
 #pragma unroll 1
@@ -1057,7 +1070,8 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
 __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
                                                  uint32_t &codes, uint32_t &s0f, bool after_start, int s0_in)
 {
-    if (pp->width != 2) return 2;                              /* 1- / 4-digit symbols: warp-level path */
+    const int width = pp->width;
+    if (width > 2 || (width == 1 && pp->key[0].len > 2)) return 2;   /* 4-digit symbols: warp-level path for every key */
     const int clk_idx = pp->clk_idx;
     const bool long_start = !after_start && pp->key[0].len > 2;   /* needs a warp-wide search: only pre-screen one / zero here */
     uint32_t acc = 0, hasf = 0;
@@ -1078,7 +1092,7 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
     }
     if (long_start) return 2;                                 /* one / zero exist somewhere in D: worth the warp-level path */
     /* a match needs regex_min consecutive symbols, all at positions of one parity: count them (necessary condition) */
-    {
+    if (width == 2) {
         const uint32_t c1 = (acc >> 8) & 0xFF, c0 = (acc >> 16) & 0xFF, cf = acc >> 24;
         uint32_t cnt = sm.cnt2[IDX((c1 & 15) * 10 + (c1 >> 4), 100)];
         if (pp->key[2].len && c0 != c1) cnt += sm.cnt2[IDX((c0 & 15) * 10 + (c0 >> 4), 100)];
