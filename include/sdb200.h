@@ -197,6 +197,23 @@ int sdb_demod_lines_host(SdbHandle *h, int kind,
                          uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info);
 
 /*
+ * Raw receive buffer -> payload lines (host code, no handle, no device): signalduino/parser/base.py:13-193
+ * (strip, ^\x02(M[sSuUcCNOo];.*;)\x03$, decompression of the reduced "Mred=1" format) and the message-type routing
+ * of signalduino/parser/__init__.py:43-77.  raw is split on '\n'; raw line i gets line_type[i] = SDB_KIND_MS / _MU /
+ * _MC / _MN, SDB_FRAME_OTHER (framed, but no parser for the type) or SDB_FRAME_NONE (not a framed message), and its
+ * payload at text[line_off[i] .. +line_len[i]) ('\n' after each, offsets ascending: ready for sdb_demod_lines_host).
+ * SDB_FRAME_PYPATH set: the payload needs str.upper() on a non-ASCII character — frame that line in Python.
+ * Returns SDB_E_OVERFLOW (with *n_lines / *text_used = what is needed) when max_lines / text_cap are too small.
+ */
+#define SDB_FRAME_OTHER  4
+#define SDB_FRAME_PYPATH 0x80
+#define SDB_FRAME_NONE   0xFF
+int sdb_frame_lines(const uint8_t *raw, size_t raw_len,
+                    uint8_t *text, size_t text_cap,
+                    uint32_t *line_off, uint32_t *line_len, uint8_t *line_type, uint32_t max_lines,
+                    uint32_t *n_lines, size_t *text_used);
+
+/*
  * Host-side JSON of the MS / MU hits of an sdb_demod_lines_host call: one string per hit, exactly
  * MqttPublisher._message_to_json(DecodedMessage) (signalduino/mqtt.py:228-245) = json.dumps({"protocol_id", "payload",
  * "metadata": {"bit_length", "rssi", "clock"}}, indent=4).  id_pool / id_off[nproto + 1]: the protocol id strings in table

@@ -29,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines",
 ]
 
 
@@ -85,6 +85,9 @@ def load_library() -> C.CDLL:
     L.sdb_format_json.restype = C.c_int
     L.sdb_format_json.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+    L.sdb_frame_lines.restype = C.c_int
+    L.sdb_frame_lines.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
@@ -95,6 +98,33 @@ def load_library() -> C.CDLL:
 
 LINEINFO_DTYPE = np.dtype([("status", "u1"), ("has_r", "u1"), ("r_len", "<u2"), ("r_off", "<u4"), ("clock", "<i4")])
 LINE_INVALID, LINE_OK, LINE_HOSTPATH = 0, 1, 2
+
+
+FRAME_OTHER, FRAME_PYPATH, FRAME_NONE = 4, 0x80, 0xFF
+
+
+def frame_lines(raw: bytes):
+    """Raw receive buffer -> (payload text uint8, line_off, line_len, line_type) per '\\n'-separated raw line
+    (base.py:13-193 natively; needs no GPU)."""
+    L = load_library()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    max_lines = raw.count(b"\n") + 1
+    cap = 2 * len(raw) + 64
+    while True:
+        text = np.empty(cap, dtype=np.uint8)
+        off = np.zeros(max_lines, dtype=np.uint32)
+        ln = np.zeros(max_lines, dtype=np.uint32)
+        typ = np.zeros(max_lines, dtype=np.uint8)
+        n, used = C.c_uint32(0), C.c_size_t(0)
+        rc = L.sdb_frame_lines(buf.ctypes.data if len(buf) else None, len(buf), text.ctypes.data, cap, off.ctypes.data,
+                               ln.ctypes.data, typ.ctypes.data, max_lines, C.byref(n), C.byref(used))
+        if rc == SDB_E_OVERFLOW:
+            max_lines, cap = max(max_lines, n.value), max(cap, used.value + 64)
+            continue
+        if rc != SDB_OK:
+            raise SdbError(f"sdb_frame_lines failed ({rc})")
+        k = n.value
+        return text[: used.value], off[:k], ln[:k], typ[:k]
 
 
 class Result:

@@ -1063,6 +1063,32 @@ __device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_id
     return false;
 }
 
+/* Thread-level necessary condition for a long start (only the warp-level path resolves it exactly): when every distinct
+ * value has exactly ONE candidate slot the id string is determined, and each of its digrams must occur in D.
+ * false = pattern_exists certainly returns -1. */
+__device__ __noinline__ bool tpre(const SdbKeyTpl *__restrict__ k, const WarpSm &sm)
+{
+    const int L = k->len, K = k->nuniq;
+    const uint32_t ids = sm.pat_ids;
+    uint32_t dg = 0, seen = 0;                                 /* 4 digits, one nibble each */
+    for (int u = 0; u < K; u++) {
+        const uint32_t c = sm.M[IDX(k->vidx[u], SDB_MAX_VALS)];
+        if (!c) return false;                                  /* pattern_utils.py:78-80 */
+        if (c & (c - 1)) return true;                          /* several candidates: undecided here */
+        if (seen & c) return false;                            /* :114 one slot cannot stand for two values */
+        seen |= c;
+        dg |= ((ids >> (4 * (__ffs(c) - 1))) & 0xF) << (4 * u);
+    }
+    const uint32_t uidx = k->uidx;
+    int prev = dg & 0xF;
+    for (int i = 1; i < L; i++) {
+        const int d = (dg >> (4 * ((uidx >> (2 * i)) & 3))) & 0xF;
+        if (sm.last2[IDX(prev * 10 + d, 100)] <= (uint32_t)(i - 1)) return false;
+        prev = d;
+    }
+    return true;
+}
+
 /* Thread-level resolution of one MU protocol (2-digit symbols, start of <= 2 pulses).
  * Returns 0 dead, 1 resolved (codes = start | one<<8 | zero<<16 | float<<24, s0f = s0 | hasf<<16),
  * 2 = needs the warp-level path (for a long start: after one / zero passed a pre-screen on the whole D).
@@ -1074,6 +1100,7 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
     if (width > 2 || (width == 1 && pp->key[0].len > 2)) return 2;   /* 4-digit symbols: warp-level path for every key */
     const int clk_idx = pp->clk_idx;
     const bool long_start = !after_start && pp->key[0].len > 2;   /* needs a warp-wide search: only pre-screen one / zero here */
+    if (long_start && !tpre(&pp->key[0], sm)) return 0;
     uint32_t acc = 0, hasf = 0;
     int s0 = after_start ? s0_in : 0;
 #pragma unroll 1

@@ -31,6 +31,50 @@ def test_extract_payload_matches_reference():
     assert not bad, (len(bad), bad[:3])
 
 
+def test_framing_fuzz_python_and_native():
+    """6 000 byte-level fuzz cases around the reduced payload grammar: parser.extract_payload (Python) and
+    sdb_frame_lines (C, host only) both equal the reference's extract_payload."""
+    from pysignalduino_b200 import capi
+
+    par = _host_module()
+    recs = load_golden("frames.json.gz") + [[r["line"], r["payload"]] for r in load_golden("lines.json.gz") if r["rfmode"] is None]
+    bad_py, bad_c, pypath = [], [], 0
+    for line, exp in recs:
+        if par.extract_payload(line) != exp:
+            bad_py.append(line)
+        raw = line.encode("latin-1")
+        if b"\n" in raw:
+            continue
+        text, off, ln, typ = capi.frame_lines(raw)
+        assert len(typ) == 1
+        t = int(typ[0])
+        if t != capi.FRAME_NONE and (t & capi.FRAME_PYPATH):
+            pypath += 1                                    # flagged for the Python implementation, never framed differently
+            continue
+        got = None if t == capi.FRAME_NONE else bytes(text[int(off[0]) : int(off[0]) + int(ln[0])]).decode("latin-1")
+        if got != exp:
+            bad_c.append(line)
+        if got is not None:
+            mt = exp[:2].upper()
+            assert t == {"MS": 0, "MU": 1, "MC": 2, "MN": 3}.get(mt, capi.FRAME_OTHER), (line, t)
+    assert not bad_py and not bad_c, (len(bad_py), len(bad_c), bad_py[:2], bad_c[:2])
+    assert pypath < len(recs) // 50
+
+
+def test_frame_lines_splits_a_buffer():
+    from pysignalduino_b200 import capi
+
+    recs = [r for r in load_golden("lines.json.gz") if r["rfmode"] is None and "\n" not in r["line"].strip()][:400]
+    raw = b"\n".join(r["line"].strip().encode("latin-1") for r in recs) + b"\n"
+    text, off, ln, typ = capi.frame_lines(raw)
+    assert len(typ) == len(recs)
+    for i, r in enumerate(recs):
+        t = int(typ[i])
+        got = None if t == capi.FRAME_NONE else bytes(text[int(off[i]) : int(off[i]) + int(ln[i])]).decode("latin-1")
+        assert got == r["payload"]
+    assert np.all(np.diff(off.astype(np.int64)) >= 0)
+
+
 def test_line_oracle_matches_reference(oracle):
     """payload -> dict (oracle/line_oracle.py) -> packed record -> C oracle == what the reference's parser returned."""
     from oracle import line_oracle
@@ -90,6 +134,17 @@ def test_gpu_parse_lines_matches_reference(sdp, rfmode):
     js = sp.parse_lines_json([r["line"] for r in recs])
     badj = [(r["line"], j[:1], [x["json"] for x in r["results"]][:1]) for r, j in zip(recs, js) if j != [x["json"] for x in r["results"]]]
     assert not badj, (len(badj), badj[:2])
+    # the same from ONE raw byte buffer: native framing, tokenizer + demodulation kernels, native JSON
+    sel = [r for r in recs if "\n" not in r["line"].strip()]
+    raw = b"\n".join(r["line"].strip().encode("latin-1") for r in sel) + b"\n"
+    batches, extra = sp.parse_text_json(raw)
+    got = {i: list(v) for i, v in extra.items()}
+    for pool, soff, hit_line in batches:
+        txt = pool.decode("ascii")
+        for k in np.argsort(hit_line, kind="stable"):
+            got.setdefault(int(hit_line[k]), []).append(txt[int(soff[k]) : int(soff[k + 1])])
+    badr = [(r["line"], got.get(i, [])[:1]) for i, r in enumerate(sel) if got.get(i, []) != [x["json"] for x in r["results"]]]
+    assert not badr, (len(badr), badr[:2])
 
 
 @pytest.mark.gpu
