@@ -42,6 +42,8 @@ struct SdbHandle {
     cudaStream_t copy_stream = nullptr; /* pipelined H2D */
     cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
     std::vector<cudaEvent_t> ev_h2d, ev_done;
+    SdbCounters *h_snap = nullptr;      /* pinned: counters after each chunk (which arena ranges are final) */
+    uint32_t snap_cap = 0;
 };
 
 static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
@@ -133,6 +135,7 @@ extern "C" void sdb_destroy(SdbHandle *h)
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->h_snap) cudaFreeHost(h->h_snap);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     delete h;
@@ -208,6 +211,41 @@ static int grow(SdbHandle *h, T *&p, size_t &cap, size_t need_bytes)
     return SDB_OK;
 }
 
+/* events + pinned counter snapshots for an nchunks-deep pipeline */
+static int pipeline_prepare(SdbHandle *h, uint32_t nchunks)
+{
+    while (h->ev_h2d.size() < nchunks) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_h2d.push_back(a); h->ev_done.push_back(b);
+    }
+    if (h->snap_cap < nchunks) {
+        if (h->h_snap) cudaFreeHost(h->h_snap);
+        h->h_snap = nullptr; h->snap_cap = 0;
+        CK(cudaMallocHost(reinterpret_cast<void **>(&h->h_snap), sizeof(SdbCounters) * (size_t)(nchunks + 8)));
+        h->snap_cap = nchunks + 8;
+    }
+    return SDB_OK;
+}
+
+/* Hits are appended through one atomic counter and the chunks run in stream order, so once chunk k is done the arena
+ * ranges [done, snapshot k) are final: copy them to the host while the next chunk's kernels run, instead of one big
+ * D2H after the last kernel (0.7 GB per 10 M mixed messages). */
+struct ArenaDrain { uint32_t hits = 0, words = 0; };
+static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, uint32_t hits_cap, uint32_t *bits, uint32_t bits_cap)
+{
+    CK(cudaEventSynchronize(h->ev_done[k]));            /* chunk k + 1 is already queued: the GPU stays busy */
+    const SdbCounters c = h->h_snap[k];
+    if (c.hits > hits_cap || c.words > bits_cap) return SDB_OK;      /* overflow: reported after the last chunk */
+    if (c.hits > d.hits && hits)
+        CK(cudaMemcpyAsync(hits + d.hits, h->d_hits + d.hits, sizeof(SdbHit) * (size_t)(c.hits - d.hits), cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (c.words > d.words && bits)
+        CK(cudaMemcpyAsync(bits + d.words, h->d_bits + d.words, sizeof(uint32_t) * (size_t)(c.words - d.words), cudaMemcpyDeviceToHost, h->d2h_stream));
+    d.hits = c.hits; d.words = c.words;
+    return SDB_OK;
+}
+
 extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
                               const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                               SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
@@ -239,31 +277,37 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
             if (pm[b].doff < pm[b - 1].doff || (size_t)pm[b].doff * 16 > digits_len) { pipelined = false; break; }
     if (pipelined) {
         const uint32_t nchunks = (n + C - 1) / C;
-        while (h->ev_h2d.size() < nchunks) {
-            cudaEvent_t a, b;
-            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-            h->ev_h2d.push_back(a); h->ev_done.push_back(b);
-        }
+        if ((rc = pipeline_prepare(h, nchunks))) return rc;
         SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
         CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));
-        for (uint32_t k = 0; k < nchunks; k++) {
+        auto h2d = [&](uint32_t k) -> int {
             const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
             const size_t dlo = (size_t)pm[lo].doff * 16;
             const size_t dhi = k + 1 < nchunks ? (size_t)pm[lo + cnt].doff * 16 : digits_len;
             CK(cudaMemcpyAsync(dm + lo, pm + lo, sizeof(SdbPulseMsg) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
             if (dhi > dlo) CK(cudaMemcpyAsync(h->d_digits + dlo, digits + dlo, dhi - dlo, cudaMemcpyHostToDevice, h->copy_stream));
             CK(cudaEventRecord(h->ev_h2d[k], h->copy_stream));
+            return SDB_OK;
+        };
+        ArenaDrain drain;
+        if ((rc = h2d(0))) return rc;
+        for (uint32_t k = 0; k < nchunks; k++) {
+            const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
+            if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
             CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
             rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
             if (rc != SDB_OK) return rc;
+            CK(cudaMemcpyAsync(&h->h_snap[k], h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev_done[k], st));
             CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
             CK(cudaMemcpyAsync(out + lo, h->d_out + lo, sizeof(SdbMsgOut) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (k && (rc = drain_chunk(h, k - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
         }
-        CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if ((rc = drain_chunk(h, nchunks - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
+        *counters = h->h_snap[nchunks - 1];
         CK(cudaStreamSynchronize(h->d2h_stream));
+        if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
+        return SDB_OK;
     } else {
         CK(cudaMemcpyAsync(h->d_msgs, msgs, rec * n, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(h->d_digits, digits, digits_len, cudaMemcpyHostToDevice, st));
@@ -320,37 +364,38 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
      * Device offsets are the caller's own (global) offsets, so digit-pool units and hit.msg need no rebasing. */
     const uint32_t C = SDB_MU_CHUNK;
     const uint32_t nchunks = (n + C - 1) / C;
-    while (h->ev_h2d.size() < nchunks) {
-        cudaEvent_t a, b;
-        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        h->ev_h2d.push_back(a); h->ev_done.push_back(b);
-    }
+    if ((rc = pipeline_prepare(h, nchunks))) return rc;
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));
-    for (uint32_t k = 0; k < nchunks; k++) {
+    auto h2d = [&](uint32_t k) -> int {
         const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
         const size_t t0 = line_off[lo], t1 = (size_t)line_off[lo + cnt - 1] + line_len[lo + cnt - 1];
         CK(cudaMemcpyAsync(h->d_text + t0, text + t0, t1 - t0, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(d_off + lo, line_off + lo, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(d_len + lo, line_len + lo, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->ev_h2d[k], h->copy_stream));
+        return SDB_OK;
+    };
+    ArenaDrain drain;
+    if ((rc = h2d(0))) return rc;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
+        if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
         CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
         rc = sdb::launch_tokenize(kind, h->d_text, d_off + lo, d_len + lo, cnt, lo, dm + lo, h->d_digits, d_info + lo, h->sm_count, st);
         if (rc != 0) return set_err(h, SDB_E_CUDA, "tokenize kernel launch", static_cast<cudaError_t>(rc));
         rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
         if (rc != SDB_OK) return rc;
+        CK(cudaMemcpyAsync(&h->h_snap[k], h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->ev_done[k], st));
         CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
         CK(cudaMemcpyAsync(out + lo, h->d_out + lo, sizeof(SdbMsgOut) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
         CK(cudaMemcpyAsync(info + lo, d_info + lo, sizeof(SdbLineInfo) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (k && (rc = drain_chunk(h, k - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
     }
-    CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if ((rc = drain_chunk(h, nchunks - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
+    *counters = h->h_snap[nchunks - 1];
     CK(cudaStreamSynchronize(h->d2h_stream));
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
-    if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
-    if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
     return SDB_OK;
 }
 
