@@ -444,11 +444,20 @@ __device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmIte
             if (cnt < mn) return false;
             continue;
         }
-        while (cnt < lim && pos < total) {
-            int c = payload_char(P, pos);
-            if (c < 0 || c >= 128 || !((m->mask[c >> 5] >> (c & 31)) & 1)) break;
-            pos++; cnt++;
+        /* one lane per character: the atom consumes the leading characters that are in its class, up to lim */
+        const int avail = min(lim, total - pos);
+        cnt = max(avail, 0);
+        for (int b0 = 0; b0 < avail; b0 += 32) {
+            const int j = b0 + lane_id();
+            bool bad = false;
+            if (j < avail) {
+                const int c = payload_char(P, pos + j);
+                bad = c < 0 || c >= 128 || !((m->mask[c >> 5] >> (c & 31)) & 1);
+            }
+            const uint32_t bm = __ballot_sync(FULL, bad);
+            if (bm) { cnt = b0 + __ffs(bm) - 1; break; }
         }
+        pos += cnt;
         if (cnt < mn) return false;
     }
     if (end && pos != total) return false;
