@@ -84,7 +84,26 @@ struct KArgs {
     uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
     uint32_t *match;           /* MU: n x MU_MCAP match records (match kernel -> emit kernel) */
     uint32_t *match_cnt;       /* MU: records per message, or MU_MARK = left to the fused fallback kernel */
+    uint32_t *ticket;          /* this launch's work counter (zeroed before the chunk): warps draw messages TICKET_BATCH at a time */
 };
+
+/* Messages differ a lot in cost (dlen 20..1024, 0..129 survivors), so a static message -> warp map leaves a tail at the
+ * end of every launch (measured: chunks of 1 M instead of 262 144 messages were 7 % faster).  Warps therefore draw
+ * their next messages from a per-launch counter. */
+#define TICKET_BATCH 8
+__device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uint32_t &left, uint32_t &mi)
+{
+    if (!left) {
+        uint32_t b = 0;
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(A.ticket, (uint32_t)TICKET_BATCH);
+        base = __shfl_sync(0xffffffffu, b, 0);
+        if (base >= A.n) return false;
+        left = min((uint32_t)TICKET_BATCH, A.n - base);
+    }
+    mi = base++;
+    left--;
+    return true;
+}
 
 /* MU scan kernel: symbol / start bitmaps of the distinct id-string sets of up to 32 survivors */
 #define MU_NB 6                       /* symbol bitmap triples resident at a time             */
@@ -1416,12 +1435,11 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
     const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
 
-    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0;
+    while (next_message(A, tk_base, tk_left, mi)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         const int dlen = m->dlen;
         uint32_t nsurv = 0;
@@ -1544,10 +1562,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0;
+    while (next_message(A, tk_base, tk_left, mi)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         SdbMsgOut mo;
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
@@ -1600,10 +1617,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_matc
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0;
+    while (next_message(A, tk_base, tk_left, mi)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         const uint32_t nsurv = A.surv_cnt[mi];
         uint32_t nrec = 0;
@@ -1665,10 +1681,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_emit
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    for (uint32_t mi = wid; mi < A.n; mi += warps) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0;
+    while (next_message(A, tk_base, tk_left, mi)) {
         const uint32_t nrec = A.match_cnt[mi];
         if (nrec == 0 || nrec == MU_MARK) continue;
         const SdbPulseMsg *m = &A.msgs[mi];
@@ -1731,7 +1746,8 @@ int pulse_blocks_per_sm(int kind)
 size_t mu_scratch_bytes(uint32_t stride, uint32_t chunk)
 {
     return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t)        /* survivor slots + counts */
-           + (size_t)chunk * MU_MCAP * sizeof(uint32_t) + (size_t)chunk * sizeof(uint32_t);   /* MU match records + counts */
+           + (size_t)chunk * MU_MCAP * sizeof(uint32_t) + (size_t)chunk * sizeof(uint32_t)    /* MU match records + counts */
+           + 64;                                                                              /* work counters */
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
@@ -1775,7 +1791,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     KArgs A;
     A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
     A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
-    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0;
+    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0; A.ticket = nullptr;
     if (n == 0) return 0;
     const uint32_t wpc = SDB_PULSE_THREADS / 32;
     if (!mu_scratch || !mu_chunk) return (int)cudaErrorInvalidValue;
@@ -1786,19 +1802,22 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     A.surv_stride = ms ? tab.n_ms : tab.n_mu;
     A.match = A.surv_cnt + mu_chunk;
     A.match_cnt = A.match + (size_t)mu_chunk * MU_MCAP;
+    uint32_t *tickets = A.match_cnt + mu_chunk;                    /* 8 work counters, zeroed per chunk */
     for (uint32_t off = 0; off < n; off += mu_chunk) {
         A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;
+        cudaError_t e = cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return (int)e;
         if (ms) {
-            resolve_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 0; resolve_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 1; scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
         } else {
-            resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
+            A.ticket = tickets + 0; resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 1; mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 2; mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 3; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
         }
     }
     return (int)cudaGetLastError();
