@@ -7,8 +7,9 @@ Workload (BASELINE.json configs[4]): a mixed corpus, 40
 15 % MC / 5 % MN, M messages per GPU (default 10 M), each message decoded against EVERY protocol of
 its class (47 MS / 129 MU protocols; MC / MN name their protocol).  The corpus is partitioned by
 message type when it is packed (the type is the first two characters of a firmware line); one
-"step" = one pass of the hot path over the whole per-GPU shard (per 262 144-message chunk: MS = resolve + scan,
-MU = resolve + match + emit + fused fallback; MC and MN one launch each).
+"step" = one pass of the hot path over the whole per-GPU shard (per 1 048 576 resident messages: MS = resolve + scan,
+MU = resolve + match + emit + fused fallback; MC and MN one launch each; the host-buffer path pipelines in stages of
+262 144 messages).
 Rank r of N decodes messages [r*M, (r+1)*M) of the N*M-message corpus: weak scaling, replicated
 protocol table, no collective on the decode path.
 
@@ -247,8 +248,8 @@ def run_ours(args):
                                  s["d_hits"].data_ptr(), s["hits_cap"], s["d_bits"].data_ptr(), s["bits_cap"],
                                  s["d_ctr"].data_ptr(), stream)
 
-    # our kernels per step: MS and MU = (resolve + scan) per 262144-message chunk, MC 1, MN 1
-    CHUNK = 262144
+    # our kernels per step: MS and MU per SDB_MU_CHUNK = 1048576 resident messages, MC 1, MN 1
+    CHUNK = 1048576
     # per chunk: MS = resolve + scan, MU = resolve + match + emit + fused fallback (sdb_pulse.cu launch_pulse)
     launches_per_step = sum(((2 if s["kind"] == 0 else 4) * ((s["n"] + CHUNK - 1) // CHUNK)) if s["kind"] <= 1 else 1 for s in slots)
 

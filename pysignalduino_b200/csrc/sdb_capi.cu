@@ -270,7 +270,7 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
     /* Pipelined path (MS / MU, several chunks): the H2D copy of chunk k+1 and the D2H copy of the result slots of
      * chunk k-1 overlap the kernels of chunk k.  Needs the digit streams stored in message order (doff non-decreasing),
      * which is what pack.py and the corpus generator produce; checked at the chunk boundaries. */
-    const uint32_t C = SDB_MU_CHUNK;
+    const uint32_t C = SDB_PIPE_CHUNK;
     bool pipelined = pulse && n > C;
     if (pipelined)
         for (uint32_t b = C; b < n; b += C)
@@ -359,10 +359,10 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
     uint32_t *d_off = reinterpret_cast<uint32_t *>(h->d_lines), *d_len = d_off + n;
     SdbLineInfo *d_info = reinterpret_cast<SdbLineInfo *>(d_len + n);
     SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
-    /* per chunk of SDB_MU_CHUNK lines: H2D of the chunk's text / offsets (copy stream) -> tokenizer + demodulation kernels
+    /* per stage of SDB_PIPE_CHUNK lines: H2D of the chunk's text / offsets (copy stream) -> tokenizer + demodulation kernels
      * (compute stream) -> D2H of the result slots and line infos (d2h stream); chunk k+1's copy overlaps chunk k's kernels.
      * Device offsets are the caller's own (global) offsets, so digit-pool units and hit.msg need no rebasing. */
-    const uint32_t C = SDB_MU_CHUNK;
+    const uint32_t C = SDB_PIPE_CHUNK;
     const uint32_t nchunks = (n + C - 1) / C;
     if ((rc = pipeline_prepare(h, nchunks))) return rc;
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));

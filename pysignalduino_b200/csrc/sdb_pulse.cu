@@ -84,21 +84,21 @@ struct KArgs {
     uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
     uint32_t *match;           /* MU: n x MU_MCAP match records (match kernel -> emit kernel) */
     uint32_t *match_cnt;       /* MU: records per message, or MU_MARK = left to the fused fallback kernel */
-    uint32_t *ticket;          /* this launch's work counter (zeroed before the chunk): warps draw messages TICKET_BATCH at a time */
+    uint32_t *ticket;          /* this launch's work counter (zeroed before the chunk): warps draw messages ticket_batch at a time */
+    uint32_t ticket_batch;
 };
 
 /* Messages differ a lot in cost (dlen 20..1024, 0..129 survivors), so a static message -> warp map leaves a tail at the
  * end of every launch (measured: chunks of 1 M instead of 262 144 messages were 7 % faster).  Warps therefore draw
  * their next messages from a per-launch counter. */
-#define TICKET_BATCH 8
 __device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uint32_t &left, uint32_t &mi)
 {
     if (!left) {
         uint32_t b = 0;
-        if ((threadIdx.x & 31) == 0) b = atomicAdd(A.ticket, (uint32_t)TICKET_BATCH);
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(A.ticket, A.ticket_batch);
         base = __shfl_sync(0xffffffffu, b, 0);
         if (base >= A.n) return false;
-        left = min((uint32_t)TICKET_BATCH, A.n - base);
+        left = min(A.ticket_batch, A.n - base);
     }
     mi = base++;
     left--;
@@ -1791,7 +1791,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     KArgs A;
     A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
     A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
-    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0; A.ticket = nullptr;
+    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0; A.ticket = nullptr; A.ticket_batch = 1;
     if (n == 0) return 0;
     const uint32_t wpc = SDB_PULSE_THREADS / 32;
     if (!mu_scratch || !mu_chunk) return (int)cudaErrorInvalidValue;
@@ -1808,6 +1808,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;
+        A.ticket_batch = SDB_TICKET_BATCH;                            /* (the fallback kernel skips nearly everything: 256) */
         cudaError_t e = cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return (int)e;
         if (ms) {
@@ -1817,7 +1818,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
             A.ticket = tickets + 0; resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
             A.ticket = tickets + 1; mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
             A.ticket = tickets + 2; mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            A.ticket = tickets + 3; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
+            A.ticket = tickets + 3; A.ticket_batch = 256; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
         }
     }
     return (int)cudaGetLastError();

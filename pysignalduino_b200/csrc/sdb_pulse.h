@@ -20,7 +20,11 @@ int pulse_blocks_per_sm(int kind);
 unsigned int debug_violations(bool reset);   /* bounds-check build only; 0xFFFFFFFF otherwise */
 size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots handed from mu_resolve_kernel to mu_scan_kernel */
 
-#define SDB_MU_CHUNK 262144u    /* messages per resolve/scan launch pair (bounds the survivor scratch: chunk * n_mu * 16 B) */
+#ifndef SDB_TICKET_BATCH
+#define SDB_TICKET_BATCH 1     /* messages a warp draws per atomicAdd on the launch's work counter */
+#endif
+#define SDB_MU_CHUNK 1048576u   /* messages per launch group of the device-resident calls (bounds the survivor scratch: chunk * n_mu * 16 B) */
+#define SDB_PIPE_CHUNK 262144u  /* messages per pipeline stage of the host-buffer calls (H2D / kernels / D2H overlap) */
 
 int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMsg *d_msgs, const uint8_t *d_digits,
                uint32_t n, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
