@@ -1808,7 +1808,7 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;
-        A.ticket_batch = SDB_TICKET_BATCH;                            /* (the fallback kernel skips nearly everything: 256) */
+        A.ticket_batch = ms ? 4 * SDB_TICKET_BATCH : SDB_TICKET_BATCH;   /* MS messages are ~10x cheaper; the fallback kernel skips nearly everything: 256 */
         cudaError_t e = cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return (int)e;
         if (ms) {
