@@ -153,24 +153,31 @@ def pack_digit_streams(streams: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.nd
     return pool, (offs[:-1] // 32).astype(np.uint32)
 
 
+_PAD32 = [b"\xff" * k for k in range(32)]          # tail padding to the 16-byte unit (0xFF -> nibble 0xF)
+_DIGIT_LUT_PAD = _DIGIT_LUT.copy()
+_DIGIT_LUT_PAD[0xFF] = DIGIT_PAD
+
+
 def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
-    """Pack MS (kind 0) or MU (kind 1) parser dicts."""
+    """Pack MS (kind 0) or MU (kind 1) parser dicts.
+
+    One pass of plain-Python bookkeeping per message (dict lookups, list appends); every array operation — the digit
+    look-up, nibble packing, record fields — runs once over the whole batch."""
     n = len(msgs)
-    rec = np.zeros(n, dtype=PULSE_DTYPE)
-    rec["cp"] = 0xFF
-    streams: List[np.ndarray] = []
     rssi: List[Any] = []
+    pats: List[int] = []            # 8 values per message
+    meta: List[int] = []            # dlen, npat, cp, pat_ids, flags per message
+    chunks: List[bytes] = []        # digit characters, each message padded to a multiple of 32 with 0xFF
     clock = np.zeros(n, dtype=np.float64)
-    empty = np.zeros(0, dtype=np.uint8)
+    zero8 = [0] * MAX_SLOTS
+    is_ms = kind == KIND_MS
     for i, m in enumerate(msgs):
         rssi.append(m.get("R"))
         data = m.get("data", "")
-        if kind == KIND_MS:
-            valid = _ms_gates(m)
-        else:
-            valid = bool(data)                     # message_unsynced.py:22-25
+        valid = _ms_gates(m) if is_ms else bool(data)          # message_unsynced.py:22-25
         if not valid:
-            streams.append(empty)
+            pats.extend(zero8)
+            meta.extend((0, 0, 0xFF, 0, 0))
             continue
         if not isinstance(data, str):
             raise DomainError(f"message {i}: 'data' must be a str")
@@ -180,26 +187,41 @@ def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
         if len(patterns) > MAX_SLOTS:
             raise DomainError(f"message {i}: {len(patterns)} pattern slots (max {MAX_SLOTS})")
         ids = 0
+        vals = zero8.copy()
         for s, (pidx, val) in enumerate(patterns.items()):
             if len(pidx) != 1:
                 raise DomainError(f"message {i}: pattern id {pidx!r} is not a single digit")
             if val != val or val in (float("inf"), float("-inf")) or val != int(val) or abs(val) > 2147483647:
                 raise DomainError(f"message {i}: pattern value {val!r} is not an int32")
-            rec["pat"][i, s] = int(val)
+            vals[s] = int(val)
             ids |= int(pidx) << (4 * s)
-        rec["pat_ids"][i] = ids
-        rec["npat"][i] = len(patterns)
-        rec["flags"][i] = MSG_VALID
-        if kind == KIND_MS:
+        cp = 0xFF
+        if is_ms:
             cp_key = str(int(m.get("CP", "")))     # message_synced.py:33,59
             if cp_key in patterns:
-                rec["cp"][i] = list(patterns).index(cp_key)
+                cp = list(patterns).index(cp_key)
                 clock[i] = abs(patterns[cp_key])
         raw = data.encode("ascii", "replace")      # one byte per character
-        streams.append(_DIGIT_LUT[np.frombuffer(raw, dtype=np.uint8)])
-        rec["dlen"][i] = len(raw)
-    pool, doff = pack_digit_streams(streams)
-    rec["doff"] = doff
+        if b"\xff" in raw:                         # cannot happen after an ascii encode; keeps the pad byte unambiguous
+            raise DomainError(f"message {i}: D contains a 0xFF byte")
+        pats.extend(vals)
+        meta.extend((len(raw), len(patterns), cp, ids, MSG_VALID))
+        chunks.append(raw)
+        pad = -len(raw) & 31
+        if pad:
+            chunks.append(_PAD32[pad])
+    rec = np.zeros(n, dtype=PULSE_DTYPE)
+    if n:
+        rec["pat"] = np.asarray(pats, dtype=np.int64).reshape(n, MAX_SLOTS).astype(np.int32)
+        mt = np.asarray(meta, dtype=np.int64).reshape(n, 5)
+        rec["dlen"], rec["npat"], rec["cp"], rec["pat_ids"], rec["flags"] = mt[:, 0], mt[:, 1], mt[:, 2], mt[:, 3], mt[:, 4]
+        units = (mt[:, 0] + 31) // 32
+        doff = np.zeros(n, dtype=np.int64)
+        np.cumsum(units[:-1], out=doff[1:])
+        rec["doff"] = doff
+    blob = b"".join(chunks) + b"\xff" * 64        # +32 B tail so device windows may over-read
+    nib = _DIGIT_LUT_PAD[np.frombuffer(blob, dtype=np.uint8)]
+    pool = (nib[0::2] | (nib[1::2] << 4)).astype(np.uint8)
     return PulseBatch(kind, rec, pool, rssi, clock)
 
 
