@@ -849,6 +849,7 @@ __device__ __forceinline__ uint64_t mu_sort3_key(uint32_t a, uint32_t b, uint32_
 {
     uint32_t lo = min(a, min(b, c)), hi = max(a, max(b, c));
     uint32_t mid = a + b + c - lo - hi;
+    if (mid == hi) mid = lo;                    /* {x, y} is (x, x, y) whichever of the two the absent keys duplicate */
     return ((uint64_t)w << 48) | ((uint64_t)lo << 32) | ((uint64_t)mid << 16) | hi;
 }
 
