@@ -111,7 +111,8 @@ typedef struct SdbPulseProto {
     uint8_t  rsv[7];
 } SdbPulseProto;
 
-/* Phase-1 prefilter row, 28 bytes: rows of the candidate-mask table that must all be non-zero. */
+/* Prefilter row, 28 bytes: rows of the candidate-mask table that must all be non-zero.  The kernels use the transposed
+ * form (kill masks per pair, off_kill); these rows stay in the blob as its source and for inspection. */
 typedef struct SdbPrefilter {
     uint16_t clk_idx;
     uint16_t nreq;
