@@ -160,8 +160,9 @@ class Corpus:
         return pack.PulseBatch(kind, msgs, digits, RssiCodes(rssi), clock)
 
 
-    def render_lines(self, batch: pack.PulseBatch):
-        """Payload lines of a packed MS / MU batch: (text uint8, line_off uint32, line_len uint32), '\\n'-separated."""
+    def render_lines(self, batch: pack.PulseBatch, framed: bool = False):
+        """Payload lines of a packed MS / MU batch: (text uint8, line_off uint32, line_len uint32), '\\n'-separated;
+        framed=True wraps every line in STX / ETX (what the serial transport delivers)."""
         L = lib()
         L.sdc_render_lines.restype = C.c_int64
         n = batch.n
@@ -175,7 +176,7 @@ class Corpus:
             text = np.empty(cap, dtype=np.uint8)
             used = L.sdc_render_lines(C.c_int(batch.kind), C.c_void_p(msgs.ctypes.data), C.c_void_p(digits.ctypes.data),
                                       C.c_void_p(rssi.ctypes.data), C.c_int64(n), C.c_void_p(text.ctypes.data), C.c_int64(cap),
-                                      C.c_void_p(off.ctypes.data), C.c_void_p(ln.ctypes.data))
+                                      C.c_void_p(off.ctypes.data), C.c_void_p(ln.ctypes.data), C.c_int(1 if framed else 0))
             if used <= cap:
                 return text[:used], off, ln
             cap = int(used) + 64

@@ -304,13 +304,14 @@ void sdc_free(void *p) { free(p); }
  * (render again with a larger buffer when > cap).
  * ------------------------------------------------------------------------------------------ */
 int64_t sdc_render_lines(int kind, const SdbPulseMsg *msgs, const uint8_t *digits, const int16_t *rssi, int64_t n,
-                         char *text, int64_t cap, uint32_t *off, uint32_t *len)
+                         char *text, int64_t cap, uint32_t *off, uint32_t *len, int framed)
 {
     int64_t used = 0;
     char buf[SDB_MAX_DIGITS + 256];
     for (int64_t i = 0; i < n; i++) {
         const SdbPulseMsg *m = &msgs[i];
         int k = 0;
+        if (framed) buf[k++] = 0x02;                        /* STX ... ETX as the firmware sends it (base.py:174-193) */
         k += sprintf(buf + k, kind == SDB_KIND_MS ? "MS;" : "MU;");
         const int valid = (m->flags & SDB_MSG_VALID) != 0;
         if (valid)
@@ -331,6 +332,7 @@ int64_t sdc_render_lines(int kind, const SdbPulseMsg *msgs, const uint8_t *digit
             k += sprintf(buf + k, "CP=%d;SP=0;", cpid);
         }
         if (rssi && rssi[i] >= 0) k += sprintf(buf + k, "R=%d;", (int)rssi[i]);
+        if (framed) buf[k++] = 0x03;
         if (off) off[i] = (uint32_t)used;
         if (len) len[i] = (uint32_t)k;
         if (used + k + 1 <= cap) { memcpy(text + used, buf, (size_t)k); text[used + k] = '\n'; }

@@ -206,12 +206,20 @@ int sdb_demod_lines_host(SdbHandle *h, int kind,
  * Returns SDB_E_OVERFLOW (with *n_lines / *text_used = what is needed) when max_lines / text_cap are too small.
  */
 #define SDB_FRAME_OTHER  4
+#define SDB_FRAME_SIDE   0x40      /* sdb_frame_lines_inplace: the (decompressed) payload is in the side buffer */
 #define SDB_FRAME_PYPATH 0x80
 #define SDB_FRAME_NONE   0xFF
 int sdb_frame_lines(const uint8_t *raw, size_t raw_len,
                     uint8_t *text, size_t text_cap,
                     uint32_t *line_off, uint32_t *line_len, uint8_t *line_type, uint32_t max_lines,
                     uint32_t *n_lines, size_t *text_used);
+
+/* The same without copying: the payload of a plain line is raw[line_off[i] .. +line_len[i]) (inside the caller's buffer,
+ * STX / ETX excluded); a reduced payload is decompressed into `side` and flagged SDB_FRAME_SIDE (offsets into side).
+ * Both offset sequences are ascending, so each subset can go to sdb_demod_lines_host with its own text buffer. */
+int sdb_frame_lines_inplace(const uint8_t *raw, size_t raw_len,
+                            uint32_t *line_off, uint32_t *line_len, uint8_t *line_type, uint32_t max_lines,
+                            uint8_t *side, size_t side_cap, uint32_t *n_lines, size_t *side_used);
 
 /*
  * Host-side JSON of the MS / MU hits of an sdb_demod_lines_host call: one string per hit, exactly

@@ -29,7 +29,7 @@ HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
-    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines",
+    "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines", "sdb_frame_lines_inplace",
 ]
 
 
@@ -88,6 +88,9 @@ def load_library() -> C.CDLL:
     L.sdb_frame_lines.restype = C.c_int
     L.sdb_frame_lines.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                   C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
+    L.sdb_frame_lines_inplace.restype = C.c_int
+    L.sdb_frame_lines_inplace.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                          C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
@@ -100,7 +103,31 @@ LINEINFO_DTYPE = np.dtype([("status", "u1"), ("has_r", "u1"), ("r_len", "<u2"), 
 LINE_INVALID, LINE_OK, LINE_HOSTPATH = 0, 1, 2
 
 
-FRAME_OTHER, FRAME_PYPATH, FRAME_NONE = 4, 0x80, 0xFF
+FRAME_OTHER, FRAME_SIDE, FRAME_PYPATH, FRAME_NONE = 4, 0x40, 0x80, 0xFF
+
+
+def frame_lines_inplace(raw: bytes):
+    """Raw receive buffer -> (line_off, line_len, line_type, side text): plain payloads are addressed inside ``raw``,
+    reduced ones are decompressed into the side buffer (type flag FRAME_SIDE)."""
+    L = load_library()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    max_lines = len(raw) // 48 + 1024          # a guess; the call reports what it needs (bytes.count would cost more than the framing)
+    cap = 4096
+    while True:
+        side = np.empty(cap, dtype=np.uint8)
+        off = np.empty(max_lines, dtype=np.uint32)
+        ln = np.empty(max_lines, dtype=np.uint32)
+        typ = np.empty(max_lines, dtype=np.uint8)
+        n, used = C.c_uint32(0), C.c_size_t(0)
+        rc = L.sdb_frame_lines_inplace(buf.ctypes.data if len(buf) else None, len(buf), off.ctypes.data, ln.ctypes.data,
+                                       typ.ctypes.data, max_lines, side.ctypes.data, cap, C.byref(n), C.byref(used))
+        if rc == SDB_E_OVERFLOW:
+            max_lines, cap = max(max_lines, n.value), max(cap, used.value + 64)
+            continue
+        if rc != SDB_OK:
+            raise SdbError(f"sdb_frame_lines_inplace failed ({rc})")
+        k = n.value
+        return off[:k], ln[:k], typ[:k], side[: used.value]
 
 
 def frame_lines(raw: bytes):

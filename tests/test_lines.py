@@ -75,6 +75,32 @@ def test_frame_lines_splits_a_buffer():
     assert np.all(np.diff(off.astype(np.int64)) >= 0)
 
 
+def test_frame_lines_inplace_single_and_multi_threaded():
+    """sdb_frame_lines_inplace: plain payloads addressed inside the caller's buffer, reduced ones decompressed into the side
+    buffer; a buffer above 4 MiB is split over host threads.  Every golden / fuzz line, repeated to 9 MiB."""
+    from pysignalduino_b200 import capi
+
+    recs = load_golden("frames.json.gz") + [[r["line"], r["payload"]] for r in load_golden("lines.json.gz") if r["rfmode"] is None]
+    lines = [(ln.encode("latin-1"), exp) for ln, exp in recs if b"\n" not in ln.encode("latin-1")]
+    one = b"\n".join(b for b, _ in lines) + b"\n"
+    for reps in (1, (9 << 20) // len(one) + 1):
+        big = one * reps
+        off, ln, typ, side = capi.frame_lines_inplace(big)
+        assert len(typ) == len(lines) * reps
+        bad = 0
+        for i in range(len(typ)):
+            t, exp = int(typ[i]), lines[i % len(lines)][1]
+            if t != capi.FRAME_NONE and (t & capi.FRAME_PYPATH):
+                continue
+            if t == capi.FRAME_NONE:
+                got = None
+            else:
+                src = side if t & capi.FRAME_SIDE else np.frombuffer(big, dtype=np.uint8)
+                got = bytes(src[int(off[i]) : int(off[i]) + int(ln[i])]).decode("latin-1")
+            bad += got != exp
+        assert bad == 0, (reps, bad)
+
+
 def test_line_oracle_matches_reference(oracle):
     """payload -> dict (oracle/line_oracle.py) -> packed record -> C oracle == what the reference's parser returned."""
     from oracle import line_oracle
