@@ -111,6 +111,7 @@ def frame_lines_inplace(raw: bytes):
     reduced ones are decompressed into the side buffer (type flag FRAME_SIDE)."""
     L = load_library()
     buf = np.frombuffer(raw, dtype=np.uint8)
+    raw = buf                                  # (bytes, memoryview and arrays alike)
     max_lines = len(raw) // 48 + 1024          # a guess; the call reports what it needs (bytes.count would cost more than the framing)
     cap = 4096
     while True:
@@ -152,6 +153,32 @@ def frame_lines(raw: bytes):
             raise SdbError(f"sdb_frame_lines failed ({rc})")
         k = n.value
         return text[: used.value], off[:k], ln[:k], typ[:k]
+
+
+def frame_chunks(raw, chunk_bytes: int = 256 << 20):
+    """Frame a large receive buffer piecewise, one chunk ahead of the consumer: yields ``(byte_base, line_base, off, ln,
+    typ, side)`` per chunk (``off`` relative to ``raw[byte_base:]`` for plain payloads).  The framing of chunk k + 1 runs
+    on the host threads (ctypes drops the GIL) while the caller feeds chunk k to the device."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    view = memoryview(raw)
+    n = len(view)
+    cuts = [0]
+    while cuts[-1] < n:
+        pos = cuts[-1] + chunk_bytes
+        if pos >= n:
+            cuts.append(n)
+            break
+        nl = bytes(view[pos : min(n, pos + (1 << 20))]).find(b"\n")       # lines are far shorter than 1 MiB
+        cuts.append(n if nl < 0 else pos + nl + 1)
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(frame_lines_inplace, view[cuts[0] : cuts[1]]) if len(cuts) > 1 else None
+        line_base = 0
+        for k in range(len(cuts) - 1):
+            off, ln, typ, side = fut.result()
+            fut = ex.submit(frame_lines_inplace, view[cuts[k + 1] : cuts[k + 2]]) if k + 2 < len(cuts) else None
+            yield cuts[k], line_base, off, ln, typ, side
+            line_base += len(typ)
 
 
 class Result:

@@ -268,25 +268,26 @@ class SignalParser:
         int64[nhits])`` per message type with device hits (hit k is ``json_pool[str_off[k]:str_off[k + 1]]`` and belongs to
         raw line ``hit_line[k]``; the hits of one line are consecutive and in reference order); ``extra`` = ``{raw line
         index: [json, ...]}`` for the lines that took the Python path (MN, lines outside the tokenizer's grammar)."""
-        from .capi import FRAME_NONE, FRAME_PYPATH, FRAME_SIDE, frame_lines_inplace
+        from .capi import FRAME_NONE, FRAME_PYPATH, FRAME_SIDE, frame_chunks
 
-        off, ln, typ, side = frame_lines_inplace(raw)
         rawbuf = np.frombuffer(raw, dtype=np.uint8)
         eng = self.protocols.engine()
         batches = []
-        framed = typ != FRAME_NONE
-        slow = [int(i) for i in np.nonzero(framed & (((typ & FRAME_PYPATH) != 0) | ((typ & 0x0F) == pack.KIND_MN)))[0]]
-        for kind in (pack.KIND_MS, pack.KIND_MU):
-            # plain payloads are addressed inside the caller's buffer, decompressed ones inside the side buffer
-            for text, sel in ((rawbuf, np.nonzero(typ == kind)[0]), (side, np.nonzero(typ == (kind | FRAME_SIDE))[0])):
-                if not len(sel):
-                    continue
-                loff = np.ascontiguousarray(off[sel])
-                res, info = eng.demod_lines(kind, text, loff, np.ascontiguousarray(ln[sel]))
-                slow.extend(int(i) for i in sel[info["status"] == LINE_HOSTPATH])
-                if len(res.hits):
-                    pool, soff = eng.format_json(kind, res.hits, res.bits, text, loff, info)
-                    batches.append((pool, soff, sel[res.hits["msg"].astype(np.int64)]))
+        slow: List[int] = []
+        for byte_base, line_base, off, ln, typ, side in frame_chunks(raw):       # chunk k + 1 is framed while chunk k decodes
+            framed = typ != FRAME_NONE
+            slow.extend(line_base + int(i) for i in np.nonzero(framed & (((typ & FRAME_PYPATH) != 0) | ((typ & 0x0F) == pack.KIND_MN)))[0])
+            for kind in (pack.KIND_MS, pack.KIND_MU):
+                # plain payloads are addressed inside the caller's buffer, decompressed ones inside the side buffer
+                for text, sel in ((rawbuf[byte_base:], np.nonzero(typ == kind)[0]), (side, np.nonzero(typ == (kind | FRAME_SIDE))[0])):
+                    if not len(sel):
+                        continue
+                    loff = np.ascontiguousarray(off[sel])
+                    res, info = eng.demod_lines(kind, text, loff, np.ascontiguousarray(ln[sel]))
+                    slow.extend(line_base + int(i) for i in sel[info["status"] == LINE_HOSTPATH])
+                    if len(res.hits):
+                        pool, soff = eng.format_json(kind, res.hits, res.bits, text, loff, info)
+                        batches.append((pool, soff, line_base + sel[res.hits["msg"].astype(np.int64)]))
         extra: Dict[int, List[str]] = {}
         if slow:
             import json
