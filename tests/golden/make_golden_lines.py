@@ -197,6 +197,13 @@ def main():
         r = reduce_line(ln, rng)
         if r:
             lines.append(r)
+    # lines the tokenizer hands to the host path on purpose: more than 32 fields, longer than 1280 bytes, non-ASCII bytes
+    for ln in base[nlit : nlit + 520 : 13]:
+        body = ln[1:-1]
+        lines.append("\x02" + body + "O;" * 40 + "\x03")
+        lines.append("\x02" + body + "zz=" + "7" * 1400 + ";\x03")
+        lines.append("\x02" + body + "q=\xe9\xb2;\x03")
+        lines.append("\x02" + body.replace(";D=", ";" * 35 + "D=", 1) + "\x03")
     lines = list(dict.fromkeys(lines))
     recs = []
     nmsg = 0
