@@ -351,13 +351,17 @@ def run_ours(args):
                 continue
             text, off, ln = corp.render_lines(s["batch"])
             t_text = torch.from_numpy(text.copy()).pin_memory()
-            info = np.zeros(s["n"], dtype=LINEINFO_DTYPE)
-            legs.append((s, hs, t_text, off, ln, info))
+            t_info = torch.zeros(s["n"] * LINEINFO_DTYPE.itemsize, dtype=torch.uint8).pin_memory()   # pageable D2H would serialise the stages
+            info = t_info.numpy().view(LINEINFO_DTYPE)
+            t_off, t_ln = torch.from_numpy(off.copy()).pin_memory(), torch.from_numpy(ln.copy()).pin_memory()
+            off, ln = t_off.numpy(), t_ln.numpy()
+            legs.append((s, hs, (t_text, t_info, t_off, t_ln), off, ln, info))
             n_lines += s["n"]
             text_bytes += int(text.nbytes)
 
         def lines_step():
-            for s, hs, t_text, off, ln, info in legs:
+            for s, hs, keep, off, ln, info in legs:
+                t_text = keep[0]
                 rc = eng.lib.sdb_demod_lines_host(eng.h, s["kind"], t_text.data_ptr(), t_text.numel(), off.ctypes.data, ln.ctypes.data,
                                                   s["n"], hs["out"].ctypes.data, hs["hits"].ctypes.data, len(hs["hits"]),
                                                   hs["bits"].ctypes.data, len(hs["bits"]), hs["ctr"].ctypes.data, info.ctypes.data)

@@ -342,10 +342,6 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
     memset(counters, 0, sizeof *counters);
     if (n == 0) return SDB_OK;
     if (text_len >= (1ull << 32)) return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: text larger than 4 GiB");
-    for (uint32_t i = 0; i < n; i++) {
-        if ((size_t)line_off[i] + line_len[i] > text_len || (i && line_off[i] < line_off[i - 1] + line_len[i - 1]))
-            return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: lines must be ascending, disjoint and inside the text");
-    }
     int rc;
     const size_t pool_bytes = sdb::lines_pool_bytes(text_len, n);
     if ((rc = grow(h, reinterpret_cast<uint8_t *&>(h->d_msgs), h->cap_msgs, sizeof(SdbPulseMsg) * (size_t)n))) return rc;
@@ -368,6 +364,10 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
     CK(cudaMemsetAsync(h->d_ctr, 0, sizeof(SdbCounters), st));
     auto h2d = [&](uint32_t k) -> int {
         const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
+        /* argument check of this stage's lines, here so that it overlaps the kernels of the stages already queued */
+        for (uint32_t i = lo; i < lo + cnt; i++)
+            if ((size_t)line_off[i] + line_len[i] > text_len || (i && line_off[i] < line_off[i - 1] + line_len[i - 1]))
+                return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: lines must be ascending, disjoint and inside the text");
         const size_t t0 = line_off[lo], t1 = (size_t)line_off[lo + cnt - 1] + line_len[lo + cnt - 1];
         CK(cudaMemcpyAsync(h->d_text + t0, text + t0, t1 - t0, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaMemcpyAsync(d_off + lo, line_off + lo, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
