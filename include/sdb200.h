@@ -177,7 +177,8 @@ int sdb_format_hits(const SdbHandle *h, int kind,
  * Results are indexed by line.  info[i].status: SDB_LINE_INVALID = the reference yields [] for the line,
  * SDB_LINE_OK = decoded here, SDB_LINE_HOSTPATH = outside the canonical grammar (non-ASCII, duplicate / multi-digit
  * pattern ids, values float() reads differently, D > 1024 digits): the caller packs that line itself.
- * All pointers are HOST pointers.
+ * All pointers are HOST pointers; pass PINNED buffers (text, offsets, out, info, hits, bits): the call pipelines H2D /
+ * kernels / D2H per stage, and a pageable buffer makes each asynchronous copy synchronous with the host.
  */
 typedef struct SdbLineInfo {
     uint8_t  status;             /* SDB_LINE_*                                                   */
