@@ -393,9 +393,9 @@ def run_ours(args):
                 t_frame += time.perf_counter() - t0
                 t0 = time.perf_counter()
                 nl = 0
-                for byte_base, line_base, foff, fln, ftyp, side in frame_chunks(raw):
+                for byte_base, byte_end, line_base, foff, fln, ftyp, side in frame_chunks(raw):
                     k = len(ftyp)
-                    rc = eng.lib.sdb_demod_lines_host(eng.h, s["kind"], t_pin.data_ptr() + byte_base, t_pin.numel() - byte_base,
+                    rc = eng.lib.sdb_demod_lines_host(eng.h, s["kind"], t_pin.data_ptr() + byte_base, byte_end - byte_base,
                                                       foff.ctypes.data, fln.ctypes.data, k, hs["out"].ctypes.data, hs["hits"].ctypes.data,
                                                       len(hs["hits"]), hs["bits"].ctypes.data, len(hs["bits"]), hs["ctr"].ctypes.data,
                                                       info.ctypes.data)

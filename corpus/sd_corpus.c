@@ -17,6 +17,7 @@
 #include "../include/sdb200.h"
 
 #define GEN_MAXLIST 16
+#define CORPUS_MAX_DIGITS 1024   /* BASELINE config 3: D <= 1 024 digits (the packed domain itself allows SDB_MAX_DIGITS) */
 
 typedef struct GenProto {
     int32_t is_ms;                 /* has a numeric list `sync` */
@@ -90,12 +91,12 @@ static int vals_find(const Vals *vs, double v)
 }
 
 typedef struct {
-    uint8_t d[SDB_MAX_DIGITS + 64];
+    uint8_t d[CORPUS_MAX_DIGITS + 64];
     int n;
 } Digits;
 static void dig_list(Digits *D, const Vals *vs, const int *slot_id, const double *l, int n)
 {
-    for (int i = 0; i < n && D->n < SDB_MAX_DIGITS + 32; i++) {
+    for (int i = 0; i < n && D->n < CORPUS_MAX_DIGITS + 32; i++) {
         int k = vals_find(vs, l[i]);
         D->d[D->n++] = (uint8_t)(k >= 0 ? slot_id[k] : 9);
     }
@@ -167,7 +168,7 @@ static void gen_ms(Rng *r, const GenProto *tab, const int *ms_ids, int nms, SdbP
     int nb = pick_bits(r, p, 24, 64);
     D->n = 0;
     dig_list(D, &vs, slot_id, p->sync, p->nsync);
-    for (int b = 0; b < nb && D->n + p->none <= SDB_MAX_DIGITS; b++) {
+    for (int b = 0; b < nb && D->n + p->none <= CORPUS_MAX_DIGITS; b++) {
         if (rng_below(r, 2)) dig_list(D, &vs, slot_id, p->one, p->none);
         else dig_list(D, &vs, slot_id, p->zero, p->nzero > 0 ? p->nzero : p->none);
     }
@@ -218,8 +219,8 @@ static void gen_mu(Rng *r, const GenProto *tab, const int *mu_ids, int nmu, SdbP
     int frames = rng_range(r, 2, 4);
     int w = p->none > 0 ? p->none : 2;
     int per_frame = p->nstart + nb * w + p->npause + p->nend + p->nsync + 1;
-    while (frames > 1 && frames * per_frame > SDB_MAX_DIGITS) frames--;
-    while (frames * per_frame > SDB_MAX_DIGITS && nb > 1) { nb--; per_frame -= w; }
+    while (frames > 1 && frames * per_frame > CORPUS_MAX_DIGITS) frames--;
+    while (frames * per_frame > CORPUS_MAX_DIGITS && nb > 1) { nb--; per_frame -= w; }
     uint64_t bits[4] = {rng_next(r), rng_next(r), rng_next(r), rng_next(r)};
     int truncate_last = p->reconstruct && rng_below(r, 100) < 30;
     D->n = 0;
@@ -236,9 +237,9 @@ static void gen_mu(Rng *r, const GenProto *tab, const int *mu_ids, int nmu, SdbP
         if (use_pause) dig_list(D, &vs, slot_id, p->pause, p->npause);
         if (use_end) dig_list(D, &vs, slot_id, p->end, p->nend);
         if (use_sync) dig_list(D, &vs, slot_id, p->sync, p->nsync);
-        if (gap_k >= 0 && D->n < SDB_MAX_DIGITS + 32) D->d[D->n++] = (uint8_t)slot_id[gap_k];
+        if (gap_k >= 0 && D->n < CORPUS_MAX_DIGITS + 32) D->d[D->n++] = (uint8_t)slot_id[gap_k];
     }
-    if (D->n > SDB_MAX_DIGITS) D->n = SDB_MAX_DIGITS;
+    if (D->n > CORPUS_MAX_DIGITS) D->n = CORPUS_MAX_DIGITS;
     m->cp = 0xFF;
     m->flags = SDB_MSG_VALID;
     *rssi = rng_below(r, 2) ? (int16_t)rng_range(r, 0, 255) : (int16_t)-1;
@@ -307,7 +308,7 @@ int64_t sdc_render_lines(int kind, const SdbPulseMsg *msgs, const uint8_t *digit
                          char *text, int64_t cap, uint32_t *off, uint32_t *len, int framed)
 {
     int64_t used = 0;
-    char buf[SDB_MAX_DIGITS + 256];
+    char buf[CORPUS_MAX_DIGITS + 256];
     for (int64_t i = 0; i < n; i++) {
         const SdbPulseMsg *m = &msgs[i];
         int k = 0;

@@ -24,7 +24,7 @@ extern "C" {
 
 /* ---- limits of the packed domain ------------------------------------------------ */
 #define SDB_MAX_SLOTS   8      /* P0..P7: pulse-pattern slots per message (firmware emits <= 8) */
-#define SDB_MAX_DIGITS  1024   /* digits in one D= stream (BASELINE config 3: D <= 1024)       */
+#define SDB_MAX_DIGITS  4096   /* digits in one D= stream (fast kernels stage 1024, longer messages take the long kernels) */
 #define SDB_DIGIT_OTHER 0xE    /* any character of D that is not '0'..'9'                      */
 #define SDB_DIGIT_PAD   0xF    /* padding nibble after the last digit                          */
 #define SDB_MAX_HEX     512    /* hex characters in one MC / MN D= field                       */
@@ -47,6 +47,8 @@ extern "C" {
 #define SDB_ST_INDEXERROR  1   /* message_unsynced.py:212 chunks[-1] on an empty capture            */
 #define SDB_ST_TYPEERROR   2   /* manchester.py:84 / :120, helpers.py:114 (MC as shipped; id 57)    */
 #define SDB_ST_VALUEERROR  3   /* message_synced.py:174 range(..., 0) with signal_width == 0        */
+#define SDB_ST_DOMAIN      4   /* NOT a reference outcome: the message is outside the packed domain (SDB_MSG_DOMAIN, or a
+                                  malformed record); it was not decoded — no hits, reported per message, never silently wrong */
 
 /*
  * One MS / MU message after host-side packing of the parser dict
@@ -65,6 +67,9 @@ typedef struct SdbPulseMsg {
 } SdbPulseMsg;
 
 #define SDB_MSG_VALID 0x01       /* passed the host-side input gates; a message without it yields [] */
+#define SDB_MSG_DOMAIN 0x04      /* the packer could not represent the message (non-integer pulse value, pattern id > 9,
+                                    more than SDB_MAX_SLOTS slots, D longer than SDB_MAX_DIGITS / SDB_MAX_HEX, lower-case hex):
+                                    status SDB_ST_DOMAIN, the rest of the batch is decoded normally */
 
 /*
  * One MC / MN message (sd_protocols.py:79-88: protocol_id, data, clock, bit_length).
@@ -87,8 +92,28 @@ typedef struct SdbMsgOut {
     uint32_t hit_off;
     uint16_t nhits;
     uint8_t  status;             /* SDB_ST_* */
-    uint8_t  rsv;
+    uint8_t  reason;             /* MC: why _demodulate_mc_data rejected the message (SDB_MCR_*, 0 = none); 0 otherwise */
 } SdbMsgOut;
+
+/* MC reject reasons (manchester.py:70-128 and the mcBit2* decoders): the host renders the reference's message text */
+#define SDB_MCR_NONE 0
+#define SDB_MCR_TOO_SHORT 1        /* 'message is too short' */
+#define SDB_MCR_TOO_LONG 2         /* 'message is too long' */
+#define SDB_MCR_WRONG_BEGIN 3      /* 'wrong bits at begin' */
+#define SDB_MCR_PARITY 4           /* 'parity error' */
+#define SDB_MCR_CHECKSUM 5         /* 'checksum error' */
+#define SDB_MCR_NO_START 6         /* '<name>: lib/mcBit2Sainlogic, start 010100 not found' */
+#define SDB_MCR_NOT_32 7           /* 'message must be 32 bits, got <n>' */
+#define SDB_MCR_NOT_56 8           /* 'message must be 56 bits, got <n>' */
+#define SDB_MCR_NO_SYNC 9          /* 'sync not found' */
+#define SDB_MCR_NO_DUP 10          /* ' no duplicate found'; sdb_unit_mc ORs SDB_MCR_DUP_*; SdbMsgOut.reason uses 12 / 13 / 14 */
+#define SDB_MCR_LOOP 11            /* 'loop error, please report this data <bits>' */
+#define SDB_MCR_CLOCK 20           /* 'clock out of range' (manchester.py:86) */
+#define SDB_MCR_NO_METHOD 21       /* [(-1, 'Protocol method not defined', {})] (:108-109) */
+#define SDB_MCR_UNKNOWN_METHOD 22  /* 'Unknown protocol method <name>' (:121-123) */
+#define SDB_MCR_DUP_SHORT 0x100    /* ', message is too short' */
+#define SDB_MCR_DUP_LONG 0x200     /* ', message is too long' */
+#define SDB_MCR_DUP_NOPROTO 0x400  /* ', protocol does not exists' */
 
 /* One decoded message ("hit"), 16 bytes.  payload bits live in the bit arena. */
 typedef struct SdbHit {
@@ -104,13 +129,16 @@ typedef struct SdbHit {
 #define SDB_HIT_HAS_F   0x01     /* a second plane of nbits follows: 1 = symbol is 'F' (float)           */
 #define SDB_HIT_LIST    0x02     /* MC TFA: element of the duplicate list (manchester.py:705-717)        */
 #define SDB_HIT_FIELDS  0x04     /* MN: bits hold decoder fields, host renders "OK 9 ..." / "OK 24 ..."  */
+#define SDB_HIT_MM_HOST 0x08     /* MU, user-edited tables only: the protocol's modulematch is a regex the device program cannot
+                                    express; the caller must still apply re.search(modulematch, payload) (message_unsynced.py:277-280)
+                                    — pysignalduino_b200's formatters do.  Never set with the shipped protocol table. */
 
 /* Device-side counters written by every demod call (16 bytes). */
 typedef struct SdbCounters {
     uint32_t hits;               /* hit records needed (may exceed capacity -> SDB_E_OVERFLOW)           */
     uint32_t words;              /* bit-arena words needed                                               */
-    uint32_t raised;             /* messages whose status != SDB_ST_OK                                   */
-    uint32_t rsv;
+    uint32_t raised;             /* messages for which the reference raises (status 1..3)                */
+    uint32_t domain;             /* messages with status SDB_ST_DOMAIN                                   */
 } SdbCounters;
 
 typedef struct SdbHandle SdbHandle;
@@ -176,7 +204,7 @@ int sdb_format_hits(const SdbHandle *h, int kind,
  * of demodulate_ms / _mu (message_synced.py:21-66, message_unsynced.py:22-35); the demodulation kernels follow.
  * Results are indexed by line.  info[i].status: SDB_LINE_INVALID = the reference yields [] for the line,
  * SDB_LINE_OK = decoded here, SDB_LINE_HOSTPATH = outside the canonical grammar (non-ASCII, duplicate / multi-digit
- * pattern ids, values float() reads differently, D > 1024 digits): the caller packs that line itself.
+ * pattern ids, values float() reads differently, D > SDB_MAX_DIGITS digits): the caller packs that line itself.
  * All pointers are HOST pointers; pass PINNED buffers (text, offsets, out, info, hits, bits): the call pipelines H2D /
  * kernels / D2H per stage, and a pageable buffer makes each asynchronous copy synchronous with the host.
  */
@@ -255,6 +283,21 @@ int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_in, uint32_
 int sdb_unit_mc(SdbHandle *h, uint32_t proto, int method_override, const uint8_t *bits, uint32_t n, int mcbitnum,
                 uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int32_t *seg, uint32_t seg_cap,
                 uint32_t *n_seg, int *rcode, int *reason);
+
+/*
+ * One pattern_exists call (sd_protocols/pattern_utils.py:34-136) through the warp-level resolver of the MS / MU kernels:
+ * does the pulse template occur in the digit string, and with which pattern ids?
+ *   tpl / tpl_len   one compiled template (48 bytes: pysignalduino_b200/table.py KEYTPL_DTYPE = csrc/sdb_table.h SdbKeyTpl:
+ *                   length, distinct values, their accepted tenths intervals, offsets into `rank`)
+ *   rank / n_rank   dense gap ranks of the template's distinct values over their intervals (candidate order, :83)
+ *   tenths[8]       10 * pattern value per slot (slot order = dict order); pat_ids = nibble s: the id digit of slot s
+ *   digits / dlen   the data string, nibble-packed as in SdbPulseMsg (16-byte padded with 0xF)
+ * *found = 1: target_digits receives the len matched id digits (one per byte), *pos the first occurrence; 0: returns -1 there.
+ */
+int sdb_unit_pattern_exists(SdbHandle *h, const void *tpl, size_t tpl_len, const uint16_t *rank, uint32_t n_rank,
+                            const int16_t *tenths, uint32_t pat_ids, uint32_t npat,
+                            const uint8_t *digits, size_t digits_len, uint32_t dlen,
+                            int *found, uint8_t *target_digits, uint32_t target_cap, int *pos);
 
 /*
  * Bounds-check build only (libsdb200_chk.so, -DSDB_BOUNDS_CHECK): number of out-of-range shared-memory

@@ -1,8 +1,9 @@
-"""Import the REAL reference (build container only: /root/reference is absent on the GPU box).
+"""Import the REAL reference: /root/reference in the build container, else the unmodified copy that
+oracle/make_ref.py installed into the git-ignored oracle/_ref/ (which travels to the GPU box).
 
-Used by oracle/validate_vs_reference.py and tests/golden/make_golden.py to pin the C oracle
-and to generate the committed golden fixtures.  Never imported by the product or by
-anything that runs on the GPU box.
+Used by oracle/validate_vs_reference.py and tests/golden/make_golden*.py to pin the C oracle and to generate the
+committed golden fixtures, and by bench.py's cpu_baseline / --impl reference legs to TIME the reference's own Python
+path on the GPU box's host cores.  Never imported by the product.
 """
 from __future__ import annotations
 
@@ -11,6 +12,8 @@ from pathlib import Path
 from typing import Any, Dict, List, Tuple
 
 REFERENCE_ROOT = Path("/root/reference")
+if not (REFERENCE_ROOT / "sd_protocols" / "sd_protocols.py").exists():
+    REFERENCE_ROOT = Path(__file__).resolve().parent / "_ref"
 
 
 def available() -> bool:
@@ -19,7 +22,7 @@ def available() -> bool:
 
 def reference_class():
     if not available():
-        raise RuntimeError("reference tree not present (expected only in the build container)")
+        raise RuntimeError("reference not present: neither /root/reference nor oracle/_ref (python oracle/make_ref.py)")
     if str(REFERENCE_ROOT) not in sys.path:
         sys.path.insert(0, str(REFERENCE_ROOT))
     from sd_protocols import SDProtocols  # type: ignore

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libsdb200.so"
 LIB_CHK = PKG / "libsdb200_chk.so"      # same sources with -DSDB_BOUNDS_CHECK
-SOURCES = ["sdb_capi.cu", "sdb_pulse.cu", "sdb_hex.cu", "sdb_lines.cu", "sdb_frame.cu"]
+SOURCES = ["sdb_capi.cu", "sdb_pulse.cu", "sdb_pulse_long.cu", "sdb_hex.cu", "sdb_lines.cu", "sdb_frame.cu"]
 HEADERS = ["sdb_table.h", "sdb_pulse.h", "sdb_postdemod.cuh", "sdb_pyctype.h", "../../include/sdb200.h"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

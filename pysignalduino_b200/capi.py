@@ -20,16 +20,18 @@ CHECKED = os.environ.get("SDB200_CHECKED") == "1"      # use the bounds-check bu
 LIB_PATH = Path(__file__).resolve().parent / ("libsdb200_chk.so" if CHECKED else "libsdb200.so")
 
 SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU = 0, -1, -2, -3, -4
-ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR = 0, 1, 2, 3
-STATUS_EXC = {ST_INDEXERROR: IndexError, ST_TYPEERROR: TypeError, ST_VALUEERROR: ValueError}
-STATUS_NAMES = {ST_OK: "ok", ST_INDEXERROR: "IndexError", ST_TYPEERROR: "TypeError", ST_VALUEERROR: "ValueError"}
+ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR, ST_DOMAIN = 0, 1, 2, 3, 4
+STATUS_EXC = {ST_INDEXERROR: IndexError, ST_TYPEERROR: TypeError, ST_VALUEERROR: ValueError, ST_DOMAIN: pack.DomainError}
+STATUS_NAMES = {ST_OK: "ok", ST_INDEXERROR: "IndexError", ST_TYPEERROR: "TypeError", ST_VALUEERROR: "ValueError",
+                ST_DOMAIN: "DomainError"}    # DomainError: outside the packed domain, NOT decoded (never a reference outcome)
 
-HIT_HAS_F, HIT_LIST, HIT_FIELDS = 0x01, 0x02, 0x04
+HIT_HAS_F, HIT_LIST, HIT_FIELDS, HIT_MM_HOST = 0x01, 0x02, 0x04, 0x08
 
 EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
     "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines", "sdb_frame_lines_inplace",
+    "sdb_unit_pattern_exists",
 ]
 
 
@@ -91,6 +93,10 @@ def load_library() -> C.CDLL:
     L.sdb_frame_lines_inplace.restype = C.c_int
     L.sdb_frame_lines_inplace.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                           C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
+    L.sdb_unit_pattern_exists.restype = C.c_int
+    L.sdb_unit_pattern_exists.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                          C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_int), C.c_void_p, C.c_uint32,
+                                          C.POINTER(C.c_int)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
     if L.sdb_abi_version() != 1:
@@ -156,28 +162,39 @@ def frame_lines(raw: bytes):
 
 
 def frame_chunks(raw, chunk_bytes: int = 256 << 20):
-    """Frame a large receive buffer piecewise, one chunk ahead of the consumer: yields ``(byte_base, line_base, off, ln,
-    typ, side)`` per chunk (``off`` relative to ``raw[byte_base:]`` for plain payloads).  The framing of chunk k + 1 runs
-    on the host threads (ctypes drops the GIL) while the caller feeds chunk k to the device."""
+    """Frame a large receive buffer piecewise, one chunk ahead of the consumer: yields ``(byte_base, byte_end, line_base,
+    off, ln, typ, side)`` per chunk (``off`` relative to ``raw[byte_base:byte_end]`` for plain payloads).  The framing of
+    chunk k + 1 runs on the host threads (ctypes drops the GIL) while the caller feeds chunk k to the device.  Chunks end
+    on a line boundary and stay below 4 GiB (the device path addresses text with 32-bit offsets)."""
     from concurrent.futures import ThreadPoolExecutor
 
     view = memoryview(raw)
     n = len(view)
+    chunk_bytes = max(1 << 16, min(chunk_bytes, 1 << 31))
     cuts = [0]
     while cuts[-1] < n:
         pos = cuts[-1] + chunk_bytes
         if pos >= n:
             cuts.append(n)
             break
-        nl = bytes(view[pos : min(n, pos + (1 << 20))]).find(b"\n")       # lines are far shorter than 1 MiB
-        cuts.append(n if nl < 0 else pos + nl + 1)
+        cut = n
+        probe = pos
+        while probe < n:                                            # lines are far shorter than 1 MiB; keep looking if not
+            if probe - cuts[-1] >= (1 << 32) - (2 << 20):
+                raise SdbError("frame_chunks: a single line of more than 3.9 GiB cannot be framed")
+            nl = bytes(view[probe : min(n, probe + (1 << 20))]).find(b"\n")
+            if nl >= 0:
+                cut = probe + nl + 1
+                break
+            probe += 1 << 20
+        cuts.append(cut)
     with ThreadPoolExecutor(max_workers=1) as ex:
         fut = ex.submit(frame_lines_inplace, view[cuts[0] : cuts[1]]) if len(cuts) > 1 else None
         line_base = 0
         for k in range(len(cuts) - 1):
             off, ln, typ, side = fut.result()
             fut = ex.submit(frame_lines_inplace, view[cuts[k + 1] : cuts[k + 2]]) if k + 2 < len(cuts) else None
-            yield cuts[k], line_base, off, ln, typ, side
+            yield cuts[k], cuts[k + 1], line_base, off, ln, typ, side
             line_base += len(typ)
 
 
@@ -366,6 +383,22 @@ class Engine:
                 o += int(ln)
             return rcode.value, reason.value, parts
         return rcode.value, reason.value, [s]
+
+    def unit_pattern_exists(self, tpl: np.ndarray, rank: np.ndarray, tenths: np.ndarray, pat_ids: int, npat: int,
+                            digits: np.ndarray, dlen: int):
+        """One pattern_exists call on the device: -> (found, [id digit per template position], first position)."""
+        tpl = np.ascontiguousarray(tpl)
+        rank = np.ascontiguousarray(rank, dtype=np.uint16)
+        tenths = np.ascontiguousarray(tenths, dtype=np.int16)
+        digits = np.ascontiguousarray(digits, dtype=np.uint8)
+        tgt = np.zeros(16, dtype=np.uint8)
+        found, pos = C.c_int(0), C.c_int(0)
+        rc = self.lib.sdb_unit_pattern_exists(self.h, tpl.ctypes.data, tpl.nbytes, rank.ctypes.data if len(rank) else None, len(rank),
+                                              tenths.ctypes.data, pat_ids, npat, digits.ctypes.data if len(digits) else None,
+                                              digits.nbytes, dlen, C.byref(found), tgt.ctypes.data, len(tgt), C.byref(pos))
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_unit_pattern_exists")
+        return bool(found.value), [int(x) for x in tgt[: int(tpl["len"])]], pos.value
 
     def debug_violations(self, reset: bool = False) -> int:
         """Out-of-range index count of the bounds-check build (0xFFFFFFFF from the normal build)."""

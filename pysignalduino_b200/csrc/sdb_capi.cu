@@ -21,7 +21,7 @@
 struct SdbHandle {
     int device = 0;
     int sm_count = 0;
-    int grid_ms = 0, grid_mu = 0, grid_hex = 0;
+    int grid_ms = 0, grid_mu = 0, grid_hex = 0, grid_long = 0;
     std::vector<uint8_t> blob;          /* host copy (formatting needs preamble / flags) */
     uint8_t *d_blob = nullptr;
     SdbDevTable tab{};
@@ -100,7 +100,7 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     CKC(cudaMalloc(&h->d_blob, blob_len));
     CKC(cudaMemcpy(h->d_blob, blob, blob_len, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&h->d_ctr, sizeof(SdbCounters)));
-    CKC(cudaMalloc(&h->d_unit, 16384));
+    CKC(cudaMalloc(&h->d_unit, 32768));
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
@@ -121,6 +121,7 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     h->grid_ms = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MS);
     h->grid_mu = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MU);
     h->grid_hex = h->sm_count * 8;
+    h->grid_long = h->sm_count * sdb_long::long_blocks_per_sm();
 #undef CKC
     *out = h;
     return SDB_OK;
@@ -174,7 +175,7 @@ static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, cons
         }
     }
     int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid,
-                               h->d_mu_scratch, h->mu_chunk, msg_base, st);
+                               h->grid_long, h->d_mu_scratch, h->mu_chunk, msg_base, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "pulse kernel launch", static_cast<cudaError_t>(rc));
     return SDB_OK;
 }
@@ -350,10 +351,11 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
     if ((rc = grow(h, h->d_hits, h->cap_hits, sizeof(SdbHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
     if ((rc = grow(h, h->d_bits, h->cap_bits, sizeof(uint32_t) * (size_t)(bits_cap ? bits_cap : 1)))) return rc;
     if ((rc = grow(h, h->d_text, h->cap_text, text_len + 16))) return rc;
-    if ((rc = grow(h, h->d_lines, h->cap_lines, (2 * sizeof(uint32_t) + sizeof(SdbLineInfo)) * (size_t)n))) return rc;
+    if ((rc = grow(h, h->d_lines, h->cap_lines, (3 * sizeof(uint32_t) + sizeof(SdbLineInfo)) * (size_t)n + 64))) return rc;
     cudaStream_t st = h->stream;
     uint32_t *d_off = reinterpret_cast<uint32_t *>(h->d_lines), *d_len = d_off + n;
     SdbLineInfo *d_info = reinterpret_cast<SdbLineInfo *>(d_len + n);
+    uint32_t *d_long = reinterpret_cast<uint32_t *>(d_info + n);      /* [0] list length, [1] work counter, then the list of long lines */
     SdbPulseMsg *dm = static_cast<SdbPulseMsg *>(h->d_msgs);
     /* per stage of SDB_PIPE_CHUNK lines: H2D of the chunk's text / offsets (copy stream) -> tokenizer + demodulation kernels
      * (compute stream) -> D2H of the result slots and line infos (d2h stream); chunk k+1's copy overlaps chunk k's kernels.
@@ -381,7 +383,7 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
         const uint32_t lo = k * C, cnt = n - lo < C ? n - lo : C;
         if (k + 1 < nchunks && (rc = h2d(k + 1))) return rc;
         CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
-        rc = sdb::launch_tokenize(kind, h->d_text, d_off + lo, d_len + lo, cnt, lo, dm + lo, h->d_digits, d_info + lo, h->sm_count, st);
+        rc = sdb::launch_tokenize(kind, h->d_text, d_off + lo, d_len + lo, cnt, lo, dm + lo, h->d_digits, d_info + lo, d_long, h->sm_count, st);
         if (rc != 0) return set_err(h, SDB_E_CUDA, "tokenize kernel launch", static_cast<cudaError_t>(rc));
         rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
         if (rc != SDB_OK) return rc;
@@ -622,10 +624,10 @@ extern "C" int sdb_unit_postdemod(SdbHandle *h, int method, const uint8_t *bits_
                                   uint8_t *bits_out, uint32_t out_cap, uint32_t *n_out, int *rcode)
 {
     if (!h || !n_out || !rcode || (n_in && !bits_in)) return SDB_E_ARG;
-    if (n_in > 2048 || out_cap > 4096) return set_err(h, SDB_E_ARG, "sdb_unit_postdemod: input too long");
+    if (n_in > SDB_MAX_DIGITS || out_cap > 8192) return set_err(h, SDB_E_ARG, "sdb_unit_postdemod: input too long");
     CK(cudaSetDevice(h->device));
-    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 4096;
-    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 12288);
+    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 8192;
+    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 24576);
     if (n_in) CK(cudaMemcpyAsync(d_in, bits_in, n_in, cudaMemcpyHostToDevice, h->stream));
     int rc = sdb::launch_unit_postdemod(method, d_in, n_in, d_out, out_cap, d_res, h->stream);
     if (rc != 0) return set_err(h, rc < 0 ? SDB_E_ARG : SDB_E_CUDA, "unit postdemod launch", rc > 0 ? static_cast<cudaError_t>(rc) : cudaSuccess);
@@ -647,9 +649,9 @@ extern "C" int sdb_unit_mc(SdbHandle *h, uint32_t proto, int method_override, co
     if (!h || !n_out || !n_seg || !rcode || !reason || (n && !bits)) return SDB_E_ARG;
     if (n > SDB_MAX_HEX * 4 || out_cap > 4096 || (proto >= h->tab.nproto && proto != 0xFFFFFFFFu)) return set_err(h, SDB_E_ARG, "sdb_unit_mc: bad argument");
     CK(cudaSetDevice(h->device));
-    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 4096;
-    int32_t *d_seg = reinterpret_cast<int32_t *>(h->d_unit + 8192);      /* <= 48 segments */
-    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 12288);
+    uint8_t *d_in = h->d_unit, *d_out = h->d_unit + 8192;
+    int32_t *d_seg = reinterpret_cast<int32_t *>(h->d_unit + 16384);     /* <= 48 segments */
+    int32_t *d_res = reinterpret_cast<int32_t *>(h->d_unit + 24576);
     if (n) CK(cudaMemcpyAsync(d_in, bits, n, cudaMemcpyHostToDevice, h->stream));
     int rc = sdb::launch_unit_mc(h->tab, proto, method_override, d_in, (int)n, mcbitnum, d_out, (int)out_cap, d_seg, d_res, h->stream);
     if (rc != 0) return set_err(h, rc < 0 ? SDB_E_ARG : SDB_E_CUDA, "unit mc launch", rc > 0 ? static_cast<cudaError_t>(rc) : cudaSuccess);
@@ -662,4 +664,45 @@ extern "C" int sdb_unit_mc(SdbHandle *h, uint32_t proto, int method_override, co
     if (no && bits_out) CK(cudaMemcpy(bits_out, d_out, no < out_cap ? no : out_cap, cudaMemcpyDeviceToHost));
     if (ns && seg) CK(cudaMemcpy(seg, d_seg, sizeof(int32_t) * (ns < seg_cap ? ns : seg_cap), cudaMemcpyDeviceToHost));
     return SDB_OK;
+}
+
+extern "C" int sdb_unit_pattern_exists(SdbHandle *h, const void *tpl, size_t tpl_len, const uint16_t *rank, uint32_t n_rank,
+                                       const int16_t *tenths, uint32_t pat_ids, uint32_t npat,
+                                       const uint8_t *digits, size_t digits_len, uint32_t dlen,
+                                       int *found, uint8_t *target_digits, uint32_t target_cap, int *pos)
+{
+    if (!h || !tpl || tpl_len != sizeof(SdbKeyTpl) || !tenths || !found || !pos || (n_rank && !rank) || (dlen && !digits))
+        return set_err(h, SDB_E_ARG, "sdb_unit_pattern_exists: bad argument");
+    if (dlen > SDB_MAX_DIGITS || npat > SDB_MAX_SLOTS || digits_len < (((size_t)dlen + 31) / 32) * 16 || n_rank > 65536)
+        return set_err(h, SDB_E_ARG, "sdb_unit_pattern_exists: outside the packed domain");
+    SdbKeyTpl k;
+    memcpy(&k, tpl, sizeof k);
+    if (k.len == 0 || k.len > SDB_MAX_TPL || k.nuniq == 0 || k.nuniq > SDB_MAX_UNIQ) return set_err(h, SDB_E_ARG, "sdb_unit_pattern_exists: bad template");
+    for (int u = 0; u < k.nuniq; u++)
+        if (k.hi[u] < k.lo[u] || (size_t)k.rank_off[u] + (size_t)(k.hi[u] - k.lo[u]) >= n_rank) return set_err(h, SDB_E_ARG, "sdb_unit_pattern_exists: rank table too short");
+    CK(cudaSetDevice(h->device));
+    /* scratch: [digits + 64 B | rank | tenths | res] */
+    const size_t dbytes = (((size_t)dlen + 31) / 32) * 16 + 64, rbytes = ((size_t)n_rank * 2 + 15) & ~(size_t)15;
+    uint8_t *buf = nullptr;
+    CK(cudaMalloc(&buf, dbytes + rbytes + 64));
+    auto done = [&](int code) { cudaFree(buf); return code; };
+    cudaStream_t st = h->stream;
+    cudaError_t e = cudaMemsetAsync(buf, 0xFF, dbytes, st);
+    if (e == cudaSuccess && dlen) e = cudaMemcpyAsync(buf, digits, (((size_t)dlen + 31) / 32) * 16, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_rank) e = cudaMemcpyAsync(buf + dbytes, rank, (size_t)n_rank * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(buf + dbytes + rbytes, tenths, 16, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return done(set_err(h, SDB_E_CUDA, "sdb_unit_pattern_exists: copy", e));
+    int32_t *d_res = reinterpret_cast<int32_t *>(buf + dbytes + rbytes + 16);
+    int rc = sdb_long::launch_unit_pattern(k, reinterpret_cast<const uint16_t *>(buf + dbytes), reinterpret_cast<const int16_t *>(buf + dbytes + rbytes),
+                                           pat_ids, (int)npat, buf, (int)dlen, d_res, st);
+    if (rc != 0) return done(set_err(h, rc < 0 ? SDB_E_ARG : SDB_E_CUDA, "unit pattern launch", rc > 0 ? static_cast<cudaError_t>(rc) : cudaSuccess));
+    int32_t res[4] = {0, 0, 0, 0};
+    e = cudaMemcpyAsync(res, d_res, sizeof res, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(set_err(h, SDB_E_CUDA, "sdb_unit_pattern_exists: sync", e));
+    *found = res[0];
+    *pos = res[3];
+    const uint64_t tg = ((uint64_t)(uint32_t)res[2] << 32) | (uint32_t)res[1];
+    if (target_digits) for (uint32_t i = 0; i < k.len && i < target_cap; i++) target_digits[i] = (uint8_t)((tg >> (4 * i)) & 0xF);
+    return done(SDB_OK);
 }

@@ -94,21 +94,7 @@ __device__ __forceinline__ bool in_range(const SdbHexProto &p, int n)
 
 /* ---- MC decoders, generic over the bit source (hex nibbles in the batch path, bytes in the unit-op path) ----
  * Reason codes of a rejected frame; the host turns them into the reference's message strings. */
-#define SDB_MCR_NONE 0
-#define SDB_MCR_TOO_SHORT 1        /* 'message is too short' */
-#define SDB_MCR_TOO_LONG 2         /* 'message is too long' */
-#define SDB_MCR_WRONG_BEGIN 3      /* 'wrong bits at begin' */
-#define SDB_MCR_PARITY 4           /* 'parity error' */
-#define SDB_MCR_CHECKSUM 5         /* 'checksum error' */
-#define SDB_MCR_NO_START 6         /* '<name>: lib/mcBit2Sainlogic, start 010100 not found' */
-#define SDB_MCR_NOT_32 7           /* 'message must be 32 bits, got <n>' */
-#define SDB_MCR_NOT_56 8           /* 'message must be 56 bits, got <n>' */
-#define SDB_MCR_NO_SYNC 9          /* 'sync not found' */
-#define SDB_MCR_NO_DUP 10          /* ' no duplicate found' (+ SDB_MCR_DUP_SHORT / _LONG: ', message is too short/long') */
-#define SDB_MCR_LOOP 11            /* 'loop error, please report this data <bits>' */
-#define SDB_MCR_DUP_SHORT 0x100
-#define SDB_MCR_DUP_LONG 0x200
-#define SDB_MCR_DUP_NOPROTO 0x400
+/* (SDB_MCR_* reason codes: include/sdb200.h) */
 
 /* bit string given as one byte per bit (unit-op path: mcBit2*(name, bit_data, protocol_id, mcbitnum)) */
 struct ByteBits {
@@ -306,20 +292,21 @@ __device__ int mc_decode(const SdbHexProto &p, const Bits &B, int mcbitnum, Res 
 /* ---- MC batch path: returns SDB_ST_* ------------------------------------------------------- */
 __device__ int mc_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMsg &m)
 {
+    /* mo.reason = why the message was rejected (SDB_MCR_*; _demodulate_mc_data returns that text, manchester.py:70-128) */
     const SdbHexProto p = A.tab.hex[m.proto];
     const int mcbitnum = m.bitlen;
     const int lmin = (p.flags & SDB_HF_HAS_MIN) ? p.length_min : -1;     /* manchester.py:70-79 */
-    if (mcbitnum < lmin) return SDB_ST_OK;
+    if (mcbitnum < lmin) { mo.reason = SDB_MCR_TOO_SHORT; return SDB_ST_OK; }
     const int lmax = (p.flags & SDB_HF_HAS_MAX) ? p.length_max : 9999;
-    if (mcbitnum > lmax) return SDB_ST_OK;
+    if (mcbitnum > lmax) { mo.reason = SDB_MCR_TOO_LONG; return SDB_ST_OK; }
     if (p.flags & SDB_HF_CLOCKRANGE) {                                   /* :81-86 */
         if (!A.repaired) return SDB_ST_TYPEERROR;                        /* int > list */
-        if (!(m.clock > p.clock_min && m.clock < p.clock_max)) return SDB_ST_OK;
+        if (!(m.clock > p.clock_min && m.clock < p.clock_max)) { mo.reason = SDB_MCR_CLOCK; return SDB_ST_OK; }
     }
     bool inv = (p.flags & SDB_HF_INVERT) != 0;                           /* :91-96 */
     if (m.flags & SDB_HEX_TOGGLE_POLARITY) inv = !inv;
-    if (p.method == SDB_M_NONE) return SDB_ST_VALUEERROR;                /* :109 1-list cannot unpack into 3 */
-    if (p.method == SDB_M_UNKNOWN) return SDB_ST_OK;                     /* :121-123 */
+    if (p.method == SDB_M_NONE) { mo.reason = SDB_MCR_NO_METHOD; return SDB_ST_VALUEERROR; }   /* :109 1-list cannot unpack into 3 */
+    if (p.method == SDB_M_UNKNOWN) { mo.reason = SDB_MCR_UNKNOWN_METHOD; return SDB_ST_OK; }  /* :121-123 */
     if (m.hlen == 0) return SDB_ST_TYPEERROR;                            /* hex_to_bin_str('') is None -> len(None) */
     if (!A.repaired) return SDB_ST_TYPEERROR;                            /* :120 self passed twice */
     if (p.method >= SDB_M_BRESSER_LIGHTNING) return SDB_ST_TYPEERROR;    /* Conv*(msg_data, msg_type) called with 4 args */
@@ -334,7 +321,12 @@ __device__ int mc_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMs
     int reason;
     const int rc = mc_decode(p, B, B.n, R, T, reason);                   /* :120 mcbitnum = len(bit_data) */
     if (rc <= -100) return -rc - 100;
-    if (rc != 1) return SDB_ST_OK;
+    if (rc != 1) {
+        int r8 = reason & 0xFF;                                          /* the TFA suffix flags fold into codes 12..14 */
+        if (reason & SDB_MCR_DUP_SHORT) r8 = 12; else if (reason & SDB_MCR_DUP_LONG) r8 = 13; else if (reason & SDB_MCR_DUP_NOPROTO) r8 = 14;
+        mo.reason = (uint8_t)r8;
+        return SDB_ST_OK;
+    }
     if (p.method == SDB_M_TFA) {
         uint32_t hb = atomicAdd(&A.ctr->hits, (uint32_t)T.n);
         mo.hit_off = hb; mo.nhits = (uint16_t)T.n;
@@ -514,11 +506,14 @@ __global__ void __launch_bounds__(SDB_HEX_THREADS) hex_kernel(HArgs A)
     for (uint32_t mi = blockIdx.x * blockDim.x + threadIdx.x; mi < A.n; mi += stride) {
         const SdbHexMsg m = A.msgs[mi];
         SdbMsgOut mo;
-        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
-        if ((m.flags & SDB_MSG_VALID) && m.proto < A.tab.nproto && m.hlen <= SDB_MAX_HEX) {
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
+        if ((m.flags & SDB_MSG_DOMAIN) || ((m.flags & SDB_MSG_VALID) && m.hlen > SDB_MAX_HEX)) {
+            mo.status = SDB_ST_DOMAIN;                      /* not representable: reported, never decoded differently */
+            atomicAdd(&A.ctr->domain, 1u);
+        } else if ((m.flags & SDB_MSG_VALID) && m.proto < A.tab.nproto) {
             int st = A.kind == SDB_KIND_MC ? mc_one(A, mo, mi, m) : mn_one(A, mo, mi, m);
             if (st != SDB_ST_OK) {
-                mo.status = (uint8_t)st; mo.nhits = 0;
+                mo.status = (uint8_t)st; mo.nhits = 0;        /* (mo.reason keeps SDB_MCR_NO_METHOD: the direct call returns a list there) */
                 atomicAdd(&A.ctr->raised, 1u);
             }
         }

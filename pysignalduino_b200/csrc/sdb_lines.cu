@@ -23,8 +23,10 @@
  *
  * Exactness: the device accepts the canonical grammar the firmware emits (keys D, CP, SP, R, P<d> with
  * values -?[0-9]{1,10}); every line outside it (non-ASCII bytes, duplicate or multi-digit pattern ids in MS,
- * values float() parses differently, D longer than 1024 digits, more than 32 fields, longer than 1280 bytes) is
- * flagged SDB_LINE_HOSTPATH and goes through the host packer (pack.py), never decoded differently.
+ * values float() parses differently, D longer than SDB_MAX_DIGITS digits, more than 32 fields, longer than LN_LONG_MAX
+ * bytes) is flagged SDB_LINE_HOSTPATH and goes through the host packer (pack.py), never decoded differently.
+ * Lines longer than LN_MAX bytes (D of more than ~1000 digits) are listed by the first pass and tokenized by a second
+ * instantiation of the same kernel with a 4.6 KB staging buffer per warp (2 warps per CTA; exits at once when the list is empty).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,8 +37,10 @@
 namespace sdb {
 
 #define FULL 0xffffffffu
-#define LN_MAX 1280                              /* staged bytes per line; longer lines take the host path */
+#define LN_MAX 1280                              /* staged bytes per line in the first pass */
 #define LN_WARPS 8
+#define LN_LONG_MAX (SDB_MAX_DIGITS + 512)       /* second pass (listed long lines); longer lines take the host path */
+#define LN_LONG_WARPS 2
 
 struct LArgs {
     const uint8_t *text;
@@ -46,10 +50,13 @@ struct LArgs {
     SdbPulseMsg *msgs;
     uint8_t *pool;            /* digit pool, ((text_len >> 5) + n + 4) * 16 bytes */
     SdbLineInfo *info;
+    uint32_t *long_list;      /* lines of this launch with LN_MAX < len <= LN_LONG_MAX (first pass -> second pass) */
+    uint32_t *long_cnt;       /* [0] list length, [1] the second pass's work counter */
 };
 
+template <int LNMAX>
 struct __align__(16) LineSm {
-    uint8_t  buf[LN_MAX + 48];                   /* the line, at the same 16-byte phase as in global memory */
+    uint8_t  buf[LNMAX + 48];                    /* the line, at the same 16-byte phase as in global memory */
     uint16_t fend[33];                           /* position of the ';' that ends field k */
     uint32_t rec[12];                            /* SdbPulseMsg being assembled */
 };
@@ -120,16 +127,24 @@ __device__ __forceinline__ int classify(const uint8_t *s, int a, int b, int &va,
     return F_IGNORE;
 }
 
-template <bool MU>
-__global__ void __launch_bounds__(LN_WARPS * 32) tokenize_kernel(LArgs A)
+template <bool MU, int LNMAX, int NW>
+__global__ void __launch_bounds__(NW * 32) tokenize_kernel(LArgs A)
 {
-    __shared__ LineSm g_ls[LN_WARPS];
-    LineSm &sm = g_ls[threadIdx.x >> 5];
+    constexpr bool LONG = LNMAX > LN_MAX;
+    __shared__ LineSm<LNMAX> g_ls[NW];
+    LineSm<LNMAX> &sm = g_ls[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    for (uint32_t li = wid; li < A.n; li += warps) {
+    for (uint32_t it = wid;; it += warps) {
+        uint32_t li = it;
+        if (LONG) {                               /* second pass: draw from the list the first pass wrote */
+            uint32_t t = 0;
+            if (lane == 0) { t = atomicAdd(&A.long_cnt[1], 1u); t = t < A.long_cnt[0] ? A.long_list[t] : 0xFFFFFFFFu; }
+            li = __shfl_sync(FULL, t, 0);
+            if (li == 0xFFFFFFFFu) break;
+        } else if (li >= A.n) break;
         const uint32_t off = A.line_off[li];
         const int len = (int)A.line_len[li];
         const uint32_t unit = (off >> 5) + A.base + li;
@@ -140,8 +155,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) tokenize_kernel(LArgs A)
         int r_off = 0, r_len = 0, has_r = 0;
         __syncwarp();
 
-        if (len > LN_MAX) status = SDB_LINE_HOSTPATH;
-        else if (len > 0) {
+        if (len > LNMAX) {
+            status = SDB_LINE_HOSTPATH;
+            if (!LONG && len <= LN_LONG_MAX) {    /* the second pass tokenizes it (and overwrites what is written below) */
+                if (lane == 0) A.long_list[atomicAdd(&A.long_cnt[0], 1u)] = li;
+            }
+        } else if (len > 0) {
             /* 1. stage (16-byte loads from the aligned address below the line start) */
             const uint32_t ph = off & 15u;
             const uint4 *src = reinterpret_cast<const uint4 *>(A.text + (off - ph));
@@ -299,16 +318,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) tokenize_kernel(LArgs A)
 size_t lines_pool_bytes(size_t text_len, uint32_t n) { return ((text_len >> 5) + (size_t)n + 4) * 16; }
 
 int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n, uint32_t base,
-                    SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, int sm_count, cudaStream_t stream)
+                    SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, uint32_t *d_long, int sm_count, cudaStream_t stream)
 {
     if (n == 0) return 0;
     LArgs A;
     A.text = d_text; A.line_off = d_off; A.line_len = d_len; A.n = n; A.base = base; A.msgs = d_msgs; A.pool = d_pool; A.info = d_info;
+    A.long_list = d_long + 2; A.long_cnt = d_long;
+    cudaError_t e = cudaMemsetAsync(d_long, 0, 2 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return (int)e;
     uint32_t need = (n + LN_WARPS - 1) / LN_WARPS;
     uint32_t grid = (uint32_t)sm_count * 8;
     if (need < grid) grid = need;
-    if (kind == SDB_KIND_MU) tokenize_kernel<true><<<grid, LN_WARPS * 32, 0, stream>>>(A);
-    else tokenize_kernel<false><<<grid, LN_WARPS * 32, 0, stream>>>(A);
+    const uint32_t grid_long = (uint32_t)sm_count * 4;
+    if (kind == SDB_KIND_MU) {
+        tokenize_kernel<true, LN_MAX, LN_WARPS><<<grid, LN_WARPS * 32, 0, stream>>>(A);
+        tokenize_kernel<true, LN_LONG_MAX, LN_LONG_WARPS><<<grid_long, LN_LONG_WARPS * 32, 0, stream>>>(A);
+    } else {
+        tokenize_kernel<false, LN_MAX, LN_WARPS><<<grid, LN_WARPS * 32, 0, stream>>>(A);
+        tokenize_kernel<false, LN_LONG_MAX, LN_LONG_WARPS><<<grid_long, LN_LONG_WARPS * 32, 0, stream>>>(A);
+    }
     return (int)cudaGetLastError();
 }
 

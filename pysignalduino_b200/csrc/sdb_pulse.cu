@@ -39,15 +39,45 @@
 #include "sdb_postdemod.cuh"
 #include "sdb_pulse.h"
 
-namespace sdb {
+/*
+ * This file is compiled TWICE:
+ *   sdb_pulse.cu       namespace sdb       the fast kernels: D <= SDB_FAST_DIGITS (1024) digits staged per warp, 8 warps / CTA
+ *   sdb_pulse_long.cu  namespace sdb_long  (#define SDB_PULSE_LONG + #include of this file) the same code sized for
+ *                                          D <= SDB_MAX_DIGITS (4096): 2 warps / CTA, resolve + fused scan only
+ * The fast resolve kernel appends every message longer than SDB_FAST_DIGITS to a per-launch list; the long kernels
+ * (tiny persistent grids that exit at once when the list is empty) decode exactly those, so the reference's "no length
+ * limit on D" (message_unsynced.py:22-25) holds up to the firmware-scale cap without taxing the common case.
+ */
+#ifdef SDB_PULSE_LONG
+#define KNS sdb_long
+#define KMAXD SDB_MAX_DIGITS
+#define KTHREADS SDB_LONG_THREADS
+#define KMIN_CTAS 1
+#define POS_BITS 13                   /* p <= 4095, n <= 4096 */
+#else
+#define KNS sdb
+#define KMAXD SDB_FAST_DIGITS
+#define KTHREADS SDB_PULSE_THREADS
+#define KMIN_CTAS SDB_PULSE_MIN_CTAS
+#define POS_BITS 11                   /* p <= 1023, n <= 1024 */
+#endif
+#define POS_MASK ((1u << POS_BITS) - 1u)
+/* SdbSurv.meta: bits 0..12 where the scanned text begins (s0 / message_start), bit 15: `float` resolved */
+#define SURV_POS_MASK 0x1FFFu
+#define SURV_HASF 0x8000u
+
+namespace KNS {
+#ifdef SDB_PULSE_LONG
+using sdb::gbit; using sdb::sbit; using sdb::postdemod;      /* sdb_postdemod.cuh lives in namespace sdb */
+#endif
 
 #define FULL 0xffffffffu
-#define DIG_WORDS (SDB_MAX_DIGITS / 8 + 4)
-#define BIT_WORDS (SDB_MAX_DIGITS / 32 + 4)
+#define DIG_WORDS (KMAXD / 8 + 4)
+#define BIT_WORDS (KMAXD / 32 + 4)
 #define ST_HITS 24
 #define ST_WORDS 112
 #define NONE32 0xffffffffu
-#define WARPS (SDB_PULSE_THREADS / 32)
+#define WARPS (KTHREADS / 32)
 
 /* compute-sanitizer is not available on the GPU pool, so the library can be built with its own bounds checks
  * (-DSDB_BOUNDS_CHECK, python -m pysignalduino_b200.build_ext --check): every data-dependent shared-memory index
@@ -66,7 +96,7 @@ __device__ __forceinline__ int sdb_chk_idx(int i, int n) { if ((unsigned)i >= (u
 struct __align__(16) SdbSurv {
     uint64_t start;        /* bits 0..55: id string of `start` (nibble-packed), bits 56..63: MU table row */
     uint16_t c1, c0, cf;   /* id strings of one / zero / float (<= 4 digits) */
-    uint16_t meta;         /* bits 0..10: s0 (where D' begins), bit 11: float resolved */
+    uint16_t meta;         /* SURV_POS_MASK: s0 (where D' begins), SURV_HASF: float resolved */
 };
 
 struct KArgs {
@@ -86,6 +116,8 @@ struct KArgs {
     uint32_t *match_cnt;       /* MU: records per message, or MU_MARK = left to the fused fallback kernel */
     uint32_t *ticket;          /* this launch's work counter (zeroed before the chunk): warps draw messages ticket_batch at a time */
     uint32_t ticket_batch;
+    uint32_t *long_list;       /* messages of this launch with SDB_FAST_DIGITS < dlen <= SDB_MAX_DIGITS (fast resolve -> long kernels) */
+    uint32_t *long_cnt;
 };
 
 /* Messages differ a lot in cost (dlen 20..1024, 0..129 survivors), so a static message -> warp map leaves a tail at the
@@ -93,6 +125,19 @@ struct KArgs {
  * their next messages from a per-launch counter. */
 __device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uint32_t &left, uint32_t &mi)
 {
+#ifdef SDB_PULSE_LONG
+    /* the long kernels draw from the list the fast resolve kernel wrote (complete: stream order) */
+    (void)left;
+    uint32_t b = 0;
+    if ((threadIdx.x & 31) == 0) {
+        b = atomicAdd(A.ticket, 1u);
+        b = b < *A.long_cnt ? A.long_list[b] : 0xFFFFFFFFu;
+    }
+    base = __shfl_sync(0xffffffffu, b, 0);
+    if (base == 0xFFFFFFFFu) return false;
+    mi = base;
+    return true;
+#else
     if (!left) {
         uint32_t b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(A.ticket, A.ticket_batch);
@@ -103,12 +148,27 @@ __device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uin
     mi = base++;
     left--;
     return true;
+#endif
+}
+
+/* A record the packed domain cannot represent (flagged by the packer, or malformed: > 8 slots, an id > 9, D longer than
+ * SDB_MAX_DIGITS): no hits and status SDB_ST_DOMAIN — reported per message, never decoded differently from the reference. */
+__device__ __forceinline__ bool msg_domain(const SdbPulseMsg *m)
+{
+    const uint32_t fl = m->flags;
+    if (fl & SDB_MSG_DOMAIN) return true;
+    if (!(fl & SDB_MSG_VALID)) return false;
+    if (m->dlen > SDB_MAX_DIGITS || m->npat > SDB_MAX_SLOTS) return true;
+    const uint32_t ids = m->pat_ids;
+    bool bad = false;
+    for (int s = 0; s < (int)m->npat; s++) bad |= ((ids >> (4 * s)) & 0xF) > 9;
+    return bad;
 }
 
 /* MU scan kernel: symbol / start bitmaps of the distinct id-string sets of up to 32 survivors */
 #define MU_NB 6                       /* symbol bitmap triples resident at a time             */
 #define MU_NS 6                       /* start bitmaps resident at a time                     */
-#define MU_BW 34                      /* words per bitmap: 1024 positions + 2 zero words      */
+#define MU_BW (KMAXD / 32 + 2)        /* words per bitmap: KMAXD positions + 2 zero words     */
 #define MU_K 4                        /* matches a lane records before the warp emits them    */
 #define MU_MCAP 64                    /* match records per message handed to the emit kernel  */
 #define MU_MARK 0xFFFFFFFFu           /* more than that: the fused fallback kernel takes the message */
@@ -206,32 +266,6 @@ __device__ __forceinline__ int tenths_fast(int p, double c, double inv10c)
         return (int)r;
     }
     return tenths(p, c);
-}
-
-/* X >> nb for a 1024-bit value spread little-endian over the warp (lane r = bits 32r..32r+31) */
-__device__ __noinline__ uint32_t shr_dist(uint32_t mine, int nb)
-{
-    int lane = lane_id();
-    int ws = nb >> 5, bs = nb & 31;
-    uint32_t a = __shfl_down_sync(FULL, mine, ws & 31);
-    uint32_t b = __shfl_down_sync(FULL, mine, (ws + 1) & 31);
-    if (lane + ws > 31) a = 0;
-    if (lane + ws + 1 > 31) b = 0;
-    return __funnelshift_r(a, b, bs);
-}
-
-/* first set bit at position >= pos of a distributed 1024-bit value, -1 if none */
-__device__ __noinline__ int first_set_from(uint32_t mine, int pos)
-{
-    int base = lane_id() * 32;
-    uint32_t w = mine;
-    if (base + 31 < pos) w = 0;
-    else if (base < pos) w &= FULL << (pos - base);
-    uint32_t nz = __ballot_sync(FULL, w != 0);
-    if (!nz) return -1;
-    int fl = __ffs(nz) - 1;
-    uint32_t wv = __shfl_sync(FULL, w, fl);
-    return fl * 32 + __ffs(wv) - 1;
 }
 
 /* ---- warp-cooperative substring search: first p >= from with D[p:p+L] == tgt, else -1 ------- */
@@ -484,7 +518,7 @@ __device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmIte
 }
 
 /* ---- hit sink: shared-memory staging, or direct global writes on the rare second pass ------ */
-__device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, int nb, bool has_f, int ordinal)
+__device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, int nb, bool has_f, int ordinal, bool mm_host)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -492,7 +526,7 @@ __device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, i
     const int nw = has_f ? 2 * nwv : nwv;
     SdbHit h;
     h.msg = sm.msg; h.proto = pp->proto; h.nbits = (uint16_t)nb; h.aux = (uint16_t)ordinal;
-    h.flags = has_f ? SDB_HIT_HAS_F : 0; h.rsv = 0;
+    h.flags = (has_f ? SDB_HIT_HAS_F : 0) | (mm_host ? SDB_HIT_MM_HOST : 0); h.rsv = 0;
     const uint32_t nh0 = sm.nh, nw0 = sm.nw;
     __syncwarp();
     if (!sm.direct) {
@@ -570,13 +604,15 @@ __device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp
     }
     if (!MS) nb = (nb + pad - 1) / pad * pad;     /* message_unsynced.py:257-259: pad AFTER postDemod */
 
+    bool mm_host = false;
     if (MS) {
         if (has_f) return SDB_ST_OK;              /* bin_str_2_hex_str -> None (:224-226) */
     } else {
         if (flags & SDB_PF_MM_NEVER) return SDB_ST_OK;
-        if (pp->mm_off != 0xFFFF && !modulematch(pp, A.tab.mm, nb, has_f)) return SDB_ST_OK;   /* :277-280 */
+        if (flags & SDB_PF_MM_HOST) mm_host = true;      /* a regex shape the program cannot express: the host formatter applies it */
+        else if (pp->mm_off != 0xFFFF && !modulematch(pp, A.tab.mm, nb, has_f)) return SDB_ST_OK;   /* :277-280 */
     }
-    emit_hit(A, pp, nb, has_f, ordinal);
+    emit_hit(A, pp, nb, has_f, ordinal, mm_host);
     return SDB_ST_OK;
 }
 
@@ -666,8 +702,30 @@ __device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint3
         }
     }
     __syncwarp();
-    /* "8 / 16 symbols in a row start here" by shifted-AND doubling on the words (lane j = word j; word 32 is all zero):
-     * the per-lane scans take their candidates from these, so the many short accidental runs cost nothing */
+    /* "8 / 16 symbols in a row start here" by shifted-AND doubling on the words: the per-lane scans take their candidates
+     * from these, so the many short accidental runs cost nothing */
+#ifdef SDB_PULSE_LONG
+    /* more words than lanes: the doubling runs in place on plane [2], block after block in ascending order (a word is
+     * combined with its still unmodified successor), plane [1] is the copy taken after the third level */
+    uint32_t *P1 = dst + MU_BW, *P2 = dst + 2 * MU_BW;
+    for (int j = lane; j < MU_BW; j += 32) P2[IDX(j, MU_BW)] = j <= nw + 1 ? dst[IDX(j, MU_BW)] : 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (int lv = 0; lv < 4; lv++) {
+        const int sh = w << lv;                                        /* w, 2w, 4w, 8w <= 32 */
+#pragma unroll 1
+        for (int b0 = 0; b0 < MU_BW; b0 += 32) {
+            const int j = b0 + lane;
+            uint32_t x = 0, nx = 0;
+            if (j < MU_BW) { x = P2[IDX(j, MU_BW)]; nx = j + 1 < MU_BW ? P2[IDX(j + 1, MU_BW)] : 0u; }
+            __syncwarp();
+            if (j < MU_BW) P2[IDX(j, MU_BW)] = x & (sh < 32 ? __funnelshift_r(x, nx, sh) : nx);
+            __syncwarp();
+        }
+        if (lv == 2) { for (int j = lane; j < MU_BW; j += 32) P1[IDX(j, MU_BW)] = P2[IDX(j, MU_BW)]; __syncwarp(); }
+    }
+#else
+    /* (lane j = word j; word 32 is all zero) */
     uint32_t x = lane <= nw + 1 ? dst[IDX(lane, MU_BW)] : 0u;
     uint32_t x8 = 0;
 #pragma unroll
@@ -682,6 +740,7 @@ __device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint3
     dst[IDX(2 * MU_BW + lane, 3 * MU_BW)] = x;
     if (lane < 2) { dst[IDX(MU_BW + 32 + lane, 3 * MU_BW)] = 0; dst[IDX(2 * MU_BW + 32 + lane, 3 * MU_BW)] = 0; }
     __syncwarp();
+#endif
 }
 
 /* warp: bitmap of the occurrences of the Ls-digit start string -> dst[0 .. nw + 1] */
@@ -729,7 +788,7 @@ struct MuLane {
     int lw, Ls, MIN, lenmax;
     uint32_t flags;              /* 1 use_tail, 2 has0, 4 hasf, 8 done */
     int pos, status, nm;
-    uint32_t m0, m1, m2, m3;     /* recorded matches: p | n << 11 | (tail + 1) << 22 */
+    uint32_t m0, m1, m2, m3;     /* recorded matches: p | n << POS_BITS | (tail + 1) << 2 POS_BITS */
     uint64_t dead;               /* 16 bits per residue class of p: no run of >= MIN symbols starts before this position */
     uint64_t cand;               /* 16 bits per residue class of p: cached next candidate i + 1 (0 unknown, 0xFFFF none) */
 };
@@ -805,7 +864,7 @@ __device__ __forceinline__ void mu_step(const uint32_t *dig, MuLane &L, int nwB)
     const int nch = n + (tail >= 0 ? 1 : 0);
     if (nch == 0) { L.status = SDB_ST_INDEXERROR; L.flags |= MU_F_DONE; return; }   /* :212 chunks[-1] on an empty capture */
     if (L.lenmax >= 0 && nch > L.lenmax) return;                        /* :217 */
-    const uint32_t rec = (uint32_t)p | ((uint32_t)n << 11) | ((uint32_t)(tail + 1) << 22);
+    const uint32_t rec = (uint32_t)p | ((uint32_t)n << POS_BITS) | ((uint32_t)(tail + 1) << (2 * POS_BITS));
     if (L.nm == 0) L.m0 = rec; else if (L.nm == 1) L.m1 = rec; else if (L.nm == 2) L.m2 = rec; else L.m3 = rec;
     L.nm++;
 }
@@ -819,7 +878,7 @@ __device__ __noinline__ int mu_emit_match(const KArgs &A, const SdbPulseProto *p
     const int w = pp->width;
     const bool has0 = pp->key[2].len != 0;
     const uint32_t wm = nibmask32(w);
-    const int p = rec & 0x7FF, n = (rec >> 11) & 0x7FF, tail = (int)(rec >> 22) - 1;
+    const int p = rec & POS_MASK, n = (rec >> POS_BITS) & POS_MASK, tail = (int)(rec >> (2 * POS_BITS)) - 1;
     __syncwarp();
 #pragma unroll 1
     for (int b0 = 0; b0 < n; b0 += 32) {
@@ -879,7 +938,7 @@ __device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slo
             w = pp->width;
             L.lw = w == 1 ? 0 : (w == 2 ? 1 : 2);
             L.Ls = pp->key[0].len;
-            const bool has0 = pp->key[2].len != 0, hasf = (mine.meta & 0x800) != 0;
+            const bool has0 = pp->key[2].len != 0, hasf = (mine.meta & SURV_HASF) != 0;
             L.c1 = mine.c1; L.c0 = has0 ? mine.c0 : mine.c1; L.cf = hasf ? mine.cf : mine.c1;
             L.MIN = pp->regex_min; L.lenmax = pp->mu_len_max;
             /* w == 1: the tail key is '' and matches nothing extra */
@@ -889,7 +948,7 @@ __device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slo
         }
         L.sym = 0;
         L.B = nullptr; L.Bx = nullptr; L.S = nullptr;
-        L.pos = mine.meta & 0x7FF; L.status = SDB_ST_OK; L.nm = 0; L.m0 = L.m1 = L.m2 = L.m3 = 0;
+        L.pos = mine.meta & SURV_POS_MASK; L.status = SDB_ST_OK; L.nm = 0; L.m0 = L.m1 = L.m2 = L.m3 = 0;
         L.dead = 0; L.cand = 0;
         int ordbase = 0;
         const uint64_t keyB = mu_sort3_key(L.c1, L.c0, L.cf, w);
@@ -1272,10 +1331,14 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
     const int lane = lane_id();
     const uint4 *src = reinterpret_cast<const uint4 *>(A.digits + (size_t)m->doff * 16);
     const int nq = (dlen + 31) >> 5;               /* 16-byte units */
+#ifdef SDB_PULSE_LONG
+    for (int q = lane; q < nq; q += 32) reinterpret_cast<uint4 *>(sm.dig)[q] = __ldg(&src[q]);
+#else
     if (lane < nq) {
         uint4 v = __ldg(&src[lane]);
         reinterpret_cast<uint4 *>(sm.dig)[lane] = v;
     }
+#endif
     if (lane < 4) sm.dig[IDX(4 * nq + lane, DIG_WORDS)] = FULL;    /* windows may read 3 words past the last digit */
     if (lane < 8) sm.pat[lane] = m->pat[lane];
     if (lane == 0) {
@@ -1342,7 +1405,7 @@ __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &r
     if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, s0, false, tf, dummy);
     rec.start = start_t;
     rec.c1 = (uint16_t)t1; rec.c0 = (uint16_t)t0; rec.cf = (uint16_t)tf;
-    rec.meta = (uint16_t)(s0 | (hasf ? 0x800 : 0));
+    rec.meta = (uint16_t)(s0 | (hasf ? SURV_HASF : 0));
     return true;
 }
 
@@ -1363,7 +1426,7 @@ __device__ __noinline__ bool resolve_ms_warp(const SdbPulseProto *pp, SdbSurv &r
     if (pp->key[3].len) hasf = resolve_key(&pp->key[3], t_slot, 0, false, tf, dummy);
     rec.start = ts;
     rec.c1 = (uint16_t)t1; rec.c0 = (uint16_t)t0; rec.cf = (uint16_t)tf;
-    rec.meta = (uint16_t)(ms | (hasf ? 0x800 : 0));
+    rec.meta = (uint16_t)(ms | (hasf ? SURV_HASF : 0));
     return true;
 }
 
@@ -1432,7 +1495,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
 }
 
 template <bool MS>
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1447,7 +1510,13 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
         /* records outside the packed domain (ids > 9, > 8 slots, D too long) yield no hits instead of undefined lookups */
         const bool ids_ok = m->npat <= SDB_MAX_SLOTS &&
                             !__any_sync(FULL, lane < m->npat && ((m->pat_ids >> (4 * (lane & 7))) & 0xF) > 9);
-        if ((m->flags & SDB_MSG_VALID) && dlen > 0 && dlen <= SDB_MAX_DIGITS && ids_ok) {
+        const bool decodable = (m->flags & SDB_MSG_VALID) && !(m->flags & SDB_MSG_DOMAIN) && dlen > 0 && dlen <= SDB_MAX_DIGITS && ids_ok;
+#ifndef SDB_PULSE_LONG
+        if (decodable && dlen > KMAXD) {               /* too long for this kernel's staging: the long kernels take it */
+            if (lane == 0) A.long_list[atomicAdd(A.long_cnt, 1u)] = mi;
+        } else
+#endif
+        if (decodable) {
             stage_message(A, sm, m, dlen, mi);
             double clock_abs = 0.0;
             if (prepare_tables<MS>(A, sm, m, clock_abs)) {
@@ -1490,7 +1559,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) resolve
                             state = MS ? thread_resolve_ms(pq, sm, codes, sf) : thread_resolve_mu(pq, sm, codes, sf, pass == 1, s0w);
                             rec.start = pass == 1 ? long_start : (uint64_t)(codes & 0xFF);
                             rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
-                            rec.meta = (uint16_t)((sf & 0x7FF) | ((sf >> 16) ? 0x800 : 0));
+                            rec.meta = (uint16_t)((sf & SURV_POS_MASK) | ((sf >> 16) ? SURV_HASF : 0));
                         }
                         if (pass == 1) break;
                         /* the few protocols that need warp-wide searches are resolved one after the other: an MU protocol with
@@ -1549,8 +1618,8 @@ __device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots,
             const uint32_t cfm = __shfl_sync(FULL, (uint32_t)mine.cf | ((uint32_t)mine.meta << 16), k);
             const SdbPulseProto *pp = &rows[shi >> 24];
             const uint64_t start_t = (((uint64_t)(shi & 0x00FFFFFFu)) << 32) | slo;
-            const int pos0 = (int)((cfm >> 16) & 0x7FF);
-            const bool hasf = ((cfm >> 16) & 0x800) != 0;
+            const int pos0 = (int)((cfm >> 16) & SURV_POS_MASK);
+            const bool hasf = ((cfm >> 16) & SURV_HASF) != 0;
             const int st = scan_ms(A, pp, pos0, (uint32_t)start_t, c10 & 0xFFFF, c10 >> 16, cfm & 0xFFFF, hasf);
             if (st != SDB_ST_OK) return st;
         }
@@ -1559,7 +1628,7 @@ __device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots,
 }
 
 template <bool MS>
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1568,9 +1637,15 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
     while (next_message(A, tk_base, tk_left, mi)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         SdbMsgOut mo;
-        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
+#ifndef SDB_PULSE_LONG
         if (!MS && A.match_cnt[mi] != MU_MARK) continue;         /* MU: only what the match kernel could not hand over */
+#endif
         const uint32_t nsurv = A.surv_cnt[mi];
+        if (MS && nsurv == 0 && msg_domain(m)) {                 /* (a record outside the domain never has survivors) */
+            mo.status = SDB_ST_DOMAIN;
+            if (lane == 0) atomicAdd(&A.ctr->domain, 1u);
+        }
         if (nsurv) {
             const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
             stage_digits(A, sm, m, m->dlen, mi);
@@ -1613,8 +1688,9 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) scan_ke
     }
 }
 
+#ifndef SDB_PULSE_LONG
 /* MU, kernel 2 of 3: every survivor's regex matches -> match records (message_unsynced.py:146-217) */
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_match_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_match_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1637,7 +1713,8 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_matc
                 A.match_cnt[mi] = raised ? 0u : nrec;
                 if (raised || nrec == 0) {                       /* nothing left to do for the emit kernel */
                     SdbMsgOut mo;
-                    mo.hit_off = 0; mo.nhits = 0; mo.status = (uint8_t)status; mo.rsv = 0;
+                    mo.hit_off = 0; mo.nhits = 0; mo.status = (uint8_t)status; mo.reason = 0;
+                    if (nsurv == 0 && msg_domain(m)) { mo.status = SDB_ST_DOMAIN; atomicAdd(&A.ctr->domain, 1u); }
                     A.out[mi] = mo;
                     if (raised) atomicAdd(&A.ctr->raised, 1u);   /* exception: earlier hits are lost */
                 }
@@ -1667,7 +1744,7 @@ __device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slot
             const uint32_t c10 = __shfl_sync(FULL, (uint32_t)sv.c1 | ((uint32_t)sv.c0 << 16), k);
             const uint32_t cfm = __shfl_sync(FULL, (uint32_t)sv.cf | ((uint32_t)sv.meta << 16), k);
             const SdbPulseProto *pp = &A.tab.mu[row];
-            const bool has0 = pp->key[2].len != 0, hasf = ((cfm >> 16) & 0x800) != 0;
+            const bool has0 = pp->key[2].len != 0, hasf = ((cfm >> 16) & SURV_HASF) != 0;
             const uint32_t c1 = c10 & 0xFFFF, c0 = has0 ? c10 >> 16 : c1, cf = hasf ? cfm & 0xFFFF : c1;
             const int si = (int)(rk >> 24);
             ordinal = si == prev ? ordinal + 1 : 0;                   /* records of one survivor are consecutive, in match order */
@@ -1678,7 +1755,7 @@ __device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slot
 }
 
 /* MU, kernel 3 of 3: match records -> hits (message_unsynced.py:220-290) */
-__global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_emit_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_emit_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1691,7 +1768,7 @@ __global__ void __launch_bounds__(SDB_PULSE_THREADS, SDB_PULSE_MIN_CTAS) mu_emit
         const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
         const uint32_t *recs = A.match + (size_t)mi * MU_MCAP;
         SdbMsgOut mo;
-        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.rsv = 0;
+        mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
         stage_digits(A, sm, m, m->dlen, mi);
         mu_emit_records(A, slots, recs, nrec);
         __syncwarp();
@@ -1748,15 +1825,17 @@ size_t mu_scratch_bytes(uint32_t stride, uint32_t chunk)
 {
     return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t)        /* survivor slots + counts */
            + (size_t)chunk * MU_MCAP * sizeof(uint32_t) + (size_t)chunk * sizeof(uint32_t)    /* MU match records + counts */
-           + 64;                                                                              /* work counters */
+           + 64                                                                               /* 16 work counters */
+           + (size_t)chunk * sizeof(uint32_t);                                                /* list of long messages */
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
+#define UNIT_WORDS (SDB_MAX_DIGITS / 32 + 8)
 __global__ void unit_postdemod_kernel(int method, const uint8_t *in, uint32_t n_in, uint8_t *out, uint32_t out_cap, int32_t *res)
 {
-    __shared__ uint32_t a[BIT_WORDS * 2], b[BIT_WORDS * 2];
+    __shared__ uint32_t a[UNIT_WORDS], b[UNIT_WORDS];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < BIT_WORDS * 2; i++) { a[i] = 0; b[i] = 0; }
+        for (int i = 0; i < UNIT_WORDS; i++) { a[i] = 0; b[i] = 0; }
         for (uint32_t i = 0; i < n_in; i++) sbit(a, (int)i, in[i] & 1);
         int no = 0;
         int rc = postdemod(method, a, (int)n_in, b, &no);
@@ -1767,7 +1846,7 @@ __global__ void unit_postdemod_kernel(int method, const uint8_t *in, uint32_t n_
 int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_t *d_out, uint32_t out_cap,
                           int32_t *d_res, cudaStream_t stream)
 {
-    if (n_in > (uint32_t)(BIT_WORDS * 32)) return -1;
+    if (n_in > (uint32_t)SDB_MAX_DIGITS) return -1;
     unit_postdemod_kernel<<<1, 32, 0, stream>>>(method, d_in, n_in, d_out, out_cap, d_res);
     return (int)cudaGetLastError();
 }
@@ -1778,7 +1857,7 @@ unsigned int debug_violations(bool reset)
     unsigned int v = 0, z = 0;
     cudaMemcpyFromSymbol(&v, g_sdb_oob, sizeof v);
     if (reset) cudaMemcpyToSymbol(g_sdb_oob, &z, sizeof z);
-    return v;
+    return v + sdb_long::debug_violations_long(reset);
 #else
     (void)reset;
     return 0xFFFFFFFFu;      /* not a checked build */
@@ -1787,7 +1866,7 @@ unsigned int debug_violations(bool reset)
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream)
+                 SdbCounters *d_ctr, int grid, int grid_long, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream)
 {
     KArgs A;
     A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
@@ -1803,14 +1882,16 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
     A.surv_stride = ms ? tab.n_ms : tab.n_mu;
     A.match = A.surv_cnt + mu_chunk;
     A.match_cnt = A.match + (size_t)mu_chunk * MU_MCAP;
-    uint32_t *tickets = A.match_cnt + mu_chunk;                    /* 8 work counters, zeroed per chunk */
+    uint32_t *tickets = A.match_cnt + mu_chunk;                    /* 16 work counters, zeroed per chunk: [0..3] fast kernels, [4..5] long kernels, [6] long-list length */
+    A.long_list = tickets + 16;
+    A.long_cnt = tickets + 6;
     for (uint32_t off = 0; off < n; off += mu_chunk) {
         A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
         A.n = n - off < mu_chunk ? n - off : mu_chunk;
         uint32_t need = (A.n + wpc - 1) / wpc;
         int g = need < (uint32_t)grid ? (int)need : grid;
         A.ticket_batch = ms ? 4 * SDB_TICKET_BATCH : SDB_TICKET_BATCH;   /* MS messages are ~10x cheaper; the fallback kernel skips nearly everything: 256 */
-        cudaError_t e = cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), stream);
+        cudaError_t e = cudaMemsetAsync(tickets, 0, 16 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return (int)e;
         if (ms) {
             A.ticket = tickets + 0; resolve_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
@@ -1821,8 +1902,97 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
             A.ticket = tickets + 2; mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
             A.ticket = tickets + 3; A.ticket_batch = 256; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
         }
+        /* messages with more than SDB_FAST_DIGITS digits (listed by the resolve kernel above; usually none) */
+        e = (cudaError_t)sdb_long::launch_long(kind, tab, A.msgs, d_digits, A.n, A.msg_base, A.out, d_hits, hits_cap, d_bits, bits_cap, d_ctr,
+                                               A.surv, A.surv_cnt, A.surv_stride, A.long_list, A.long_cnt, tickets + 4, grid_long, stream);
+        if (e != cudaSuccess) return (int)e;
     }
     return (int)cudaGetLastError();
 }
 
-}  // namespace sdb
+#else  /* SDB_PULSE_LONG */
+
+unsigned int debug_violations_long(bool reset)
+{
+#ifdef SDB_BOUNDS_CHECK
+    unsigned int v = 0, z = 0;
+    cudaMemcpyFromSymbol(&v, g_sdb_oob, sizeof v);
+    if (reset) cudaMemcpyToSymbol(g_sdb_oob, &z, sizeof z);
+    return v;
+#else
+    (void)reset;
+    return 0u;
+#endif
+}
+
+int long_blocks_per_sm()
+{
+    int a = 0, b = 0, c = 0, d = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, KTHREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, KTHREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false>, KTHREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, scan_kernel<false>, KTHREADS, 0);
+    int nb = a;
+    if (b < nb) nb = b;
+    if (c < nb) nb = c;
+    if (d < nb) nb = d;
+    return nb > 0 ? nb : 1;
+}
+
+/* unit op: pattern_exists (pattern_utils.py:34-136) for ONE template on ONE digit string — the warp-level resolver the
+ * kernels use (resolve_key / resolve_general / warp_find), behind the module-level pattern_utils.pattern_exists of the
+ * drop-in package.  res = {found, target digits 0..7, target digits 8..15, position of the first occurrence}. */
+__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) unit_pattern_kernel(SdbKeyTpl tpl, const uint16_t *rank, const int16_t *tenths,
+                                                                            uint32_t pat_ids, int npat, const uint8_t *digits, int dlen,
+                                                                            int32_t *res)
+{
+    if (threadIdx.x >= 32) return;
+    WarpSm &sm = SM();
+    const int lane = lane_id();
+    KArgs A;
+    A.digits = digits; A.tab.rank = rank; A.msg_base = 0;
+    __shared__ SdbPulseMsg m;
+    if (lane == 0) { m.doff = 0; m.dlen = (uint16_t)dlen; m.npat = (uint8_t)npat; m.cp = 0xFF; m.pat_ids = pat_ids; m.flags = SDB_MSG_VALID; }
+    if (lane < 8) m.pat[lane] = 0;
+    __syncwarp();
+    stage_message(A, sm, &m, dlen, 0);
+    const int t_slot = tenths[lane & 7];
+    uint64_t tgt = 0;
+    int pos = 0;
+    const SdbKeyTpl k = tpl;
+    const bool ok = resolve_key(&k, t_slot, 0, true, tgt, pos);
+    if (lane == 0) { res[0] = ok ? 1 : 0; res[1] = (int32_t)(uint32_t)tgt; res[2] = (int32_t)(uint32_t)(tgt >> 32); res[3] = pos; }
+}
+
+int launch_unit_pattern(const SdbKeyTpl &tpl, const uint16_t *d_rank, const int16_t *d_tenths, uint32_t pat_ids, int npat,
+                        const uint8_t *d_digits, int dlen, int32_t *d_res, cudaStream_t stream)
+{
+    if (dlen < 0 || dlen > SDB_MAX_DIGITS || npat < 0 || npat > SDB_MAX_SLOTS || tpl.len > SDB_MAX_TPL || tpl.nuniq > SDB_MAX_UNIQ) return -1;
+    unit_pattern_kernel<<<1, 32, 0, stream>>>(tpl, d_rank, d_tenths, pat_ids, npat, d_digits, dlen, d_res);
+    return (int)cudaGetLastError();
+}
+
+/* The messages the fast resolve kernel listed (SDB_FAST_DIGITS < dlen <= SDB_MAX_DIGITS): resolve + fused scan, sized for
+ * the long staging buffers.  Arguments are the fast launch's own (same chunk, same scratch); tickets = two zeroed counters. */
+int launch_long(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
+                uint32_t msg_base, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
+                SdbCounters *d_ctr, void *surv, uint32_t *surv_cnt, uint32_t surv_stride, uint32_t *long_list, uint32_t *long_cnt,
+                uint32_t *tickets, int grid, cudaStream_t stream)
+{
+    KArgs A;
+    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base; A.out = d_out;
+    A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
+    A.surv = static_cast<SdbSurv *>(surv); A.surv_cnt = surv_cnt; A.surv_stride = surv_stride;
+    A.match = nullptr; A.match_cnt = nullptr; A.ticket_batch = 1; A.long_list = long_list; A.long_cnt = long_cnt;
+    if (kind == SDB_KIND_MS) {
+        A.ticket = tickets + 0; resolve_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = tickets + 1; scan_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
+    } else {
+        A.ticket = tickets + 0; resolve_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = tickets + 1; scan_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
+    }
+    return (int)cudaGetLastError();
+}
+#endif /* SDB_PULSE_LONG */
+
+}  // namespace KNS

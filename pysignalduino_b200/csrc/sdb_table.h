@@ -22,6 +22,7 @@
 #define SDB_PF_MM_END       0x08
 #define SDB_PF_MM_NEVER     0x10
 #define SDB_PF_HAS_LIR_MAX  0x20
+#define SDB_PF_MM_HOST      0x40   /* modulematch outside the device program's shapes: hits carry SDB_HIT_MM_HOST */
 
 /* postDemodulation ids (sd_protocols/postdemodulation.py) */
 #define SDB_PD_EM 1

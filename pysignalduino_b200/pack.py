@@ -9,8 +9,10 @@ Layout (include/sdb200.h): ``SdbPulseMsg`` 48 B/message + a nibble-packed digit 
 per-message streams start on 16-byte boundaries and are padded with 0xF nibbles.
 
 Inputs the packed domain cannot represent (non-integer pulse values, pattern ids >= 10,
-more than 8 pattern slots, D longer than SDB_MAX_DIGITS) raise :class:`DomainError`;
-they are never silently decoded differently from the reference.
+more than 8 pattern slots, D longer than SDB_MAX_DIGITS = 4096) are marked PER MESSAGE
+(``SDB_MSG_DOMAIN`` -> status ``"DomainError"``, reason in ``batch.domain``): the rest of the
+batch is decoded normally, and such a message is never silently decoded differently from the
+reference.  ``strict=True`` raises :class:`DomainError` at the first one instead.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 MAX_SLOTS = 8
-MAX_DIGITS = 1024
+MAX_DIGITS = 4096        # SDB_MAX_DIGITS: the fast kernels stage 1024 digits, longer messages take the long kernels
 MAX_HEX = 512
 DIGIT_OTHER = 0xE
 DIGIT_PAD = 0xF
@@ -29,6 +31,7 @@ KIND_BY_NAME = {"MS": KIND_MS, "MU": KIND_MU, "MC": KIND_MC, "MN": KIND_MN}
 
 MSG_VALID = 0x01
 HEX_TOGGLE_POLARITY = 0x02
+MSG_DOMAIN = 0x04
 
 PULSE_DTYPE = np.dtype(
     [
@@ -57,7 +60,7 @@ HEX_DTYPE = np.dtype(
 )
 assert HEX_DTYPE.itemsize == 16
 
-MSGOUT_DTYPE = np.dtype([("hit_off", "<u4"), ("nhits", "<u2"), ("status", "u1"), ("rsv", "u1")])
+MSGOUT_DTYPE = np.dtype([("hit_off", "<u4"), ("nhits", "<u2"), ("status", "u1"), ("reason", "u1")])
 HIT_DTYPE = np.dtype(
     [
         ("msg", "<u4"),
@@ -69,7 +72,7 @@ HIT_DTYPE = np.dtype(
         ("rsv", "u1"),
     ]
 )
-COUNTERS_DTYPE = np.dtype([("hits", "<u4"), ("words", "<u4"), ("raised", "<u4"), ("rsv", "<u4")])
+COUNTERS_DTYPE = np.dtype([("hits", "<u4"), ("words", "<u4"), ("raised", "<u4"), ("domain", "<u4")])
 assert MSGOUT_DTYPE.itemsize == 8 and HIT_DTYPE.itemsize == 16 and COUNTERS_DTYPE.itemsize == 16
 
 
@@ -123,15 +126,17 @@ def _ms_gates(msg_data: Dict[str, Any]) -> bool:
 class PulseBatch:
     """Packed MS or MU batch plus the host-only fields needed to format results."""
 
-    __slots__ = ("kind", "msgs", "digits", "rssi", "clock", "n")
+    __slots__ = ("kind", "msgs", "digits", "rssi", "clock", "n", "domain")
 
-    def __init__(self, kind: int, msgs: np.ndarray, digits: np.ndarray, rssi: List[Any], clock: np.ndarray):
+    def __init__(self, kind: int, msgs: np.ndarray, digits: np.ndarray, rssi: List[Any], clock: np.ndarray,
+                 domain: Optional[Dict[int, str]] = None):
         self.kind = kind
         self.msgs = msgs
         self.digits = digits
         self.rssi = rssi      # msg_data.get('R') per message (meta.rssi is the raw value)
         self.clock = clock    # MS: abs(P[CP]) per message (meta.clock); unused for MU
         self.n = len(msgs)
+        self.domain = domain or {}   # message index -> why it is outside the packed domain (status "DomainError")
 
     def algorithmic_input_bytes(self) -> int:
         """48 B header + ceil(dlen/2) digit bytes per message."""
@@ -158,17 +163,35 @@ _DIGIT_LUT_PAD = _DIGIT_LUT.copy()
 _DIGIT_LUT_PAD[0xFF] = DIGIT_PAD
 
 
-def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
+def _pulse_domain_reason(data, patterns: Dict[str, float]) -> Optional[str]:
+    """Why the packed record cannot hold this (gate-passing) message, or None."""
+    if not isinstance(data, str):
+        return "'data' must be a str"
+    if len(data) > MAX_DIGITS:
+        return f"D has {len(data)} digits (max {MAX_DIGITS})"
+    if len(patterns) > MAX_SLOTS:
+        return f"{len(patterns)} pattern slots (max {MAX_SLOTS})"
+    for pidx, val in patterns.items():
+        if len(pidx) != 1:
+            return f"pattern id {pidx!r} is not a single digit"
+        if val != val or val in (float("inf"), float("-inf")) or val != int(val) or abs(val) > 2147483647:
+            return f"pattern value {val!r} is not an int32"
+    return None
+
+
+def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int, strict: bool = False) -> PulseBatch:
     """Pack MS (kind 0) or MU (kind 1) parser dicts.
 
     One pass of plain-Python bookkeeping per message (dict lookups, list appends); every array operation — the digit
-    look-up, nibble packing, record fields — runs once over the whole batch."""
+    look-up, nibble packing, record fields — runs once over the whole batch.  A message outside the packed domain becomes
+    an SDB_MSG_DOMAIN record (status "DomainError" for that message only); ``strict`` raises instead."""
     n = len(msgs)
     rssi: List[Any] = []
     pats: List[int] = []            # 8 values per message
     meta: List[int] = []            # dlen, npat, cp, pat_ids, flags per message
     chunks: List[bytes] = []        # digit characters, each message padded to a multiple of 32 with 0xFF
     clock = np.zeros(n, dtype=np.float64)
+    domain: Dict[int, str] = {}
     zero8 = [0] * MAX_SLOTS
     is_ms = kind == KIND_MS
     for i, m in enumerate(msgs):
@@ -179,20 +202,23 @@ def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
             pats.extend(zero8)
             meta.extend((0, 0, 0xFF, 0, 0))
             continue
-        if not isinstance(data, str):
-            raise DomainError(f"message {i}: 'data' must be a str")
-        if len(data) > MAX_DIGITS:
-            raise DomainError(f"message {i}: D has {len(data)} digits (max {MAX_DIGITS})")
         patterns = parse_patterns(m)
-        if len(patterns) > MAX_SLOTS:
-            raise DomainError(f"message {i}: {len(patterns)} pattern slots (max {MAX_SLOTS})")
+        why = _pulse_domain_reason(data, patterns)
+        raw = b""
+        if why is None:
+            raw = data.encode("ascii", "replace")  # one byte per character
+            if b"\xff" in raw:                     # cannot happen after an ascii encode; keeps the pad byte unambiguous
+                why = "D contains a 0xFF byte"
+        if why is not None:
+            if strict:
+                raise DomainError(f"message {i}: {why}")
+            domain[i] = why
+            pats.extend(zero8)
+            meta.extend((0, 0, 0xFF, 0, MSG_DOMAIN))
+            continue
         ids = 0
         vals = zero8.copy()
         for s, (pidx, val) in enumerate(patterns.items()):
-            if len(pidx) != 1:
-                raise DomainError(f"message {i}: pattern id {pidx!r} is not a single digit")
-            if val != val or val in (float("inf"), float("-inf")) or val != int(val) or abs(val) > 2147483647:
-                raise DomainError(f"message {i}: pattern value {val!r} is not an int32")
             vals[s] = int(val)
             ids |= int(pidx) << (4 * s)
         cp = 0xFF
@@ -201,9 +227,6 @@ def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
             if cp_key in patterns:
                 cp = list(patterns).index(cp_key)
                 clock[i] = abs(patterns[cp_key])
-        raw = data.encode("ascii", "replace")      # one byte per character
-        if b"\xff" in raw:                         # cannot happen after an ascii encode; keeps the pad byte unambiguous
-            raise DomainError(f"message {i}: D contains a 0xFF byte")
         pats.extend(vals)
         meta.extend((len(raw), len(patterns), cp, ids, MSG_VALID))
         chunks.append(raw)
@@ -222,7 +245,7 @@ def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int) -> PulseBatch:
     blob = b"".join(chunks) + b"\xff" * 64        # +32 B tail so device windows may over-read
     nib = _DIGIT_LUT_PAD[np.frombuffer(blob, dtype=np.uint8)]
     pool = (nib[0::2] | (nib[1::2] << 4)).astype(np.uint8)
-    return PulseBatch(kind, rec, pool, rssi, clock)
+    return PulseBatch(kind, rec, pool, rssi, clock, domain)
 
 
 def unpack_pulse(batch: PulseBatch, i: int) -> Dict[str, Any]:
@@ -256,27 +279,29 @@ def unpack_pulse(batch: PulseBatch, i: int) -> Dict[str, Any]:
 class HexBatch:
     """Packed MC or MN batch."""
 
-    __slots__ = ("kind", "msgs", "digits", "n", "protocol_ids", "data")
+    __slots__ = ("kind", "msgs", "digits", "n", "protocol_ids", "data", "domain")
 
-    def __init__(self, kind, msgs, digits, protocol_ids, data):
+    def __init__(self, kind, msgs, digits, protocol_ids, data, domain=None):
         self.kind = kind
         self.msgs = msgs
         self.digits = digits
         self.protocol_ids = protocol_ids
         self.data = data
         self.n = len(msgs)
+        self.domain = domain or {}   # message index -> why it is outside the packed domain
 
     def algorithmic_input_bytes(self) -> int:
         return int(16 * self.n + ((self.msgs["hlen"].astype(np.int64) + 1) // 2).sum())
 
 
 def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, int],
-             toggle_polarity: bool = False, method_override: int = 0) -> HexBatch:
+             toggle_polarity: bool = False, method_override: int = 0, strict: bool = False) -> HexBatch:
     """Pack MC (kind 2) or MN (kind 3) dicts: protocol_id, data (hex), clock, bit_length.
 
     D must be upper-case hex (what the firmware emits): the reference's polarity inversion is an
     upper-case-only ``str.translate`` (manchester.py:36) and several MN converters echo the input
-    verbatim, neither of which a 4-bit nibble can express -> DomainError for lower-case letters.
+    verbatim, neither of which a 4-bit nibble can express -> such a message is outside the packed
+    domain (SDB_MSG_DOMAIN, status "DomainError" for that message; ``strict`` raises instead).
     """
     n = len(msgs)
     rec = np.zeros(n, dtype=HEX_DTYPE)
@@ -284,6 +309,7 @@ def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, i
     streams: List[np.ndarray] = []
     pids: List[Any] = []
     datas: List[Any] = []
+    domain: Dict[int, str] = {}
     empty = np.zeros(0, dtype=np.uint8)
     for i, m in enumerate(msgs):
         pid = m.get("protocol_id")
@@ -300,32 +326,44 @@ def pack_hex(msgs: Sequence[Dict[str, Any]], kind: int, proto_index: Dict[str, i
             continue
         rec["proto"][i] = proto_index[pid] if not method_override else 0
         rec["rsv"][i] = method_override
-        rec["flags"][i] = MSG_VALID | (HEX_TOGGLE_POLARITY if toggle_polarity else 0)
         if data is None:
             data = ""
+        why = None
+        nib = empty
+        clock = bitlen = 0
         if not isinstance(data, str):
-            raise DomainError(f"message {i}: 'data' must be a str")
-        raw = data.encode("ascii", "replace")
-        if len(raw) > MAX_HEX:
-            raise DomainError(f"message {i}: D has {len(raw)} hex characters (max {MAX_HEX})")
-        b = np.frombuffer(raw, dtype=np.uint8)
-        nib = _HEX_LUT[b]
-        if (nib == 0xFF).any():
-            raise DomainError(f"message {i}: D is not a hex string")
-        if ((b >= ord("a")) & (b <= ord("f"))).any():
-            raise DomainError(f"message {i}: D must be upper-case hex (what the firmware emits)")
-        streams.append(nib)
-        rec["hlen"][i] = len(raw)
-        if kind == KIND_MC:
+            why = "'data' must be a str"
+        else:
+            raw = data.encode("ascii", "replace")
+            b = np.frombuffer(raw, dtype=np.uint8)
+            nib = _HEX_LUT[b]
+            if len(raw) > MAX_HEX:
+                why = f"D has {len(raw)} hex characters (max {MAX_HEX})"
+            elif (nib == 0xFF).any():
+                why = "D is not a hex string"
+            elif ((b >= ord("a")) & (b <= ord("f"))).any():
+                why = "D must be upper-case hex (what the firmware emits)"
+        if why is None and kind == KIND_MC:
             clock = m.get("clock", 0)
             bitlen = m.get("bit_length", 0)
             if not isinstance(clock, int) or not isinstance(bitlen, int):
-                raise DomainError(f"message {i}: clock / bit_length must be int")
+                why = "clock / bit_length must be int"
+        if why is not None:
+            if strict:
+                raise DomainError(f"message {i}: {why}")
+            domain[i] = why
+            rec["flags"][i] = MSG_DOMAIN
+            streams.append(empty)
+            continue
+        rec["flags"][i] = MSG_VALID | (HEX_TOGGLE_POLARITY if toggle_polarity else 0)
+        streams.append(nib)
+        rec["hlen"][i] = len(nib)
+        if kind == KIND_MC:
             rec["clock"][i] = max(-(2**31), min(2**31 - 1, clock))
             rec["bitlen"][i] = max(-32768, min(32767, bitlen))
     pool, doff = pack_digit_streams(streams)
     rec["doff"] = doff
-    return HexBatch(kind, rec, pool, pids, datas)
+    return HexBatch(kind, rec, pool, pids, datas, domain)
 
 
 def unpack_hex(batch: HexBatch, i: int) -> Dict[str, Any]:

@@ -24,7 +24,7 @@ from typing import Any, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import pack
-from .capi import LINE_HOSTPATH, LINE_OK, ST_OK
+from .capi import HIT_MM_HOST, LINE_HOSTPATH, LINE_OK, ST_OK
 from .sd_protocols import SDProtocols
 
 
@@ -165,6 +165,11 @@ class SignalParser:
         self.logger = logger or logging.getLogger(__name__)
         self.protocols.register_log_callback(self._log_adapter)
         self.rfmode = rfmode
+        # Lines the packed domain cannot hold (D longer than 4096 digits, more than 8 pattern slots, pulse values that are not
+        # int32 ...) are NOT decoded — and never decoded differently from the reference.  Each one is logged at error level
+        # and appended here as (index in the call, payload line, reason); strict_domain = True raises DomainError instead.
+        self.domain_errors: List[tuple] = []
+        self.strict_domain = False
 
     def _log_adapter(self, message: str, level: int):
         """__init__.py:54-66"""
@@ -248,7 +253,13 @@ class SignalParser:
                 pool, off = eng.format_json(kind, res.hits, res.bits, text, offs32, info)
                 js = pool.decode("ascii")
                 o = res.out
-                for k in np.nonzero((o["nhits"] > 0) & (o["status"] == ST_OK) & (info["status"] == LINE_OK))[0]:
+                take = (o["nhits"] > 0) & (o["status"] == ST_OK) & (info["status"] == LINE_OK)
+                mmh = (res.hits["flags"] & HIT_MM_HOST) != 0
+                if mmh.any():                                               # host-evaluated modulematch: those lines take parse_lines
+                    lines_mm = np.unique(res.hits["msg"][mmh].astype(np.int64))
+                    take[lines_mm] = False
+                    rest.extend(dev[int(k)] for k in lines_mm)
+                for k in np.nonzero(take)[0]:
                     h0, nh = int(o["hit_off"][k]), int(o["nhits"][k])
                     out[dev[int(k)]] = [js[int(off[h]) : int(off[h + 1])] for h in range(h0, h0 + nh)]
         if rest:
@@ -274,20 +285,27 @@ class SignalParser:
         eng = self.protocols.engine()
         batches = []
         slow: List[int] = []
-        for byte_base, line_base, off, ln, typ, side in frame_chunks(raw):       # chunk k + 1 is framed while chunk k decodes
+        for byte_base, byte_end, line_base, off, ln, typ, side in frame_chunks(raw):       # chunk k + 1 is framed while chunk k decodes
             framed = typ != FRAME_NONE
             slow.extend(line_base + int(i) for i in np.nonzero(framed & (((typ & FRAME_PYPATH) != 0) | ((typ & 0x0F) == pack.KIND_MN)))[0])
             for kind in (pack.KIND_MS, pack.KIND_MU):
                 # plain payloads are addressed inside the caller's buffer, decompressed ones inside the side buffer
-                for text, sel in ((rawbuf[byte_base:], np.nonzero(typ == kind)[0]), (side, np.nonzero(typ == (kind | FRAME_SIDE))[0])):
+                for text, sel in ((rawbuf[byte_base:byte_end], np.nonzero(typ == kind)[0]), (side, np.nonzero(typ == (kind | FRAME_SIDE))[0])):
                     if not len(sel):
                         continue
                     loff = np.ascontiguousarray(off[sel])
                     res, info = eng.demod_lines(kind, text, loff, np.ascontiguousarray(ln[sel]))
                     slow.extend(line_base + int(i) for i in sel[info["status"] == LINE_HOSTPATH])
                     if len(res.hits):
-                        pool, soff = eng.format_json(kind, res.hits, res.bits, text, loff, info)
-                        batches.append((pool, soff, line_base + sel[res.hits["msg"].astype(np.int64)]))
+                        hits = res.hits
+                        mmh = (hits["flags"] & HIT_MM_HOST) != 0
+                        if mmh.any():                                       # host-evaluated modulematch: those lines take parse_lines
+                            lines_mm = np.unique(hits["msg"][mmh].astype(np.int64))
+                            slow.extend(line_base + int(sel[k]) for k in lines_mm)
+                            hits = hits[~np.isin(hits["msg"].astype(np.int64), lines_mm)]
+                        if len(hits):
+                            pool, soff = eng.format_json(kind, hits, res.bits, text, loff, info)
+                            batches.append((pool, soff, line_base + sel[hits["msg"].astype(np.int64)]))
         extra: Dict[int, List[str]] = {}
         if slow:
             import json
@@ -356,6 +374,9 @@ class SignalParser:
             for hi in range(h0, h0 + int(out["nhits"][k])):
                 h = hits[hi]
                 pi = int(h["proto"])
+                if int(h["flags"]) & HIT_MM_HOST:                           # user-edited table: regex the device program cannot express
+                    if not re.search(str(self.protocols.get_property(ids[pi], "modulematch")), text[int(off[hi]) : int(off[hi + 1])]):
+                        continue
                 if kind == pack.KIND_MS:
                     clock = float(li["clock"])                              # message_synced.py:239
                 else:
@@ -382,12 +403,23 @@ class SignalParser:
                     self.logger.warning("Could not parse %s value: %s", key, msg[key])
         try:
             decoded = self.protocols.demodulate(msg, mt)
+        except pack.DomainError as e:
+            # NOT a reference outcome: the packed domain cannot hold this line, so it was not decoded.  Reported apart from
+            # the reference's own "logged and dropped" exceptions so that a caller can see (and count) every such line.
+            self._domain_error(i, frame.line, str(e))
+            return
         except Exception:                                                   # ms.py:52-54: logged and dropped
             self.logger.exception("Error during %s demodulation for line: %s", mt, frame.line)
             return
         for d in decoded:
             results[i].append(DecodedMessage(protocol_id=str(d["protocol_id"]), payload=str(d.get("payload", "")), raw=frame,
                                              metadata=d.get("meta", {})))
+
+    def _domain_error(self, i: int, line: str, why: str) -> None:
+        self.domain_errors.append((i, line, why))
+        self.logger.error("line outside the packed domain, NOT decoded (%s): %s", why, line[:200])
+        if self.strict_domain:
+            raise pack.DomainError(f"line {i}: {why}")
 
     # ------------------------------------------------------------------ MN (mn.py:30-191)
     def _mn_lines(self, idx: List[int], frames, results) -> None:
@@ -418,9 +450,6 @@ class SignalParser:
                     if not (fn and callable(fn)):
                         self.logger.warning("MN Parse: Method %s not found for protocol %s", name, pid)
                         continue
-                    if len(raw) > pack.MAX_HEX:
-                        self.logger.warning("MN Parse: D longer than %d hex characters is outside the packed domain", pack.MAX_HEX)
-                        continue
                     msgs.append({"data": raw, "protocol_id": pid})
                 tasks.append((i, pid, raw, rssi, afc, P.check_property(pid, "modulation", None), prf, bool(method)))
         statuses, decoded = P.demodulate_batch(msgs, "MN") if msgs else ([], [])
@@ -430,6 +459,9 @@ class SignalParser:
             if has_method:
                 st, lst = statuses[k], decoded[k]
                 k += 1
+                if st == "DomainError":                                     # e.g. D longer than 512 hex characters: not decoded
+                    self._domain_error(i, frames[i].line, f"MN protocol {pid}: D outside the packed domain")
+                    continue
                 if st != "ok":                                              # mn.py:167-169: logged, next protocol
                     self.logger.error("Error executing method for protocol %s: %s", pid, st)
                     continue

@@ -8,16 +8,16 @@ packs inputs (pack.py), compiles the protocol table (table.py) and formats strin
 """
 from __future__ import annotations
 
-import copy
-import json
+import re
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import pack
-from .capi import (HIT_LIST, ST_OK, STATUS_EXC, STATUS_NAMES, Engine, Result)
+from .capi import (HIT_LIST, HIT_MM_HOST, ST_DOMAIN, ST_OK, STATUS_EXC, STATUS_NAMES, Engine, Result)
 from .protocol_data import load_protocol_table
-from .table import PD_IDS, compile_table
+from .table import HF_HAS_MAX, HF_HAS_MIN, PD_IDS, CompiledTable, compile_table
+from .tracked import TrackedDict, Version
 
 # SDB_M_* ids of the manchester.py decoders (csrc/sdb_table.h)
 MC_METHODS = {"mcBit2Funkbus": 1, "mcBit2Sainlogic": 2, "mcBit2AS": 3, "mcBit2Hideki": 4, "mcBit2Maverick": 5,
@@ -35,13 +35,27 @@ class SDProtocols:
     """
 
     def __init__(self, device: int = 0, mc_repaired: bool = False):
-        self._protocols = self._load_protocols()
+        self._ver = Version()
+        self._table: Optional[CompiledTable] = None
+        self._table_ver = -1
+        self._engine: Optional[Engine] = None
+        self._engine_ver = -1
         self._log_callback: Optional[Callable[[str, int], None]] = None
+        self._protocols = self._load_protocols()
         self.set_defaults()
         self._device = device
         self.mc_repaired = mc_repaired
-        self._engine: Optional[Engine] = None
-        self._engine_key: Optional[int] = None
+
+    # The protocol dict is wrapped in mutation-tracking containers (tracked.py): callers may edit rows between calls as they
+    # can with the reference (tests/test_manchester_protocols.py:54,84), and the compiled device table follows.
+    @property
+    def _protocols(self) -> Dict[str, Any]:
+        return self._proto_dict
+
+    @_protocols.setter
+    def _protocols(self, value: Dict[str, Any]) -> None:
+        self._proto_dict = TrackedDict(value, self._ver)
+        self._ver.n += 1
 
     # ------------------------------------------------------------------ table / property API
     def _load_protocols(self) -> Dict[str, Any]:
@@ -80,17 +94,26 @@ class SDProtocols:
             self._log_callback(message, level)
 
     # ------------------------------------------------------------------ engine management
-    def _table_key(self) -> int:
-        return hash(json.dumps(self._protocols, sort_keys=False, default=str))
+    def compiled_table(self) -> CompiledTable:
+        """The compiled form of the CURRENT protocol dict (host only, no GPU needed)."""
+        v = self._ver.n
+        if self._table is None or v != self._table_ver:
+            self._table = compile_table(self._protocols)
+            self._table_ver = v
+            for pid, why in self._table.unsupported.items():
+                self._logging(f"protocol {pid} is not compiled into the device table and never matches: {why}", 2)
+        return self._table
 
     def engine(self) -> Engine:
-        """The device engine for the CURRENT protocol dict (recompiled when the dict was mutated)."""
-        key = self._table_key()
-        if self._engine is None or key != self._engine_key:
+        """The device engine for the CURRENT protocol dict (recompiled when the dict was mutated: one integer compare
+        per call, see tracked.py)."""
+        v = self._ver.n
+        if self._engine is None or v != self._engine_ver:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(compile_table(self._protocols), self._device)
-            self._engine_key = key
+                self._engine = None
+            self._engine = Engine(self.compiled_table(), self._device)
+            self._engine_ver = v
         return self._engine
 
     # ------------------------------------------------------------------ batch API (new)
@@ -111,7 +134,9 @@ class SDProtocols:
 
         Returns (statuses, results): statuses[i] is "ok" or the name of the exception the reference
         raises for message i ("IndexError", "TypeError", "ValueError"); results[i] is the list the
-        reference's demodulate() returns (empty when it raises).
+        reference's demodulate() returns (empty when it raises).  A message the packed domain cannot
+        represent (pack.py) gets status "DomainError" and [] — it was NOT decoded; every other message
+        of the batch is.
         """
         if msg_type not in pack.KIND_BY_NAME:
             self._logging(f"Unknown message type {msg_type}", 3)
@@ -140,6 +165,9 @@ class SDProtocols:
                     continue
                 pi = int(h["proto"])
                 payload = text[int(off[i]) : int(off[i + 1])]
+                if int(h["flags"]) & HIT_MM_HOST:                          # a modulematch shape the device program cannot express
+                    if not re.search(str(self._protocols[ids[pi]].get("modulematch")), payload):     # message_unsynced.py:277-280
+                        continue
                 if kind in (pack.KIND_MS, pack.KIND_MU):
                     if kind == pack.KIND_MS:
                         clock = float(batch.clock[m])                      # message_synced.py:239
@@ -173,12 +201,18 @@ class SDProtocols:
         self._logging(f"Unknown message type {msg_type}", 3)
         return []
 
+    def _raise_status(self, status: int, batch, what: str):
+        if status == ST_DOMAIN:
+            raise pack.DomainError(f"{what}: outside the packed domain, not decoded: {batch.domain.get(0, 'malformed record')}")
+        raise STATUS_EXC[status](f"reference {what} raises {STATUS_NAMES[status]} on this message")
+
     def _one(self, msg_data: Dict[str, Any], msg_type: str) -> list:
-        statuses, results = self.demodulate_batch([msg_data], msg_type)
-        if statuses[0] != "ok":
-            raise {"IndexError": IndexError, "TypeError": TypeError, "ValueError": ValueError}[statuses[0]](
-                f"reference demodulate_{msg_type.lower()} raises {statuses[0]} on this message")
-        return results[0]
+        batch = self.pack([msg_data], msg_type)
+        res = self.demodulate_packed(batch)
+        st = int(res.out["status"][0])
+        if st != ST_OK:
+            self._raise_status(st, batch, f"demodulate_{msg_type.lower()}")
+        return self.format_results(batch, res)[1][0]
 
     def demodulate_ms(self, msg_data: Dict[str, Any], msg_type: str = "MS") -> List[Dict[str, Any]]:
         """message_synced.py:10-243 (invalid input -> [] with a level-3 log line, :21-47)"""
@@ -215,10 +249,10 @@ class SDProtocols:
         index = {pid: i for i, pid in enumerate(eng.table.ids)}
         batch = pack.pack_hex([msg_data], pack.KIND_MC, index, toggle_polarity=toggle)
         res = eng.demod_host(batch, mc_repaired=self.mc_repaired)
-        statuses, results = self.format_results(batch, res)
-        if statuses[0] != "ok":
-            raise STATUS_EXC[int(res.out["status"][0])](f"reference demodulate_mc raises {statuses[0]} on this message")
-        return results[0]
+        st = int(res.out["status"][0])
+        if st != ST_OK:
+            self._raise_status(st, batch, "demodulate_mc")
+        return self.format_results(batch, res)[1][0]
 
     def demodulate_mn(self, msg_data: Dict[str, Any], msg_type: str) -> list:
         """sd_protocols.py:113-155"""
@@ -239,10 +273,10 @@ class SDProtocols:
         eng = self.engine()
         batch = pack.pack_hex([msg_data], pack.KIND_MN, {}, method_override=method)
         res = eng.demod_host(batch, mc_repaired=self.mc_repaired)
-        statuses, results = self.format_results(batch, res)
-        if statuses[0] != "ok":
-            raise STATUS_EXC[int(res.out["status"][0])](f"reference converter raises {statuses[0]} on this message")
-        return results[0]
+        st = int(res.out["status"][0])
+        if st != ST_OK:
+            self._raise_status(st, batch, "MN converter")
+        return self.format_results(batch, res)[1][0]
 
     def ConvBresser_lightning(self, msg_data, msg_type="MN"):
         """helpers.py:223-279"""
@@ -405,6 +439,10 @@ class SDProtocols:
             return (-1, "no bitData provided")
         if protocol_id is None:
             return (-1, "no protocolId provided")
+        if isinstance(bit_data, str) and bit_data and any(c not in "01" for c in bit_data):
+            # the length rule is checked first (:112-115), then bin_str_2_hex_str rejects the string (:118-120)
+            rc, msg = self._mc_unit(10, name, "0" * len(bit_data), protocol_id, len(bit_data) if mcbitnum is None else mcbitnum)
+            return (-1, "message is to long") if rc == -1 else (-1, "invalid bit data")
         rc, msg = self._mc_unit(10, name, bit_data, protocol_id, mcbitnum)
         return (rc, "message is to long") if rc == -1 else (rc, msg)
 
@@ -419,6 +457,152 @@ class SDProtocols:
     def mcBit2SomfyRTS(self, name, bit_data, protocol_id, mcbitnum=None):
         """manchester.py:756-795"""
         return self._mc_unit(MC_METHODS["mcBit2SomfyRTS"], name, bit_data, protocol_id, mcbitnum)
+
+    # ------------------------------------------------------------------ MC / MN internals reachable by name (manchester.py)
+    def _mc_reason_text(self, reason: int, name: str, method_name_full, bit_len: int, bit_data: Optional[str]) -> str:
+        base = reason & 0xFF
+        if base in self._MC_REASONS:
+            return self._MC_REASONS[base]
+        if base == 6:
+            return f"{name}: lib/mcBit2Sainlogic, start 010100 not found"
+        if base == 7:
+            return f"message must be 32 bits, got {bit_len}"
+        if base == 8:
+            return f"message must be 56 bits, got {bit_len - 1 if bit_len == 57 else bit_len}"      # manchester.py:783-789
+        if base in (10, 12, 13, 14):
+            return " no duplicate found" + {10: "", 12: ", message is too short", 13: ", message is too long",
+                                            14: ", protocol does not exists"}[base]
+        if base == 11:
+            return f"loop error, please report this data {bit_data}"
+        if base == 20:
+            return "clock out of range"
+        if base == 22:
+            return f"Unknown protocol method {method_name_full}"
+        raise RuntimeError(f"unknown MC reason code {reason}")
+
+    def _convert_mc_hex_to_bits(self, name, raw_hex, polarity_invert, hlen):
+        """manchester.py:18-47: optional (upper-case only) nibble inversion, then hex_to_bin_str.  Pure string formatting:
+        the batch path does the same with index arithmetic on the nibble stream (McBits in csrc/sdb_hex.cu)."""
+        text = raw_hex
+        if polarity_invert:
+            text = "".join("FEDCBA9876543210"["0123456789ABCDEF".index(c)] if c in "0123456789ABCDEF" else c for c in raw_hex)
+        bit_data = self.hex_to_bin_str(text)
+        self._logging(f"{name}: extracted data {bit_data} (bin)", 5)
+        return (1, bit_data)
+
+    def _demodulate_mc_data(self, name, protocol_id, clock, raw_hex, mcbitnum, messagetype, version):
+        """manchester.py:49-144 as one device call: the checks, the decoder and the reject reason all come from the MC kernel
+        (``SdbMsgOut.reason``); the host renders the reference's message strings."""
+        eng = self.engine()
+        pid = protocol_id
+        if not isinstance(pid, str) or pid not in self._protocols:
+            # check_property falls back to its defaults for an unknown id: limits -1 / 9999, no clockrange, no method
+            if mcbitnum < -1:
+                return (-1, "message is too short", {})
+            if mcbitnum > 9999:
+                return (-1, "message is too long", {})
+            return [(-1, "Protocol method not defined", {})]
+        toggle = messagetype == "Mc" or bool(version and version[:6] == "V 3.2.")      # manchester.py:94
+        msg = {"protocol_id": pid, "data": raw_hex, "clock": clock, "bit_length": mcbitnum}
+        batch = pack.pack_hex([msg], pack.KIND_MC, {pid: eng.table.ids.index(pid)}, toggle_polarity=toggle)
+        res = eng.demod_host(batch, mc_repaired=self.mc_repaired)
+        st, reason = int(res.out["status"][0]), int(res.out["reason"][0])
+        if reason == 21:
+            return [(-1, "Protocol method not defined", {})]                           # :108-109 (a list, as shipped)
+        if st != ST_OK:
+            self._raise_status(st, batch, "_demodulate_mc_data")
+        if int(res.out["nhits"][0]) == 0:
+            lead = len(raw_hex) - len(raw_hex.lstrip("0")) if raw_hex.strip("0") else max(len(raw_hex) - 1, 0)
+            bit_len = 4 * (len(raw_hex) - lead)
+            bits = None
+            if (reason & 0xFF) == 11:
+                inv = (self.check_property(pid, "polarity", "") == "invert") ^ toggle
+                bits = self._convert_mc_hex_to_bits(name, raw_hex, inv, len(raw_hex))[1]
+            return (-1, self._mc_reason_text(reason, name, self.get_property(pid, "method"), bit_len, bits), {})
+        pool, off = eng.format_hits(pack.KIND_MC, res.hits, res.bits)
+        dmsg = pool[int(off[0]) : int(off[1])].decode("latin-1")
+        return (1, dmsg, {"protocol_id": protocol_id, "rssi": None, "freq_afc": None})        # :134-142
+
+    def _demodulate_mn_data(self, name, protocol_id, msg_data):
+        """manchester.py:147-204: method lookup, one converter call (on the device), first well-formed result."""
+        method_name_full = self.get_property(protocol_id, "method")
+        if not method_name_full:
+            return []
+        method_name = method_name_full.split(".")[-1]
+        func = getattr(self, method_name, None)
+        if not callable(func):
+            return []
+        try:
+            demodulated_list = func(msg_data, "MN")
+        except TypeError:
+            return []
+        if not isinstance(demodulated_list, list) or not demodulated_list:
+            return []
+        for decoded in demodulated_list:
+            if not isinstance(decoded, dict) or "protocol_id" not in decoded:
+                continue
+            return [{"protocol_id": str(decoded["protocol_id"]), "payload": str(decoded.get("payload", "")),
+                     "meta": decoded.get("meta", {})}]
+        return []
+
+    # ------------------------------------------------------------------ checksum helpers (helpers.py), scalar API surface
+    # The batch path computes these inside the MN kernel (lfsr16 / crc16 / the LaCrosse CRC in csrc/sdb_hex.cu); the methods
+    # exist because the reference's converters and tests call them by name.
+    def lfsr_digest16(self, bytes_count, gen, key, raw_data):
+        """helpers.py:190-221: Galois LFSR digest over the first bytes_count bytes of a hex string (0 when it is too short
+        or not hex)."""
+        if len(raw_data) < 2 * bytes_count:
+            return 0
+        try:
+            data = [int(raw_data[2 * k : 2 * k + 2], 16) for k in range(bytes_count)]
+        except ValueError:
+            return 0
+        digest = 0
+        for byte in data:
+            for bit in (0x80, 0x40, 0x20, 0x10, 0x08, 0x04, 0x02, 0x01):
+                if byte & bit:
+                    digest ^= key
+                key = (key >> 1) ^ gen if key & 1 else key >> 1
+        return digest
+
+    def _calc_crc16(self, hex_data, poly, init, refin, refout, xorout):
+        """helpers.py:281-309: bitwise CRC-16, MSB first, optional input / output reflection; '0000' for non-hex input."""
+        try:
+            data = bytes.fromhex(hex_data)
+        except ValueError:
+            self._logging(f"_calc_crc16: Invalid hex data provided: {hex_data}", 3)
+            return "0000"
+        reg = init
+        for byte in data:
+            if refin:
+                byte = int(format(byte, "08b")[::-1], 2)
+            reg ^= byte << 8
+            for _ in range(8):
+                reg = ((reg << 1) ^ poly if reg & 0x8000 else reg << 1) & 0xFFFF
+        if refout:
+            reg = int(format(reg, "016b")[::-1], 2)
+        return format(reg ^ xorout, "04X")
+
+    def _calc_crc8_la_crosse(self, hex_data):
+        """helpers.py:311-380: what the method returns is its last loop — a right-shifting CRC-8 with 0x31 XORed in on a set
+        low bit (bytes.fromhex raises ValueError on bad input, as there)."""
+        reg = 0
+        for byte in bytes.fromhex(hex_data):
+            reg ^= byte
+            for _ in range(8):
+                reg = ((reg >> 1) ^ 0x31 if reg & 1 else reg >> 1) & 0xFF
+        return reg
+
+    # ------------------------------------------------------------------ RSL placeholders (rsl_handler.py:12-55)
+    def decode_rsl(self, bit_data):
+        """rsl_handler.py:12-33 (a placeholder upstream as well: echoes its input)"""
+        self._logging(f"lib/decode_rsl, bit_data length: {len(str(bit_data))}", 5)
+        return {"decoded": str(bit_data), "status": 1}
+
+    def encode_rsl(self, data):
+        """rsl_handler.py:35-55"""
+        self._logging(f"lib/encode_rsl, data: {data}", 5)
+        return {"encoded": str(data), "status": 1}
 
     # ------------------------------------------------------------------ small pure helpers (API surface)
     def bin_str_2_hex_str(self, num):
@@ -443,24 +627,19 @@ class SDProtocols:
         return b.zfill((len(b) + 3) // 4 * 4)
 
     def length_in_range(self, protocol_id, message_length):
-        """helpers.py:124-166"""
-        if not self.protocol_exists(str(protocol_id)):
+        """helpers.py:124-166 — answered from the compiled table's per-protocol length rules (the same row the MC / MN
+        kernels and ``in_range`` in csrc/sdb_hex.cu read)."""
+        tab = self.compiled_table()
+        pid = str(protocol_id)
+        if pid not in self._protocols:
             return (0, "protocol does not exists")
-        min_len = self.check_property(protocol_id, "length_min", -1)
-        if min_len is not None:
-            try:
-                min_len = int(min_len)
-            except (ValueError, TypeError):
-                pass
-        if min_len != -1 and message_length < min_len:
-            return (0, "message is too short")
-        max_len = self.get_property(protocol_id, "length_max")
-        if max_len is not None:
-            try:
-                if message_length > int(max_len):
-                    return (0, "message is too long")
-            except (ValueError, TypeError):
-                pass
+        row = tab.hex_rows[tab.ids.index(pid)]
+        if protocol_id in self._protocols:                      # check_property / get_property look the id up as passed (int ids miss)
+            fl = int(row["flags"])
+            if fl & HF_HAS_MIN and int(row["length_min"]) != -1 and message_length < int(row["length_min"]):
+                return (0, "message is too short")
+            if fl & HF_HAS_MAX and message_length > int(row["length_max"]):
+                return (0, "message is too long")
         return (1, "")
 
     def mc2dmc(self, bit_data):

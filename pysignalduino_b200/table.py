@@ -44,6 +44,7 @@ PF_REMOVE_ZERO = 0x04
 PF_MM_END = 0x08      # modulematch ends with '$'
 PF_MM_NEVER = 0x10    # modulematch can never match this protocol's preamble
 PF_HAS_LIR_MAX = 0x20
+PF_MM_HOST = 0x40
 
 PD_IDS = {
     "postDemo_EM": 1, "postDemo_Revolt": 2, "postDemo_FS20": 3, "postDemo_FHT80": 4,
@@ -284,12 +285,17 @@ def fold_preamble(items, end: bool, preamble: str):
 # table compiler
 # --------------------------------------------------------------------------------------------
 class CompiledTable:
-    def __init__(self, blob: bytes, ids: List[str], ms_ids: List[str], mu_ids: List[str], info: Dict[str, Any]):
+    def __init__(self, blob: bytes, ids: List[str], ms_ids: List[str], mu_ids: List[str], info: Dict[str, Any],
+                 hex_rows: Optional[np.ndarray] = None, unsupported: Optional[Dict[str, str]] = None):
         self.blob = blob
         self.ids = ids              # protocol ids in table order (hit.proto indexes this)
         self.ms_ids = ms_ids
         self.mu_ids = mu_ids
         self.info = info
+        self.hex_rows = hex_rows    # HEXPROTO_DTYPE row per protocol id (length rules, method, preamble)
+        # "<id> (MS|MU|MC/MN)" -> why that row is NOT in the device table (the protocol never matches in that class).
+        # Empty for the shipped table; a user-edited table degrades per protocol instead of failing engine creation.
+        self.unsupported = unsupported or {}
 
 
 class _RankPool:
@@ -334,31 +340,47 @@ def _as_floats(v) -> Optional[List[float]]:
         return None
 
 
-def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
-    """Compile a protocol dict (``SDProtocols._protocols``) into the device blob."""
+def compile_table(protocols: Dict[str, Dict[str, Any]], strict: bool = False) -> CompiledTable:
+    """Compile a protocol dict (``SDProtocols._protocols``) into the device blob.
+
+    Tolerant like the reference (which skips what it cannot use, message_synced.py:206, message_unsynced.py:234): a row
+    whose shape the device layout cannot hold (more than 4 distinct template values, symbol widths other than 1 / 2 / 4, ...)
+    is left out and listed in ``CompiledTable.unsupported``; a ``modulematch`` outside the compiled program's shapes is
+    evaluated by the host formatter (PF_MM_HOST).  ``strict=True`` raises ``NotImplementedError`` instead.
+    """
     ids = list(protocols.keys())
     if len(ids) >= 0xFFFF:
         raise NotImplementedError("too many protocols")
     pool = _RankPool()
     mm_items: List[Tuple[int, int, int]] = []
+    unsupported: Dict[str, str] = {}
+
+    def guarded(label: str, fn):
+        """Run one row compiler; an unsupported shape drops that row only."""
+        if strict:
+            return fn()
+        try:
+            return fn()
+        except (NotImplementedError, ValueError, TypeError, OverflowError) as e:
+            unsupported[label] = f"{type(e).__name__}: {e}"
+            return None
 
     # ---------------- MS: get_keys('sync') (message_synced.py:79) ----------------
     ms_rows, ms_pf, ms_ids = [], [], []
-    for idx, (pid, pr) in enumerate(protocols.items()):
-        if "sync" not in pr:
-            continue
+
+    def ms_row(idx, pid, pr):
         sync = pr.get("sync")
         if not sync:
             raise NotImplementedError(f"protocol {pid}: falsy 'sync'")
         svals = _as_floats(sync)
         if svals is None:
-            continue                                   # float('D') -> match_failed (:114-118): never hits
+            return None                                # float('D') -> match_failed (:114-118): never hits
         one = pr.get("one")
         if not one:
             # signal_width 0 (:106-107): fails `length_min > 0` (:150-156) unless length_min <= 0,
             # in which case range(..., 0) raises (:174)
             if int(pr.get("length_min", -1)) > 0:
-                continue
+                return None
             raise NotImplementedError(f"protocol {pid}: MS protocol without 'one' and length_min <= 0")
         rec = np.zeros((), dtype=PULSEPROTO_DTYPE)
         _fill_common(rec, idx, pid, pr, pool, ms=True)
@@ -367,19 +389,21 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         rec["regex_min"] = int(pr.get("length_min", -1))   # :152
         if pr.get("postDemodulation") and rec["postdemod"] and pr.get("float"):
             raise NotImplementedError(f"protocol {pid}: MS postDemodulation with 'float' symbols raises in the reference")
-        ms_rows.append(rec)
-        ms_ids.append(pid)
+        return rec
+
+    for idx, (pid, pr) in enumerate(protocols.items()):
+        if "sync" not in pr:
+            continue
+        rec = guarded(f"{pid} (MS)", lambda: ms_row(idx, pid, pr))
+        if rec is not None:
+            ms_rows.append(rec)
+            ms_ids.append(pid)
 
     # ---------------- MU: get_keys('clockabs') + active (message_unsynced.py:45-49) ----------------
     mu_rows, mu_pf, mu_ids, clocks = [], [], [], []
     mu_vals: Dict[Tuple[int, int, int], int] = {}
-    for idx, (pid, pr) in enumerate(protocols.items()):
-        if "clockabs" not in pr:
-            continue
-        if not pr.get("active", True):
-            continue
-        if not pr.get("one"):
-            continue                                   # signal_width == 0 -> every match skipped (:205)
+
+    def mu_row(idx, pid, pr):
         rec = np.zeros((), dtype=PULSEPROTO_DTYPE)
         _fill_common(rec, idx, pid, pr, pool, ms=False)
         start = pr.get("start")
@@ -389,9 +413,6 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         if clock == 0:
             raise NotImplementedError(f"protocol {pid}: clockabs 0 (ZeroDivisionError in the reference)")
         rec["clock"] = clock
-        if clock not in clocks:
-            clocks.append(clock)
-        rec["clk_idx"] = clocks.index(clock)
         lmin = pr.get("length_min", 0)                 # :178 goes into the regex text {MIN,}
         if not re.fullmatch(r"\d+", str(lmin)):
             raise NotImplementedError(f"protocol {pid}: length_min {lmin!r} is not a regex repeat count")
@@ -400,10 +421,18 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
             raise NotImplementedError(f"protocol {pid}: empty-match regex (no start, length_min 0)")
         lmax = pr.get("length_max", None)              # :197,:217 truthiness
         rec["mu_len_max"] = int(lmax) if lmax else -1
+        new_items: List[Tuple[int, int, int]] = []
         mm = pr.get("modulematch")
         if mm:                                         # :277-280
-            items, end = compile_modulematch(mm)
-            items, never = fold_preamble(items, end, str(pr.get("preamble", "")))
+            try:
+                items, end = compile_modulematch(mm)
+                items, never = fold_preamble(items, end, str(pr.get("preamble", "")))
+            except (NotImplementedError, re.error, ValueError):
+                if strict:
+                    raise
+                re.compile(mm)                         # a regex Python itself rejects raises in the reference too
+                rec["flags"] |= PF_MM_HOST             # hits are flagged; the host formatter runs re.search
+                return rec, new_items
             if not end and items:
                 # re.search without '$': a trailing {lo,hi} only needs its minimum; {0,..} is a no-op
                 mask, lo, _hi = items[-1]
@@ -420,11 +449,34 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
             if never:
                 rec["flags"] |= PF_MM_NEVER
             elif items or end:
-                rec["mm_off"] = len(mm_items)
+                if len(items) > 255:
+                    raise NotImplementedError(f"protocol {pid}: modulematch program too long")
                 rec["mm_nitems"] = len(items)
-                mm_items.extend(items)
+                new_items = list(items)
                 if end:
                     rec["flags"] |= PF_MM_END
+                if not items:
+                    rec["mm_off"] = 0xFFFE             # '$' only: patched to a valid offset below
+        return rec, new_items
+
+    for idx, (pid, pr) in enumerate(protocols.items()):
+        if "clockabs" not in pr:
+            continue
+        if not pr.get("active", True):
+            continue
+        if not pr.get("one"):
+            continue                                   # signal_width == 0 -> every match skipped (:205)
+        got = guarded(f"{pid} (MU)", lambda: mu_row(idx, pid, pr))
+        if got is None:
+            continue
+        rec, new_items = got
+        clock = float(rec["clock"])
+        if clock not in clocks:
+            clocks.append(clock)
+        rec["clk_idx"] = clocks.index(clock)
+        if new_items or int(rec["mm_off"]) == 0xFFFE:
+            rec["mm_off"] = len(mm_items)
+            mm_items.extend(new_items)
         # every (clock, accept interval) pair gets one slot of the per-message candidate-mask table
         for kk in range(4):
             kt = rec["key"][kk]
@@ -450,8 +502,9 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
 
     # ---------------- MC / MN protocol rows (every protocol id, table order) ----------------
     hexrows = np.zeros(len(ids), dtype=HEXPROTO_DTYPE)
-    for idx, (pid, pr) in enumerate(protocols.items()):
-        h = hexrows[idx]
+
+    def hex_row(idx, pid, pr):
+        h = np.zeros((), dtype=HEXPROTO_DTYPE)
         fl = HF_EXISTS
         if pr.get("length_min") is not None:
             fl |= HF_HAS_MIN
@@ -477,6 +530,12 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         if len(pre) > 16:
             raise NotImplementedError(f"protocol {pid}: preamble too long")
         h["preamble"], h["pre_len"] = pre, len(pre)
+        return h
+
+    for idx, (pid, pr) in enumerate(protocols.items()):
+        h = guarded(f"{pid} (MC/MN)", lambda: hex_row(idx, pid, pr))
+        if h is not None:
+            hexrows[idx] = h                           # a dropped row keeps flags == 0: "protocol does not exist" on the device
 
     # ---------------- assemble ----------------
     def arr(rows, dtype):
@@ -549,7 +608,7 @@ def compile_table(protocols: Dict[str, Dict[str, Any]]) -> CompiledTable:
         blob[start : start + len(b)] = b
     info = {"n_ms": len(ms_arr), "n_mu": len(mu_arr), "n_clk": len(clocks), "n_rank": len(rank_arr), "n_vals": len(mu_vals) + len(ms_vals), "n_mu_vals": len(mu_vals),
             "n_mm_items": len(mm_arr), "bytes": total, "clocks": clocks}
-    return CompiledTable(bytes(blob), ids, ms_ids, mu_ids, info)
+    return CompiledTable(bytes(blob), ids, ms_ids, mu_ids, info, hexrows, unsupported)
 
 
 def _fill_common(rec, idx: int, pid: str, pr: Dict[str, Any], pool: _RankPool, ms: bool) -> None:

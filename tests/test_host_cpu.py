@@ -65,14 +65,27 @@ def test_pack_ms_gates():
 
 
 def test_pack_domain_errors():
-    with pytest.raises(pack.DomainError):
-        pack.pack_pulse([{"P0": "300.5", "data": "00"}], pack.KIND_MU)
-    with pytest.raises(pack.DomainError):
-        pack.pack_pulse([{"P12": "300", "data": "00"}], pack.KIND_MU)
-    with pytest.raises(pack.DomainError):
-        pack.pack_pulse([{"P0": "300", "data": "0" * 1025}], pack.KIND_MU)
-    with pytest.raises(pack.DomainError):
-        pack.pack_hex([{"protocol_id": "10", "data": "abcd", "clock": 400, "bit_length": 16}], pack.KIND_MC, {"10": 0})
+    """Unrepresentable messages are marked per message (status DomainError on the device); strict=True raises."""
+    bad = [{"P0": "300.5", "data": "00"}, {"P12": "300", "data": "00"}, {"P0": "300", "data": "0" * (pack.MAX_DIGITS + 1)},
+           {f"P{k}": "100" for k in range(9)} | {"data": "00"}]
+    good = {"P0": "300", "P1": "-300", "data": "0101"}
+    for m in bad:
+        with pytest.raises(pack.DomainError):
+            pack.pack_pulse([m], pack.KIND_MU, strict=True)
+    b = pack.pack_pulse([good] + bad + [good], pack.KIND_MU)
+    assert sorted(b.domain) == [1, 2, 3, 4]
+    assert [int(f) for f in b.msgs["flags"]] == [pack.MSG_VALID] + [pack.MSG_DOMAIN] * 4 + [pack.MSG_VALID]
+    assert int(b.msgs["dlen"][5]) == 4 and int(b.msgs["doff"][5]) == 1          # the good messages keep their streams
+    ok_long = pack.pack_pulse([{"P0": "300", "data": "0" * pack.MAX_DIGITS}], pack.KIND_MU)
+    assert not ok_long.domain and int(ok_long.msgs["dlen"][0]) == pack.MAX_DIGITS
+    hexbad = [{"protocol_id": "10", "data": "abcd", "clock": 400, "bit_length": 16},
+              {"protocol_id": "10", "data": "A" * (pack.MAX_HEX + 1), "clock": 400, "bit_length": 16},
+              {"protocol_id": "10", "data": "XYZ", "clock": 400, "bit_length": 16}]
+    for m in hexbad:
+        with pytest.raises(pack.DomainError):
+            pack.pack_hex([m], pack.KIND_MC, {"10": 0}, strict=True)
+    hb = pack.pack_hex(hexbad + [{"protocol_id": "10", "data": "ABCD", "clock": 400, "bit_length": 16}], pack.KIND_MC, {"10": 0})
+    assert sorted(hb.domain) == [0, 1, 2] and [int(f) for f in hb.msgs["flags"]] == [pack.MSG_DOMAIN] * 3 + [pack.MSG_VALID]
 
 
 def test_pack_unpack_roundtrip(corpus):

@@ -116,7 +116,7 @@ def test_line_oracle_matches_reference(oracle):
                 assert r["results"] == [], r["line"]
                 continue
             try:
-                pack.pack_pulse([m], pack.KIND_BY_NAME[typ])
+                pack.pack_pulse([m], pack.KIND_BY_NAME[typ], strict=True)
             except pack.DomainError:
                 continue                               # outside the packed domain (documented): not an oracle case
             msgs.append(m)
