@@ -31,7 +31,7 @@ EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
     "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines", "sdb_frame_lines_inplace",
-    "sdb_unit_pattern_exists",
+    "sdb_unit_pattern_exists", "sdb_demod_host_payloads",
 ]
 
 
@@ -71,6 +71,8 @@ def load_library() -> C.CDLL:
     L.sdb_demod_host.restype = C.c_int
     L.sdb_demod_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                  C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.sdb_demod_host_payloads.restype = C.c_int
+    L.sdb_demod_host_payloads.argtypes = L.sdb_demod_host.argtypes + [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
     L.sdb_format_hits.restype = C.c_int
     L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.POINTER(C.c_size_t)]
@@ -271,6 +273,19 @@ class Engine:
             raise self._err(rc, "sdb_demod_host")
         return rc
 
+    def demod_host_payloads_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, hits: np.ndarray,
+                                 bits: np.ndarray, ctr: np.ndarray, pool: np.ndarray, off: np.ndarray, mc_repaired: bool = False):
+        """Decode + payload strings in one pipelined call with caller-owned arrays (``pool`` uint8, ``off`` uint64[len(hits) + 1]);
+        returns (raw code, pool bytes used)."""
+        used = C.c_size_t(0)
+        rc = self.lib.sdb_demod_host_payloads(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
+                                              digits.nbytes, len(msgs), out.ctypes.data, hits.ctypes.data, len(hits),
+                                              bits.ctypes.data, len(bits), ctr.ctypes.data, pool.ctypes.data, pool.nbytes,
+                                              off.ctypes.data, C.byref(used))
+        if rc not in (SDB_OK, SDB_E_OVERFLOW):
+            raise self._err(rc, "sdb_demod_host_payloads")
+        return rc, used.value
+
     # ---- text lines (tokenizer kernel + demodulation) ---------------------------------------
     def demod_lines(self, kind: int, text: np.ndarray, line_off: np.ndarray, line_len: np.ndarray,
                     hits_cap: int = 0, bits_cap: int = 0):
@@ -333,6 +348,17 @@ class Engine:
             if rc != SDB_OK:
                 raise self._err(rc, "sdb_format_hits")
             return pool[: used.value].tobytes(), off
+
+    def format_hits_into(self, kind: int, hits: np.ndarray, bits: np.ndarray, pool: np.ndarray, off: np.ndarray) -> int:
+        """Same with caller-owned buffers (``pool`` uint8, ``off`` uint64[len(hits) + 1]); returns the bytes used
+        (raises when the pool is too small).  The formatter splits large batches over the host threads."""
+        used = C.c_size_t(0)
+        rc = self.lib.sdb_format_hits(self.h, kind, hits.ctypes.data if len(hits) else None, len(hits),
+                                      bits.ctypes.data if len(bits) else None, pool.ctypes.data, pool.nbytes, off.ctypes.data,
+                                      C.byref(used))
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_format_hits")
+        return used.value
 
     def format_json(self, kind: int, hits: np.ndarray, bits: np.ndarray, text: np.ndarray, line_off: np.ndarray,
                     info: np.ndarray) -> Tuple[bytes, np.ndarray]:

@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sdb200.h"
@@ -41,7 +45,7 @@ struct SdbHandle {
     cudaStream_t stream = nullptr;      /* compute + final copies of the host-buffer path */
     cudaStream_t copy_stream = nullptr; /* pipelined H2D */
     cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
-    std::vector<cudaEvent_t> ev_h2d, ev_done;
+    std::vector<cudaEvent_t> ev_h2d, ev_done, ev_d2h;
     SdbCounters *h_snap = nullptr;      /* pinned: counters after each chunk (which arena ranges are final) */
     uint32_t snap_cap = 0;
 };
@@ -135,6 +139,7 @@ extern "C" void sdb_destroy(SdbHandle *h)
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_d2h) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->h_snap) cudaFreeHost(h->h_snap);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -216,10 +221,11 @@ static int grow(SdbHandle *h, T *&p, size_t &cap, size_t need_bytes)
 static int pipeline_prepare(SdbHandle *h, uint32_t nchunks)
 {
     while (h->ev_h2d.size() < nchunks) {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, c;
         CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        h->ev_h2d.push_back(a); h->ev_done.push_back(b);
+        CK(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+        h->ev_h2d.push_back(a); h->ev_done.push_back(b); h->ev_d2h.push_back(c);
     }
     if (h->snap_cap < nchunks) {
         if (h->h_snap) cudaFreeHost(h->h_snap);
@@ -234,7 +240,10 @@ static int pipeline_prepare(SdbHandle *h, uint32_t nchunks)
  * ranges [done, snapshot k) are final: copy them to the host while the next chunk's kernels run, instead of one big
  * D2H after the last kernel (0.7 GB per 10 M mixed messages). */
 struct ArenaDrain { uint32_t hits = 0, words = 0; };
-static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, uint32_t hits_cap, uint32_t *bits, uint32_t bits_cap)
+struct FmtSink;                                           /* payload strings formatted on the host threads while later chunks run */
+static void sink_push(FmtSink *s, uint32_t hits_end, cudaEvent_t arrived);
+static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, uint32_t hits_cap, uint32_t *bits, uint32_t bits_cap,
+                       FmtSink *sink = nullptr)
 {
     CK(cudaEventSynchronize(h->ev_done[k]));            /* chunk k + 1 is already queued: the GPU stays busy */
     const SdbCounters c = h->h_snap[k];
@@ -244,13 +253,17 @@ static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, ui
     if (c.words > d.words && bits)
         CK(cudaMemcpyAsync(bits + d.words, h->d_bits + d.words, sizeof(uint32_t) * (size_t)(c.words - d.words), cudaMemcpyDeviceToHost, h->d2h_stream));
     d.hits = c.hits; d.words = c.words;
+    if (sink) {
+        CK(cudaEventRecord(h->ev_d2h[k], h->d2h_stream));
+        sink_push(sink, c.hits, h->ev_d2h[k]);          /* hits [.., c.hits) and their bits are final and on their way */
+    }
     return SDB_OK;
 }
 
-extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
-                              const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
-                              SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
-                              uint32_t *bits, uint32_t bits_cap, SdbCounters *counters)
+static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
+                           const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                           SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                           uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, FmtSink *sink, bool *sink_fed)
 {
     if (!h) return SDB_E_ARG;
     if (!counters || (n && (!msgs || !digits || !out))) return set_err(h, SDB_E_ARG, "sdb_demod_host: null pointer");
@@ -302,9 +315,10 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
             CK(cudaEventRecord(h->ev_done[k], st));
             CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
             CK(cudaMemcpyAsync(out + lo, h->d_out + lo, sizeof(SdbMsgOut) * (size_t)cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-            if (k && (rc = drain_chunk(h, k - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
+            if (k && (rc = drain_chunk(h, k - 1, drain, hits, hits_cap, bits, bits_cap, sink))) return rc;
         }
-        if ((rc = drain_chunk(h, nchunks - 1, drain, hits, hits_cap, bits, bits_cap))) return rc;
+        if ((rc = drain_chunk(h, nchunks - 1, drain, hits, hits_cap, bits, bits_cap, sink))) return rc;
+        if (sink_fed) *sink_fed = true;
         *counters = h->h_snap[nchunks - 1];
         CK(cudaStreamSynchronize(h->d2h_stream));
         if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
@@ -328,6 +342,14 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
     if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SDB_OK;
+}
+
+extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
+                              const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                              SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                              uint32_t *bits, uint32_t bits_cap, SdbCounters *counters)
+{
+    return demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr, nullptr);
 }
 
 extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
@@ -402,109 +424,262 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
 }
 
 /* ---- host-side formatting --------------------------------------------------------------- */
+/* Payload strings of the hits: preamble + hex / bits + postamble.  Two passes over the hits (string lengths -> offsets ->
+ * characters), each split over the host threads for large batches: 27 M hits per 10 M-message mixed corpus would take
+ * seconds on one core, and the reference side of the comparison (its CPU path) produces these strings too. */
 static inline int hbit(const uint32_t *w, uint32_t i) { return (w[i >> 5] >> (i & 31)) & 1; }
+static const uint8_t kRev4[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
+
+/* hex digit j of nb bits (LSB-first words), right-aligned nibbles as helpers.py:28-64 builds them */
+static inline int hex_digit_at(const uint32_t *w, int nb, int nd, int j)
+{
+    const int b0 = nb - 4 * (nd - j);
+    if (b0 >= 0) {                                    /* message bits b0 .. b0+3, the first one is the digit's MSB */
+        const int sh = b0 & 31;
+        uint32_t x = w[b0 >> 5] >> sh;
+        if (sh > 28) x |= w[(b0 >> 5) + 1] << (32 - sh);      /* b0 + 3 < nb: that word exists */
+        return kRev4[x & 0xF];
+    }
+    int v = 0;
+    for (int k = 0; k < 4; k++) { const int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
+    return v;
+}
+
+namespace {
+struct Fmt {
+    const SdbTblHeader *hd;
+    int kind;
+    bool pulse;
+    std::vector<const SdbPulseProto *> row;       /* table-order index -> pulse row (preamble / flags) */
+    const SdbHexProto *hx;
+    const SdbHit *hits;
+    uint32_t nhits;
+    const uint32_t *bits;
+
+    /* characters of hit i appended at dst (dst == nullptr: count only); returns the count, or (size_t)-1 for a bad record */
+    size_t one(uint32_t i, char *dst) const
+    {
+        size_t n = 0;
+        auto put = [&](char c) { if (dst) dst[n] = c; n++; };
+        auto put_hex = [&](const uint32_t *w, uint32_t nb, bool strip) {
+            const int nd = (int)((nb + 3) >> 2);
+            int j = 0;
+            if (strip) while (j < nd && hex_digit_at(w, (int)nb, nd, j) == 0) j++;
+            if (!dst) { n += (size_t)(nd - j); return; }
+            for (; j < nd; j++) dst[n++] = "0123456789ABCDEF"[hex_digit_at(w, (int)nb, nd, j)];
+        };
+        const SdbHit &ht = hits[i];
+        if (ht.proto >= hd->nproto) return (size_t)-1;
+        const uint32_t *w = bits + ht.bits_off;
+        if (pulse) {
+            const SdbPulseProto *pp = row[ht.proto];
+            if (!pp) return (size_t)-1;
+            const uint32_t nb = ht.nbits, nwv = (nb + 31) >> 5;
+            const bool has_f = (ht.flags & SDB_HIT_HAS_F) != 0;
+            for (int k = 0; k < pp->pre_len; k++) put(pp->preamble[k]);
+            if (pp->flags & SDB_PF_DISPATCH_BIN) {
+                for (uint32_t b = 0; b < nb; b++) put(has_f && hbit(w + nwv, b) ? 'F' : (char)('0' + hbit(w, b)));
+            } else if (has_f) {
+                put('N'); put('o'); put('n'); put('e');       /* f"{None}" (message_unsynced.py:267,274) */
+            } else put_hex(w, nb, (pp->flags & SDB_PF_REMOVE_ZERO) != 0);
+            for (int k = 0; k < pp->post_len; k++) put(pp->postamble[k]);
+            return n;
+        }
+        /* MC: preamble + hex, or preamble + repr(list) for TFA (manchester.py:131-132, :713-717)
+         * MN: the converter's own string (helpers.py:223-716), no preamble (sd_protocols.py:151-155) */
+        const SdbHexProto &p = hx[ht.proto];
+        if (kind == SDB_KIND_MC) {
+            if (ht.flags & SDB_HIT_LIST) {
+                if (ht.aux != 0) return 0;                /* the first element of a list carries the whole string */
+                for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
+                put('[');
+                for (uint32_t e = i; e < nhits && hits[e].msg == ht.msg && (hits[e].flags & SDB_HIT_LIST) && hits[e].aux == e - i; e++) {
+                    if (e > i) { put(','); put(' '); }
+                    put('\'');
+                    put_hex(bits + hits[e].bits_off, hits[e].nbits, false);
+                    put('\'');
+                }
+                put(']');
+            } else {
+                for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
+                put_hex(w, ht.nbits, false);
+            }
+        } else if (ht.flags & SDB_HIT_FIELDS) {
+            char num[96];
+            int k;
+            if (ht.aux == SDB_M_PCA301)                    /* MN hits carry the converter that produced them in aux */
+                k = snprintf(num, sizeof num, "OK 24 %u %u %u %u %u %u %u %u %u %u %04X", w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], w[9], w[10]);
+            else
+                k = snprintf(num, sizeof num, "OK 9 %u %u %u %u %u", w[0], w[1], w[2], w[3], w[4]);
+            for (int q = 0; q < k; q++) put(num[q]);
+        } else {
+            if (ht.aux == SDB_M_KOPP) { put('k'); put('r'); }
+            put_hex(w, ht.nbits, false);
+        }
+        return n;
+    }
+};
+
+template <typename F>
+void parallel_ranges(uint32_t n, unsigned threads, F fn)
+{
+    if (threads <= 1 || n < 65536) { fn(0u, 0u, n); return; }
+    std::vector<std::thread> th;
+    const uint32_t per = (n + threads - 1) / threads;
+    for (unsigned t = 0; t < threads; t++) {
+        const uint32_t lo = t * per < n ? t * per : n, hi = lo + per < n ? lo + per : n;
+        th.emplace_back([=] { fn(t, lo, hi); });
+    }
+    for (auto &x : th) x.join();
+}
+}  // namespace
+
+static int fmt_init(Fmt &F, const SdbHandle *h, int kind)
+{
+    F.hd = reinterpret_cast<const SdbTblHeader *>(h->blob.data());
+    F.kind = kind;
+    F.pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
+    F.hx = reinterpret_cast<const SdbHexProto *>(h->blob.data() + F.hd->off_hex);
+    F.hits = nullptr; F.nhits = 0; F.bits = nullptr;
+    if (!F.pulse && kind != SDB_KIND_MC && kind != SDB_KIND_MN) return SDB_E_ARG;
+    if (F.pulse) {
+        F.row.assign(F.hd->nproto, nullptr);
+        const SdbPulseProto *tab = reinterpret_cast<const SdbPulseProto *>(h->blob.data() + (kind == SDB_KIND_MS ? F.hd->off_ms : F.hd->off_mu));
+        const uint32_t cnt = kind == SDB_KIND_MS ? F.hd->n_ms : F.hd->n_mu;
+        for (uint32_t i = 0; i < cnt; i++) F.row[tab[i].proto] = &tab[i];
+    }
+    return SDB_OK;
+}
+
+static unsigned fmt_threads()
+{
+    unsigned t = std::thread::hardware_concurrency();
+    if (t == 0) t = 1;
+    return t > 64 ? 64 : t;
+}
+
+/* Strings of hits [lo, hi) appended at pool + base (only when they fit); str_off[lo + 1 .. hi] filled (str_off[lo] must
+ * hold base).  Returns the new end offset, or UINT64_MAX for a malformed hit record. */
+static uint64_t format_range(const Fmt &F, uint32_t lo, uint32_t hi, uint64_t base, char *pool, size_t pool_cap, uint64_t *str_off)
+{
+    const unsigned threads = fmt_threads();
+    const uint32_t n = hi - lo;
+    std::vector<uint64_t> part(threads + 1, 0);
+    std::vector<int> bad(threads, 0);
+    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {       /* pass 1: lengths, per-range totals */
+        uint64_t sum = 0;
+        for (uint32_t i = lo + a; i < lo + b; i++) {
+            const size_t len = F.one(i, nullptr);
+            if (len == (size_t)-1) { bad[t] = 1; str_off[i + 1] = 0; continue; }
+            str_off[i + 1] = len;
+            sum += len;
+        }
+        part[t + 1] = sum;
+    });
+    for (unsigned t = 0; t < threads; t++) if (bad[t]) return UINT64_MAX;
+    part[0] = base;
+    for (unsigned t = 0; t < threads; t++) part[t + 1] += part[t];
+    const uint64_t end = part[threads];
+    const bool fits = end <= pool_cap && (pool || end == 0);
+    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {       /* pass 2: offsets, then the characters */
+        uint64_t at = part[t];                        /* (a serial run is range 0) */
+        for (uint32_t i = lo + a; i < lo + b; i++) {
+            const uint64_t len = str_off[i + 1];
+            if (fits && len) F.one(i, pool + at);
+            at += len;
+            str_off[i + 1] = at;
+        }
+    });
+    return end;
+}
 
 extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
                                const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
                                char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
 {
-    if (!h || !str_off || !pool_used) return SDB_E_ARG;
-    const SdbTblHeader *hd = reinterpret_cast<const SdbTblHeader *>(h->blob.data());
-    const bool pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
-    /* table-order index -> pulse row (for preamble / flags) */
-    std::vector<const SdbPulseProto *> row(hd->nproto, nullptr);
-    if (pulse) {
-        const SdbPulseProto *tab = reinterpret_cast<const SdbPulseProto *>(h->blob.data() + (kind == SDB_KIND_MS ? hd->off_ms : hd->off_mu));
-        uint32_t cnt = kind == SDB_KIND_MS ? hd->n_ms : hd->n_mu;
-        for (uint32_t i = 0; i < cnt; i++) row[tab[i].proto] = &tab[i];
-    }
-    size_t used = 0;
-    auto put = [&](char c) { if (used < pool_cap) pool[used] = c; used++; };
-    auto put_str = [&](const char *s) { while (*s) put(*s++); };
-    auto put_hex = [&](const uint32_t *w, uint32_t nb, bool strip) {
-        uint32_t nd = (nb + 3) >> 2;                      /* right-aligned nibbles, helpers.py:28-64 */
-        for (uint32_t j = 0; j < nd; j++) {
-            int b0 = (int)nb - 4 * (int)(nd - j), v = 0;
-            for (int k = 0; k < 4; k++) { int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
-            if (strip && v == 0) continue;
-            strip = false;
-            put("0123456789ABCDEF"[v]);
-        }
-    };
-    if (!pulse) {
-        /* MC: preamble + hex, or preamble + repr(list) for TFA (manchester.py:131-132, :713-717)
-         * MN: the converter's own string (helpers.py:223-716), no preamble (sd_protocols.py:151-155) */
-        const SdbHexProto *hx = reinterpret_cast<const SdbHexProto *>(h->blob.data() + hd->off_hex);
-        char num[64];
-        for (uint32_t i = 0; i < nhits; i++) {
-            str_off[i] = used;
-            const SdbHit &ht = hits[i];
-            if (ht.proto >= hd->nproto) return SDB_E_ARG;
-            const SdbHexProto &p = hx[ht.proto];
-            const uint32_t *w = bits + ht.bits_off;
-            if (kind == SDB_KIND_MC) {
-                if (ht.flags & SDB_HIT_LIST) {
-                    if (ht.aux != 0) continue;           /* the first element of a list carries the whole string */
-                    for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
-                    put('[');
-                    for (uint32_t e = i; e < nhits && hits[e].msg == ht.msg && (hits[e].flags & SDB_HIT_LIST) && hits[e].aux == e - i; e++) {
-                        if (e > i) { put(','); put(' '); }
-                        put('\'');
-                        put_hex(bits + hits[e].bits_off, hits[e].nbits, false);
-                        put('\'');
-                    }
-                    put(']');
-                } else {
-                    for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
-                    put_hex(w, ht.nbits, false);
-                }
-            } else if (ht.flags & SDB_HIT_FIELDS) {
-                if (ht.aux == SDB_M_PCA301) {              /* MN hits carry the converter that produced them in aux */
-                    snprintf(num, sizeof num, "OK 24 %u %u %u %u %u %u %u %u %u %u %04X", w[0], w[1], w[2], w[3], w[4],
-                             w[5], w[6], w[7], w[8], w[9], w[10]);
-                    put_str(num);
-                } else {
-                    snprintf(num, sizeof num, "OK 9 %u %u %u %u %u", w[0], w[1], w[2], w[3], w[4]);
-                    put_str(num);
-                }
-            } else {
-                if (ht.aux == SDB_M_KOPP) put_str("kr");
-                put_hex(w, ht.nbits, false);
+    if (!h || !str_off || !pool_used || (nhits && !hits)) return SDB_E_ARG;
+    Fmt F;
+    if (fmt_init(F, h, kind) != SDB_OK) return SDB_E_ARG;
+    F.hits = hits; F.nhits = nhits; F.bits = bits;
+    str_off[0] = 0;
+    const uint64_t end = format_range(F, 0, nhits, 0, pool, pool_cap, str_off);
+    if (end == UINT64_MAX) return SDB_E_ARG;
+    *pool_used = (size_t)end;
+    return end <= pool_cap && (pool || end == 0) ? SDB_OK : SDB_E_OVERFLOW;
+}
+
+/* ---- decode + payload strings in one pipelined call --------------------------------------- */
+struct FmtSink {
+    Fmt F;
+    int device = 0;
+    char *pool = nullptr; size_t cap = 0; uint64_t *str_off = nullptr;
+    uint64_t at = 0;                 /* end of the strings written so far */
+    uint32_t done = 0;               /* hits formatted so far */
+    bool bad = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::pair<uint32_t, cudaEvent_t>> jobs;
+    bool closing = false;
+    std::thread worker;
+
+    void run()
+    {
+        cudaSetDevice(device);
+        for (;;) {
+            std::pair<uint32_t, cudaEvent_t> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return closing || !jobs.empty(); });
+                if (jobs.empty()) return;
+                job = jobs.front();
+                jobs.pop_front();
             }
+            if (job.second && cudaEventSynchronize(job.second) != cudaSuccess) { bad = true; continue; }
+            if (job.first <= done || bad) continue;
+            F.nhits = job.first;
+            const uint64_t end = format_range(F, done, job.first, at, pool, cap, str_off);
+            if (end == UINT64_MAX) { bad = true; continue; }
+            at = end;
+            done = job.first;
         }
-        str_off[nhits] = used;
-        *pool_used = used;
-        return used > pool_cap ? SDB_E_OVERFLOW : SDB_OK;
     }
-    for (uint32_t i = 0; i < nhits; i++) {
-        str_off[i] = used;
-        const SdbHit &ht = hits[i];
-        const uint32_t *w = bits + ht.bits_off;
-        const uint32_t nb = ht.nbits, nwv = (nb + 31) >> 5;
-        const SdbPulseProto *pp = pulse && ht.proto < hd->nproto ? row[ht.proto] : nullptr;
-        if (pulse && !pp) return SDB_E_ARG;
-        if (pp) for (int k = 0; k < pp->pre_len; k++) put(pp->preamble[k]);
-        const bool has_f = (ht.flags & SDB_HIT_HAS_F) != 0;
-        if (pp && (pp->flags & SDB_PF_DISPATCH_BIN)) {
-            for (uint32_t b = 0; b < nb; b++) put(has_f && hbit(w + nwv, b) ? 'F' : (char)('0' + hbit(w, b)));
-        } else if (has_f) {
-            put('N'); put('o'); put('n'); put('e');       /* f"{None}" (message_unsynced.py:267,274) */
-        } else {
-            uint32_t nd = (nb + 3) >> 2;
-            bool strip = pp && (pp->flags & SDB_PF_REMOVE_ZERO);
-            for (uint32_t j = 0; j < nd; j++) {
-                int b0 = (int)nb - 4 * (int)(nd - j), v = 0;
-                for (int k = 0; k < 4; k++) { int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
-                if (strip && v == 0) continue;
-                strip = false;
-                put("0123456789ABCDEF"[v]);
-            }
-        }
-        if (pp) for (int k = 0; k < pp->post_len; k++) put(pp->postamble[k]);
+    void close()
+    {
+        { std::lock_guard<std::mutex> lk(mu); closing = true; }
+        cv.notify_all();
+        if (worker.joinable()) worker.join();
     }
-    str_off[nhits] = used;
-    *pool_used = used;
-    return used > pool_cap ? SDB_E_OVERFLOW : SDB_OK;
+};
+static void sink_push(FmtSink *s, uint32_t hits_end, cudaEvent_t arrived)
+{
+    { std::lock_guard<std::mutex> lk(s->mu); s->jobs.emplace_back(hits_end, arrived); }
+    s->cv.notify_one();
+}
+
+extern "C" int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
+                                       const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                                       SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                                       uint32_t *bits, uint32_t bits_cap, SdbCounters *counters,
+                                       char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
+{
+    if (!h) return SDB_E_ARG;
+    if (!str_off || !pool_used || !hits || !bits) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
+    FmtSink sink;
+    if (fmt_init(sink.F, h, kind) != SDB_OK) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
+    sink.F.hits = hits; sink.F.bits = bits;
+    sink.device = h->device; sink.pool = pool; sink.cap = pool_cap; sink.str_off = str_off;
+    str_off[0] = 0;
+    *pool_used = 0;
+    sink.worker = std::thread([&sink] { sink.run(); });
+    bool fed = false;
+    const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink, &fed);
+    if (rc == SDB_OK && !fed) sink_push(&sink, counters->hits, nullptr);      /* single-stage path: everything is on the host already */
+    sink.close();
+    if (rc != SDB_OK) return rc;
+    if (sink.bad || sink.done != counters->hits) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: malformed hit records");
+    *pool_used = (size_t)sink.at;
+    if (sink.at > pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
+    return SDB_OK;
 }
 
 /* ---- unit ops ----------------------------------------------------------------------------- */

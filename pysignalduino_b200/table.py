@@ -297,6 +297,12 @@ class CompiledTable:
         # Empty for the shipped table; a user-edited table degrades per protocol instead of failing engine creation.
         self.unsupported = unsupported or {}
 
+    def pulse_rows(self, kind: str) -> np.ndarray:
+        """The compiled MS / MU protocol rows (PULSEPROTO_DTYPE) as a read-only view of the blob."""
+        hdr = np.frombuffer(self.blob, dtype=HEADER_DTYPE, count=1)[0]
+        n, off = (int(hdr["n_ms"]), int(hdr["off_ms"])) if kind == "MS" else (int(hdr["n_mu"]), int(hdr["off_mu"]))
+        return np.frombuffer(self.blob, dtype=PULSEPROTO_DTYPE, count=n, offset=off)
+
 
 class _RankPool:
     def __init__(self):

@@ -132,3 +132,41 @@ def test_pure_helpers(protocols):
     assert protocols.length_in_range("nope", 1) == (0, "protocol does not exists")
     assert protocols.dec_2_bin_ppari(32) == "001000001"
     assert protocols.mc2dmc("1010") == "000"
+
+
+def test_demod_host_payloads_equals_decode_then_format(sdp, corpus):
+    """sdb_demod_host_payloads (decode + payload strings, formatted per pipeline stage on the host threads) returns exactly
+    what sdb_demod_host followed by sdb_format_hits returns — multi-stage (pipelined) and single-stage batches."""
+    import numpy as np
+
+    from pysignalduino_b200 import pack
+
+    eng = sdp.engine()
+    for kind, n in ((pack.KIND_MU, 300_000), (pack.KIND_MS, 270_000), (pack.KIND_MU, 1000), (pack.KIND_MC, 5000)):
+        b = corpus.pulse(kind, n) if kind <= 1 else corpus.hexmsgs(kind, n)
+        ref = eng.demod_host(b, mc_repaired=True)
+        pool_ref, off_ref = eng.format_hits(kind, ref.hits, ref.bits)
+        nh, nw = len(ref.hits), len(ref.bits)
+        out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
+        hits = np.zeros(nh + 8, dtype=pack.HIT_DTYPE)
+        bits = np.zeros(nw + 8, dtype=np.uint32)
+        ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
+        pool = np.zeros(len(pool_ref) + 16, dtype=np.uint8)
+        off = np.zeros(len(hits) + 1, dtype=np.uint64)
+        rc, used = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
+                                                pool, off, mc_repaired=True)
+        assert rc == 0 and int(ctr["hits"][0]) == nh and used == len(pool_ref)
+        # hit order differs between runs (atomics), so compare per message: the strings of message m in hit order
+        def per_message(o, hh, pl, of):
+            res = {}
+            for m in np.nonzero(o["nhits"])[0][:: max(1, n // 3000)]:
+                h0, k = int(o["hit_off"][m]), int(o["nhits"][m])
+                res[int(m)] = [bytes(pl[int(of[i]) : int(of[i + 1])]) for i in range(h0, h0 + k)]
+            return res
+        got = per_message(out, hits, pool, off)
+        exp = per_message(ref.out, ref.hits, np.frombuffer(pool_ref, dtype=np.uint8), off_ref)
+        assert got == exp and len(got) > 100
+        small = np.zeros(8, dtype=np.uint8)
+        rc, used2 = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
+                                                 small, off, mc_repaired=True)
+        assert rc == -3 and used2 == len(pool_ref)              # SDB_E_OVERFLOW reports the size needed
