@@ -431,14 +431,17 @@ def run_ours(args):
         t_bits = torch.empty(4 * s["bits_cap"], dtype=torch.uint8).pin_memory()
         t_ctr = torch.zeros(16, dtype=torch.uint8).pin_memory()
         c = ctrs[s["name"]]
+        t_pool = torch.empty(int(c[0]) * 48 + 4096, dtype=torch.uint8).pin_memory()
+        t_off = torch.empty(4 * s["hits_cap"], dtype=torch.uint8).pin_memory()
         host.append({
-            "kind": s["kind"], "keep": (t_msgs, t_dig, t_out, t_hits, t_bits, t_ctr), "msgs": msgs, "digits": digits,
+            "kind": s["kind"], "keep": (t_msgs, t_dig, t_out, t_hits, t_bits, t_ctr, t_pool, t_off), "msgs": msgs, "digits": digits,
             "out": t_out.numpy().view(pack.MSGOUT_DTYPE), "hits": t_hits.numpy().view(pack.HIT_DTYPE),
             "bits": t_bits.numpy().view(np.uint32), "ctr": t_ctr.numpy().view(pack.COUNTERS_DTYPE),
-            "pool": np.empty(int(c[0]) * 40 + 4096, dtype=np.uint8), "off": np.empty(s["hits_cap"] + 1, dtype=np.uint64), "used": 0,
+            "pool": t_pool.numpy(), "off": t_off.numpy().view(np.uint32), "used": 0,
         })
         h2d += msgs.nbytes + digits.nbytes
-        d2h += 8 * s["n"] + 16 + 16 * int(c[0]) + 4 * int(c[1])
+        # result slots + counters + hits + string offsets + strings (MS / MU; counted after the first e2e step) | + bit arena (MC / MN)
+        d2h += 8 * s["n"] + 16 + (16 + 4) * int(c[0]) + (4 * int(c[1]) if s["kind"] >= 2 else 0)
 
     def e2e_step(nmsgs=None):
         for i, hs in enumerate(host):
@@ -446,8 +449,8 @@ def run_ours(args):
             if nmsgs is not None and nmsgs[i] < len(msgs):
                 msgs = msgs[: nmsgs[i]]
                 digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
-            rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], hs["bits"], hs["ctr"], hs["pool"],
-                                                    hs["off"], mc_repaired=True)
+            rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], hs["bits"] if hs["kind"] >= 2 else None,
+                                                    hs["ctr"], hs["pool"], hs["off"], mc_repaired=True)
             if rc != 0:
                 raise SystemExit("bench.py: e2e arena / payload pool overflow")
             hs["used"] = used
@@ -464,6 +467,7 @@ def run_ours(args):
     t_e2e = timed_e2e()
     e2e_value = world * M * args.steps / t_e2e
     payload_bytes = int(sum(hs["used"] for hs in host))
+    d2h += int(sum(hs["used"] for hs in host if hs["kind"] <= 1))          # MS / MU strings come back from the device
 
     # device-resident and host-buffer runs must agree (same hits, same words)
     for s, hs in zip(slots, host):
@@ -662,7 +666,7 @@ def run_ours(args):
             raw = ora.run_pulse_raw(sub, nthreads=threads) if sl["kind"] <= 1 else ora.run_hex_raw(sub, mc_repaired=True, nthreads=threads)
             t_port += time.perf_counter() - t0
             res = sdp.demodulate_packed(sub)
-            why = compare_raw(sdp, sub, res, *raw)
+            why = compare_raw(sdp, sub, res, *raw, check_bits=sl["kind"] <= 1)      # MC / MN oracle hits carry no bit length
             if why:
                 raise SystemExit(f"bench.py: PARITY FAILURE against the oracle port, class {sl['name']}: {why}")
             checked_port += c
@@ -711,7 +715,8 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "payload_bytes_per_step": payload_bytes,
-                "includes": "pinned H2D, kernels, D2H of result slots / hits / bits, and the payload string of every hit (preamble + hex + postamble) formatted on the host threads under the next stage's kernels"},
+                "includes": "pinned H2D, decode kernels, the payload string of every hit (preamble + hex + postamble; MS / MU by the device format "
+                            "kernel of each pipeline stage, MC / MN on the host), D2H of result slots / hits / string offsets / strings"},
         "gpu_launches": args.steps * launches(full),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "per_kernel": per_kernel,
         "hit_histogram": {"protocols_with_hits": int((hist > 0).sum()), "total_hits": int(hist.sum()), "ranks": world,

@@ -187,17 +187,18 @@ int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
                    uint32_t *bits, uint32_t bits_cap, SdbCounters *counters);
 
 /*
- * sdb_demod_host plus the payload string of every hit (sdb_format_hits) in one call: the strings of a pipeline stage are
- * formatted on the host threads while the GPU decodes the following stages, so the caller gets what
- * SDProtocols.demodulate() returns — protocol, bit length and payload text — at the cost of the decode alone.
- * pool / str_off as in sdb_format_hits (str_off has hits_cap + 1 entries); SDB_E_OVERFLOW when an arena or the pool is too
- * small (counters / *pool_used say how much is needed).
+ * sdb_demod_host plus the payload string of every hit in one call: what SDProtocols.demodulate() returns per hit is a
+ * string (preamble + hex / bits + postamble, message_synced.py:224-231, message_unsynced.py:254-274, manchester.py:131-132).
+ * MS / MU: a format kernel runs after the decode kernels of every pipeline stage and the strings travel back with the hits
+ * under the next stage's kernels; `bits` may be NULL (the bit arena is then not copied back).  MC / MN: formatted on the
+ * host.  Hit i's string starts at pool[str_off[i]] and is NUL-terminated (str_off has hits_cap entries; the pool is NOT in
+ * hit order).  SDB_E_OVERFLOW when an arena or the pool is too small (counters / *pool_used say how much is needed).
  */
 int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
                             const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                             SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                             uint32_t *bits, uint32_t bits_cap, SdbCounters *counters,
-                            char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used);
+                            char *pool, size_t pool_cap, uint32_t *str_off, size_t *pool_used);
 
 /*
  * Host-side result formatting (the payload string of every hit:

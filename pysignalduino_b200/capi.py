@@ -18,6 +18,8 @@ import os
 
 CHECKED = os.environ.get("SDB200_CHECKED") == "1"      # use the bounds-check build (libsdb200_chk.so)
 LIB_PATH = Path(__file__).resolve().parent / ("libsdb200_chk.so" if CHECKED else "libsdb200.so")
+if os.environ.get("SDB200_LIB"):                       # an experiment variant built with build_ext.py -D... --out=...
+    LIB_PATH = Path(os.environ["SDB200_LIB"]).resolve()
 
 SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU = 0, -1, -2, -3, -4
 ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR, ST_DOMAIN = 0, 1, 2, 3, 4
@@ -72,7 +74,7 @@ def load_library() -> C.CDLL:
     L.sdb_demod_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                  C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdb_demod_host_payloads.restype = C.c_int
-    L.sdb_demod_host_payloads.argtypes = L.sdb_demod_host.argtypes + [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+    L.sdb_demod_host_payloads.argtypes = list(L.sdb_demod_host.argtypes) + [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
     L.sdb_format_hits.restype = C.c_int
     L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.POINTER(C.c_size_t)]
@@ -274,17 +276,43 @@ class Engine:
         return rc
 
     def demod_host_payloads_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, hits: np.ndarray,
-                                 bits: np.ndarray, ctr: np.ndarray, pool: np.ndarray, off: np.ndarray, mc_repaired: bool = False):
-        """Decode + payload strings in one pipelined call with caller-owned arrays (``pool`` uint8, ``off`` uint64[len(hits) + 1]);
-        returns (raw code, pool bytes used)."""
+                                 bits: Optional[np.ndarray], ctr: np.ndarray, pool: np.ndarray, off: np.ndarray,
+                                 mc_repaired: bool = False):
+        """Decode + payload strings in one pipelined call with caller-owned (ideally pinned) arrays: ``pool`` uint8, ``off``
+        uint32[len(hits)]; hit i's string starts at ``pool[off[i]]`` and is NUL-terminated.  ``bits`` may be None for MS / MU
+        (the bit arena then stays on the device).  Returns (raw code, pool bytes used)."""
         used = C.c_size_t(0)
         rc = self.lib.sdb_demod_host_payloads(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
                                               digits.nbytes, len(msgs), out.ctypes.data, hits.ctypes.data, len(hits),
-                                              bits.ctypes.data, len(bits), ctr.ctypes.data, pool.ctypes.data, pool.nbytes,
-                                              off.ctypes.data, C.byref(used))
+                                              bits.ctypes.data if bits is not None else None,
+                                              len(bits) if bits is not None else max(4096, 4 * len(hits)), ctr.ctypes.data,
+                                              pool.ctypes.data, pool.nbytes, off.ctypes.data, C.byref(used))
         if rc not in (SDB_OK, SDB_E_OVERFLOW):
             raise self._err(rc, "sdb_demod_host_payloads")
         return rc, used.value
+
+    def demod_payloads(self, batch, mc_repaired: bool = False):
+        """Convenience form: -> (Result without bits for MS / MU, pool bytes, offsets uint32[nhits])."""
+        n = batch.n
+        kind = batch.kind
+        msgs = np.ascontiguousarray(batch.msgs)
+        digits = np.ascontiguousarray(batch.digits)
+        out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
+        ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
+        hits_cap, bits_cap, pool_cap = max(1024, 4 * n), max(4096, 16 * n), max(4096, 96 * n)
+        while True:
+            hits = np.empty(hits_cap, dtype=pack.HIT_DTYPE)
+            bits = np.empty(bits_cap, dtype=np.uint32)
+            pool = np.empty(pool_cap, dtype=np.uint8)
+            off = np.empty(hits_cap, dtype=np.uint32)
+            rc, used = self.demod_host_payloads_into(kind, msgs, digits, out, hits, bits, ctr, pool, off, mc_repaired=mc_repaired)
+            if rc == SDB_E_OVERFLOW:
+                hits_cap = max(hits_cap, int(ctr["hits"][0]) + 16)
+                bits_cap = max(bits_cap, int(ctr["words"][0]) + 16)
+                pool_cap = max(pool_cap, used + 64)
+                continue
+            nh = int(ctr["hits"][0])
+            return Result(kind, out, hits[:nh], bits[: int(ctr["words"][0])], ctr[0]), pool[:used], off[:nh]
 
     # ---- text lines (tokenizer kernel + demodulation) ---------------------------------------
     def demod_lines(self, kind: int, text: np.ndarray, line_off: np.ndarray, line_len: np.ndarray,
@@ -424,7 +452,7 @@ class Engine:
                                               digits.nbytes, dlen, C.byref(found), tgt.ctypes.data, len(tgt), C.byref(pos))
         if rc != SDB_OK:
             raise self._err(rc, "sdb_unit_pattern_exists")
-        return bool(found.value), [int(x) for x in tgt[: int(tpl["len"])]], pos.value
+        return bool(found.value), [int(x) for x in tgt[: int(tpl["len"].reshape(-1)[0])]], pos.value
 
     def debug_violations(self, reset: bool = False) -> int:
         """Out-of-range index count of the bounds-check build (0xFFFFFFFF from the normal build)."""

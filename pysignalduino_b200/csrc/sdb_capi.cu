@@ -11,14 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <condition_variable>
-#include <deque>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/sdb200.h"
+#include "sdb_fmt.h"
 #include "sdb_pulse.h"
 #include "sdb_table.h"
 
@@ -47,7 +45,12 @@ struct SdbHandle {
     cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
     std::vector<cudaEvent_t> ev_h2d, ev_done, ev_d2h;
     SdbCounters *h_snap = nullptr;      /* pinned: counters after each chunk (which arena ranges are final) */
+    uint32_t *h_used = nullptr;         /* pinned: payload-pool bytes in use after each chunk */
     uint32_t snap_cap = 0;
+    uint16_t *d_rowmap = nullptr;       /* [nproto] MS rows, then [nproto] MU rows: table-order protocol index -> row (format kernel) */
+    char *d_chars = nullptr;    size_t cap_chars = 0;     /* device payload pool of sdb_demod_host_payloads */
+    uint32_t *d_stroff = nullptr; size_t cap_stroff = 0;
+    uint32_t *d_fmt = nullptr;          /* [0] first hit not formatted yet, [1] scratch, [2] pool bytes handed out */
 };
 
 static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
@@ -104,6 +107,17 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     CKC(cudaMalloc(&h->d_blob, blob_len));
     CKC(cudaMemcpy(h->d_blob, blob, blob_len, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&h->d_ctr, sizeof(SdbCounters)));
+    CKC(cudaMalloc(&h->d_fmt, 4 * sizeof(uint32_t)));
+    {
+        /* protocol index -> pulse row, for the device formatter */
+        std::vector<uint16_t> map(2 * (size_t)hd->nproto, 0);
+        const SdbPulseProto *ms = reinterpret_cast<const SdbPulseProto *>(static_cast<const uint8_t *>(blob) + hd->off_ms);
+        const SdbPulseProto *mu = reinterpret_cast<const SdbPulseProto *>(static_cast<const uint8_t *>(blob) + hd->off_mu);
+        for (uint32_t i = 0; i < hd->n_ms; i++) if (ms[i].proto < hd->nproto) map[ms[i].proto] = (uint16_t)i;
+        for (uint32_t i = 0; i < hd->n_mu; i++) if (mu[i].proto < hd->nproto) map[hd->nproto + mu[i].proto] = (uint16_t)i;
+        CKC(cudaMalloc(&h->d_rowmap, map.size() * sizeof(uint16_t) + 16));
+        CKC(cudaMemcpy(h->d_rowmap, map.data(), map.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     CKC(cudaMalloc(&h->d_unit, 32768));
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -137,6 +151,8 @@ extern "C" void sdb_destroy(SdbHandle *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch); cudaFree(h->d_text); cudaFree(h->d_lines);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
+    cudaFree(h->d_rowmap); cudaFree(h->d_chars); cudaFree(h->d_stroff); cudaFree(h->d_fmt);
+    if (h->h_used) cudaFreeHost(h->h_used);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_d2h) cudaEventDestroy(e);
@@ -231,6 +247,9 @@ static int pipeline_prepare(SdbHandle *h, uint32_t nchunks)
         if (h->h_snap) cudaFreeHost(h->h_snap);
         h->h_snap = nullptr; h->snap_cap = 0;
         CK(cudaMallocHost(reinterpret_cast<void **>(&h->h_snap), sizeof(SdbCounters) * (size_t)(nchunks + 8)));
+        if (h->h_used) cudaFreeHost(h->h_used);
+        h->h_used = nullptr;
+        CK(cudaMallocHost(reinterpret_cast<void **>(&h->h_used), sizeof(uint32_t) * (size_t)(nchunks + 8)));
         h->snap_cap = nchunks + 8;
     }
     return SDB_OK;
@@ -239,11 +258,16 @@ static int pipeline_prepare(SdbHandle *h, uint32_t nchunks)
 /* Hits are appended through one atomic counter and the chunks run in stream order, so once chunk k is done the arena
  * ranges [done, snapshot k) are final: copy them to the host while the next chunk's kernels run, instead of one big
  * D2H after the last kernel (0.7 GB per 10 M mixed messages). */
-struct ArenaDrain { uint32_t hits = 0, words = 0; };
-struct FmtSink;                                           /* payload strings formatted on the host threads while later chunks run */
-static void sink_push(FmtSink *s, uint32_t hits_end, cudaEvent_t arrived);
+struct ArenaDrain { uint32_t hits = 0, words = 0, chars = 0; };
+/* sdb_demod_host_payloads: the strings of every stage are formatted on the device (sdb_format.cu) right after its decode
+ * kernels and copied back with the hits, under the next stage's kernels */
+struct PayloadSink {
+    char *pool = nullptr; uint32_t pool_cap = 0;
+    uint32_t *str_off = nullptr;
+    uint32_t used = 0;
+};
 static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, uint32_t hits_cap, uint32_t *bits, uint32_t bits_cap,
-                       FmtSink *sink = nullptr)
+                       PayloadSink *sink = nullptr)
 {
     CK(cudaEventSynchronize(h->ev_done[k]));            /* chunk k + 1 is already queued: the GPU stays busy */
     const SdbCounters c = h->h_snap[k];
@@ -252,18 +276,37 @@ static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, ui
         CK(cudaMemcpyAsync(hits + d.hits, h->d_hits + d.hits, sizeof(SdbHit) * (size_t)(c.hits - d.hits), cudaMemcpyDeviceToHost, h->d2h_stream));
     if (c.words > d.words && bits)
         CK(cudaMemcpyAsync(bits + d.words, h->d_bits + d.words, sizeof(uint32_t) * (size_t)(c.words - d.words), cudaMemcpyDeviceToHost, h->d2h_stream));
-    d.hits = c.hits; d.words = c.words;
     if (sink) {
-        CK(cudaEventRecord(h->ev_d2h[k], h->d2h_stream));
-        sink_push(sink, c.hits, h->ev_d2h[k]);          /* hits [.., c.hits) and their bits are final and on their way */
+        const uint32_t used = h->h_used[k];
+        sink->used = used;
+        if (used <= sink->pool_cap) {
+            if (c.hits > d.hits)
+                CK(cudaMemcpyAsync(sink->str_off + d.hits, h->d_stroff + d.hits, sizeof(uint32_t) * (size_t)(c.hits - d.hits), cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (used > d.chars)
+                CK(cudaMemcpyAsync(sink->pool + d.chars, h->d_chars + d.chars, (size_t)(used - d.chars), cudaMemcpyDeviceToHost, h->d2h_stream));
+            d.chars = used;
+        }
     }
+    d.hits = c.hits; d.words = c.words;
+    return SDB_OK;
+}
+
+/* format kernel of the stage just decoded + snapshot of the pool counter (payload mode, MS / MU) */
+static int enqueue_format(SdbHandle *h, int kind, uint32_t hits_cap, uint32_t bits_cap, PayloadSink *sink, uint32_t k, cudaStream_t st)
+{
+    const SdbPulseProto *rows = kind == SDB_KIND_MS ? h->tab.ms : h->tab.mu;
+    const uint16_t *map = h->d_rowmap + (kind == SDB_KIND_MS ? 0 : h->tab.nproto);
+    int rc = sdb::launch_format(h->d_hits, h->d_bits, rows, map, h->tab.nproto, h->d_fmt, h->d_ctr, hits_cap, bits_cap, h->d_chars,
+                                sink->pool_cap, h->d_stroff, h->d_fmt + 2, h->sm_count * 8, st);
+    if (rc != 0) return set_err(h, SDB_E_CUDA, "format kernel launch", static_cast<cudaError_t>(rc));
+    CK(cudaMemcpyAsync(&h->h_used[k], h->d_fmt + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return SDB_OK;
 }
 
 static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
                            const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                            SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
-                           uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, FmtSink *sink, bool *sink_fed)
+                           uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, PayloadSink *sink)
 {
     if (!h) return SDB_E_ARG;
     if (!counters || (n && (!msgs || !digits || !out))) return set_err(h, SDB_E_ARG, "sdb_demod_host: null pointer");
@@ -280,6 +323,12 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
     if ((rc = grow(h, h->d_hits, h->cap_hits, sizeof(SdbHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
     if ((rc = grow(h, h->d_bits, h->cap_bits, sizeof(uint32_t) * (size_t)(bits_cap ? bits_cap : 1)))) return rc;
     cudaStream_t st = h->stream;
+    if (sink) {                                               /* payload mode (MS / MU): device pool + one offset per hit */
+        if ((rc = grow(h, h->d_chars, h->cap_chars, (size_t)sink->pool_cap + 16))) return rc;
+        if ((rc = grow(h, h->d_stroff, h->cap_stroff, sizeof(uint32_t) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
+        if ((rc = pipeline_prepare(h, 1))) return rc;
+        CK(cudaMemsetAsync(h->d_fmt, 0, 4 * sizeof(uint32_t), st));
+    }
     const SdbPulseMsg *pm = static_cast<const SdbPulseMsg *>(msgs);
     /* Pipelined path (MS / MU, several chunks): the H2D copy of chunk k+1 and the D2H copy of the result slots of
      * chunk k-1 overlap the kernels of chunk k.  Needs the digit streams stored in message order (doff non-decreasing),
@@ -311,6 +360,7 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
             CK(cudaStreamWaitEvent(st, h->ev_h2d[k], 0));
             rc = enqueue_pulse(h, kind, dm + lo, h->d_digits, cnt, lo, h->d_out + lo, h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
             if (rc != SDB_OK) return rc;
+            if (sink && (rc = enqueue_format(h, kind, hits_cap, bits_cap, sink, k, st))) return rc;
             CK(cudaMemcpyAsync(&h->h_snap[k], h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev_done[k], st));
             CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[k], 0));
@@ -318,7 +368,6 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
             if (k && (rc = drain_chunk(h, k - 1, drain, hits, hits_cap, bits, bits_cap, sink))) return rc;
         }
         if ((rc = drain_chunk(h, nchunks - 1, drain, hits, hits_cap, bits, bits_cap, sink))) return rc;
-        if (sink_fed) *sink_fed = true;
         *counters = h->h_snap[nchunks - 1];
         CK(cudaStreamSynchronize(h->d2h_stream));
         if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
@@ -333,13 +382,21 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
             rc = sdb_demod_hex_device(h, kind, mc_repaired, static_cast<const SdbHexMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
                                       h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
         if (rc != SDB_OK) return rc;
+        if (sink && pulse && (rc = enqueue_format(h, kind, hits_cap, bits_cap, sink, 0, st))) return rc;
         CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
-    if (counters->hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
-    if (counters->words) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
+    if (counters->hits && hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
+    if (counters->words && bits) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
+    if (sink && pulse) {
+        sink->used = h->h_used[0];
+        if (sink->used <= sink->pool_cap) {
+            if (counters->hits) CK(cudaMemcpyAsync(sink->str_off, h->d_stroff, sizeof(uint32_t) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
+            if (sink->used) CK(cudaMemcpyAsync(sink->pool, h->d_chars, sink->used, cudaMemcpyDeviceToHost, st));
+        }
+    }
     CK(cudaStreamSynchronize(st));
     return SDB_OK;
 }
@@ -349,7 +406,8 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
                               SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                               uint32_t *bits, uint32_t bits_cap, SdbCounters *counters)
 {
-    return demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr, nullptr);
+    if (n && (!hits || !bits)) return h ? set_err(h, SDB_E_ARG, "sdb_demod_host: null pointer") : SDB_E_ARG;
+    return demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr);
 }
 
 extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
@@ -474,16 +532,7 @@ struct Fmt {
         if (pulse) {
             const SdbPulseProto *pp = row[ht.proto];
             if (!pp) return (size_t)-1;
-            const uint32_t nb = ht.nbits, nwv = (nb + 31) >> 5;
-            const bool has_f = (ht.flags & SDB_HIT_HAS_F) != 0;
-            for (int k = 0; k < pp->pre_len; k++) put(pp->preamble[k]);
-            if (pp->flags & SDB_PF_DISPATCH_BIN) {
-                for (uint32_t b = 0; b < nb; b++) put(has_f && hbit(w + nwv, b) ? 'F' : (char)('0' + hbit(w, b)));
-            } else if (has_f) {
-                put('N'); put('o'); put('n'); put('e');       /* f"{None}" (message_unsynced.py:267,274) */
-            } else put_hex(w, nb, (pp->flags & SDB_PF_REMOVE_ZERO) != 0);
-            for (int k = 0; k < pp->post_len; k++) put(pp->postamble[k]);
-            return n;
+            return sdb_fmt_pulse(pp, ht, w, dst);         /* sdb_fmt.h: the same code the device formatter runs */
         }
         /* MC: preamble + hex, or preamble + repr(list) for TFA (manchester.py:131-132, :713-717)
          * MN: the converter's own string (helpers.py:223-716), no preamble (sd_protocols.py:151-155) */
@@ -502,7 +551,8 @@ struct Fmt {
                 put(']');
             } else {
                 for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
-                put_hex(w, ht.nbits, false);
+                if (ht.flags & SDB_HIT_HAS_F) { put('N'); put('o'); put('n'); put('e'); }      /* f"{preamble}{None}" (as-shipped mcRaw) */
+                else put_hex(w, ht.nbits, false);
             }
         } else if (ht.flags & SDB_HIT_FIELDS) {
             char num[96];
@@ -593,6 +643,38 @@ static uint64_t format_range(const Fmt &F, uint32_t lo, uint32_t hi, uint64_t ba
     return end;
 }
 
+/* NUL-terminated variant with one 32-bit offset per hit (the layout sdb_demod_host_payloads returns) */
+static uint64_t format_range_nul(const Fmt &F, uint32_t n, char *pool, size_t pool_cap, uint32_t *str_off)
+{
+    const unsigned threads = fmt_threads();
+    std::vector<uint64_t> part(threads + 1, 0);
+    std::vector<int> bad(threads, 0);
+    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {
+        uint64_t sum = 0;
+        for (uint32_t i = a; i < b; i++) {
+            const size_t len = F.one(i, nullptr);
+            if (len == (size_t)-1) { bad[t] = 1; continue; }
+            str_off[i] = (uint32_t)len;
+            sum += len + 1;
+        }
+        part[t + 1] = sum;
+    });
+    for (unsigned t = 0; t < threads; t++) if (bad[t]) return UINT64_MAX;
+    for (unsigned t = 0; t < threads; t++) part[t + 1] += part[t];
+    const uint64_t end = part[threads];
+    const bool fits = end <= pool_cap && end < 0xFFFFFFF0ull;
+    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {
+        uint64_t at = part[t];
+        for (uint32_t i = a; i < b; i++) {
+            const uint32_t len = str_off[i];
+            if (fits) { if (len) F.one(i, pool + at); pool[at + len] = 0; }
+            str_off[i] = (uint32_t)at;
+            at += (uint64_t)len + 1;
+        }
+    });
+    return end;
+}
+
 extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
                                const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
                                char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
@@ -609,76 +691,38 @@ extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
 }
 
 /* ---- decode + payload strings in one pipelined call --------------------------------------- */
-struct FmtSink {
-    Fmt F;
-    int device = 0;
-    char *pool = nullptr; size_t cap = 0; uint64_t *str_off = nullptr;
-    uint64_t at = 0;                 /* end of the strings written so far */
-    uint32_t done = 0;               /* hits formatted so far */
-    bool bad = false;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::deque<std::pair<uint32_t, cudaEvent_t>> jobs;
-    bool closing = false;
-    std::thread worker;
-
-    void run()
-    {
-        cudaSetDevice(device);
-        for (;;) {
-            std::pair<uint32_t, cudaEvent_t> job;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return closing || !jobs.empty(); });
-                if (jobs.empty()) return;
-                job = jobs.front();
-                jobs.pop_front();
-            }
-            if (job.second && cudaEventSynchronize(job.second) != cudaSuccess) { bad = true; continue; }
-            if (job.first <= done || bad) continue;
-            F.nhits = job.first;
-            const uint64_t end = format_range(F, done, job.first, at, pool, cap, str_off);
-            if (end == UINT64_MAX) { bad = true; continue; }
-            at = end;
-            done = job.first;
-        }
-    }
-    void close()
-    {
-        { std::lock_guard<std::mutex> lk(mu); closing = true; }
-        cv.notify_all();
-        if (worker.joinable()) worker.join();
-    }
-};
-static void sink_push(FmtSink *s, uint32_t hits_end, cudaEvent_t arrived)
-{
-    { std::lock_guard<std::mutex> lk(s->mu); s->jobs.emplace_back(hits_end, arrived); }
-    s->cv.notify_one();
-}
-
 extern "C" int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
                                        const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                                        SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                                        uint32_t *bits, uint32_t bits_cap, SdbCounters *counters,
-                                       char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
+                                       char *pool, size_t pool_cap, uint32_t *str_off, size_t *pool_used)
 {
     if (!h) return SDB_E_ARG;
-    if (!str_off || !pool_used || !hits || !bits) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
-    FmtSink sink;
-    if (fmt_init(sink.F, h, kind) != SDB_OK) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
-    sink.F.hits = hits; sink.F.bits = bits;
-    sink.device = h->device; sink.pool = pool; sink.cap = pool_cap; sink.str_off = str_off;
-    str_off[0] = 0;
+    if (!str_off || !pool_used || !hits || (pool_cap && !pool)) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
     *pool_used = 0;
-    sink.worker = std::thread([&sink] { sink.run(); });
-    bool fed = false;
-    const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink, &fed);
-    if (rc == SDB_OK && !fed) sink_push(&sink, counters->hits, nullptr);      /* single-stage path: everything is on the host already */
-    sink.close();
+    const bool pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
+    if (pulse) {
+        /* MS / MU: format kernel per stage, strings instead of the bit arena on the wire (bits may be NULL) */
+        PayloadSink sink;
+        sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.str_off = str_off;
+        const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink);
+        *pool_used = sink.used;
+        if (rc != SDB_OK) return rc;
+        if (sink.used > sink.pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
+        return SDB_OK;
+    }
+    /* MC / MN: few hits, list / decimal renderings — formatted on the host from the bit arena */
+    std::vector<uint32_t> tmp_bits;
+    if (!bits) { tmp_bits.resize(bits_cap ? bits_cap : 1); bits = tmp_bits.data(); }
+    int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr);
     if (rc != SDB_OK) return rc;
-    if (sink.bad || sink.done != counters->hits) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: malformed hit records");
-    *pool_used = (size_t)sink.at;
-    if (sink.at > pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
+    Fmt F;
+    if (fmt_init(F, h, kind) != SDB_OK) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
+    F.hits = hits; F.nhits = counters->hits; F.bits = bits;
+    const uint64_t end = format_range_nul(F, counters->hits, pool, pool_cap, str_off);
+    if (end == UINT64_MAX) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: malformed hit records");
+    *pool_used = (size_t)end;
+    if (end > pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
     return SDB_OK;
 }
 

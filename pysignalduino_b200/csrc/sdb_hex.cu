@@ -308,6 +308,16 @@ __device__ int mc_one(const HArgs &A, SdbMsgOut &mo, uint32_t mi, const SdbHexMs
     if (p.method == SDB_M_NONE) { mo.reason = SDB_MCR_NO_METHOD; return SDB_ST_VALUEERROR; }   /* :109 1-list cannot unpack into 3 */
     if (p.method == SDB_M_UNKNOWN) { mo.reason = SDB_MCR_UNKNOWN_METHOD; return SDB_ST_OK; }  /* :121-123 */
     if (m.hlen == 0) return SDB_ST_TYPEERROR;                            /* hex_to_bin_str('') is None -> len(None) */
+    if (!A.repaired && p.method == SDB_M_MCRAW_MANCHESTER) {
+        /* :120 passes self twice; mcRaw has a spare parameter, so the call works with shifted arguments (:588-613):
+         * bit_data = the name, protocol_id = the bit string (no such id: length_max 0), mcbitnum = int(protocol id) */
+        if (p.pid_int == 0) return SDB_ST_VALUEERROR;                    /* int('13.2') */
+        if (p.pid_int == 1) { mo.reason = SDB_MCR_TOO_LONG; return SDB_ST_OK; }
+        Res R0;
+        R0.clear();
+        emit_one(A, mo, mi, m.proto, R0.w, 0, 0, SDB_HIT_HAS_F, 0);     /* bin_str_2_hex_str(name) is None: payload = preamble + "None" */
+        return SDB_ST_OK;
+    }
     if (!A.repaired) return SDB_ST_TYPEERROR;                            /* :120 self passed twice */
     if (p.method >= SDB_M_BRESSER_LIGHTNING) return SDB_ST_TYPEERROR;    /* Conv*(msg_data, msg_type) called with 4 args */
 

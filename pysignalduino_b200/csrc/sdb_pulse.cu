@@ -71,6 +71,28 @@ namespace KNS {
 using sdb::gbit; using sdb::sbit; using sdb::postdemod;      /* sdb_postdemod.cuh lives in namespace sdb */
 #endif
 
+/* Message digits, survivor and match records are touched once per kernel: loading them without allocating in L1 keeps them
+ * from evicting the protocol table (83 KB, read by every lane all the time); L2 still keeps them for the next kernel of the
+ * launch group. */
+#ifdef SDB_STREAM_HINTS
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#else
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) { return *p; }
+#endif
+#define LD_STREAM(p) ld_stream(p)
+
 #define FULL 0xffffffffu
 #define DIG_WORDS (KMAXD / 8 + 4)
 #define BIT_WORDS (KMAXD / 32 + 4)
@@ -927,7 +949,7 @@ __device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slo
         const bool have = s0i + lane < nsurv;
         SdbSurv mine;
         mine.start = 0; mine.c1 = mine.c0 = mine.cf = 0; mine.meta = 0;
-        if (have) mine = slots[s0i + lane];                            /* coalesced 16-byte loads */
+        if (have) *reinterpret_cast<uint4 *>(&mine) = LD_STREAM(reinterpret_cast<const uint4 *>(&slots[s0i + lane]));   /* coalesced 16-byte loads */
         const int cnt = min(32u, nsurv - s0i);
         const uint32_t row = have ? (uint32_t)(mine.start >> 56) : 0u;
         const uint64_t start_t = mine.start & 0x00FFFFFFFFFFFFFFull;
@@ -1332,10 +1354,10 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
     const uint4 *src = reinterpret_cast<const uint4 *>(A.digits + (size_t)m->doff * 16);
     const int nq = (dlen + 31) >> 5;               /* 16-byte units */
 #ifdef SDB_PULSE_LONG
-    for (int q = lane; q < nq; q += 32) reinterpret_cast<uint4 *>(sm.dig)[q] = __ldg(&src[q]);
+    for (int q = lane; q < nq; q += 32) reinterpret_cast<uint4 *>(sm.dig)[q] = LD_STREAM(&src[q]);
 #else
     if (lane < nq) {
-        uint4 v = __ldg(&src[lane]);
+        uint4 v = LD_STREAM(&src[lane]);
         reinterpret_cast<uint4 *>(sm.dig)[lane] = v;
     }
 #endif
@@ -1437,6 +1459,15 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
     const int lane = lane_id();
     const int npat = sm.npat;
     int v0, v1;
+    /* A slot whose id digit never occurs in D cannot be part of a target string that is found in D (pattern_utils.py:133), so
+     * it is left out of every candidate list: same result (combinations are tried in the same order, the ones dropped could only
+     * fail), but more protocols die in the prefilter and fewer values have several candidates.  Such a slot gets the tenths
+     * value of an empty slot. */
+#ifndef SDB_NO_SLOT_FILTER
+#define SLOT_USED(j) (sm.first1[IDX((sm.pat_ids >> (4 * (j))) & 0xF, 12)] != NONE32)
+#else
+#define SLOT_USED(j) true
+#endif
     if (MS) {
         const int cp = m->cp;
         if (cp == 0xFF) return false;                                /* message_synced.py:60-62 */
@@ -1444,7 +1475,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
         if (pc == 0) return false;                                   /* :65-66 */
         clock_abs = fabs((double)pc);
         /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
-        const int t = (lane & 7) < npat ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
+        const int t = ((lane & 7) < npat && SLOT_USED(lane & 7)) ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
         if (lane < 8) sm.T[IDX(0, SDB_MAX_CLK)][lane] = (int16_t)t;
         v0 = (int)A.tab.n_mu_vals; v1 = (int)A.tab.n_vals;          /* the MS intervals follow the MU pairs */
     } else {
@@ -1453,7 +1484,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
 #pragma unroll 1
         for (int idx = lane; idx < ncl * 8; idx += 32) {
             int c = idx >> 3, j = idx & 7;
-            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)(j < npat ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
+            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)((j < npat && SLOT_USED(j)) ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
         }
         v0 = 0; v1 = (int)A.tab.n_mu_vals;
     }
@@ -1608,7 +1639,7 @@ __device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots,
     for (uint32_t s0i = 0; s0i < nsurv; s0i += 32) {
         SdbSurv mine;
         mine.start = 0; mine.c1 = mine.c0 = mine.cf = 0; mine.meta = 0;
-        if (s0i + lane < nsurv) mine = slots[s0i + lane];             /* coalesced 16-byte loads */
+        if (s0i + lane < nsurv) *reinterpret_cast<uint4 *>(&mine) = LD_STREAM(reinterpret_cast<const uint4 *>(&slots[s0i + lane]));   /* coalesced 16-byte loads */
         const int cnt = min(32u, nsurv - s0i);
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
@@ -1732,10 +1763,10 @@ __device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slot
 #pragma unroll 1
     for (uint32_t r0 = 0; r0 < nrec; r0 += 32) {
         const bool have = r0 + lane < nrec;
-        const uint32_t rec = have ? recs[r0 + lane] : 0u;             /* coalesced */
+        const uint32_t rec = have ? LD_STREAM(&recs[r0 + lane]) : 0u; /* coalesced */
         SdbSurv sv;
         sv.start = 0; sv.c1 = sv.c0 = sv.cf = 0; sv.meta = 0;
-        if (have) sv = slots[rec >> 24];
+        if (have) *reinterpret_cast<uint4 *>(&sv) = LD_STREAM(reinterpret_cast<const uint4 *>(&slots[rec >> 24]));
         const int cnt = min(32u, nrec - r0);
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {

@@ -25,7 +25,10 @@ size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots hand
 #ifndef SDB_TICKET_BATCH
 #define SDB_TICKET_BATCH 1     /* messages a warp draws per atomicAdd on the launch's work counter */
 #endif
-#define SDB_MU_CHUNK 1048576u   /* messages per launch group of the device-resident calls (bounds the survivor scratch: chunk * n_mu * 16 B) */
+#ifndef SDB_MU_CHUNK
+#define SDB_MU_CHUNK 1048576u
+#endif
+/* SDB_MU_CHUNK: messages per launch group of the device-resident calls (bounds the survivor scratch: chunk * n_mu * 16 B) */
 #define SDB_PIPE_CHUNK 262144u  /* messages per pipeline stage of the host-buffer calls (H2D / kernels / D2H overlap) */
 
 int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMsg *d_msgs, const uint8_t *d_digits,
@@ -35,6 +38,11 @@ int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMs
 size_t lines_pool_bytes(size_t text_len, uint32_t n);
 int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n, uint32_t base,
                     SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, uint32_t *d_long /* 2 + n words */, int sm_count, cudaStream_t stream);
+
+/* sdb_format.cu: payload strings of the MS / MU hits [range[0], ctr->hits) into a device pool (NUL-terminated, str_off per hit) */
+int launch_format(const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulseProto *rows, const uint16_t *row_of_proto, uint32_t nproto,
+                  uint32_t *d_range, const SdbCounters *d_ctr, uint32_t hits_cap, uint32_t bits_cap, char *d_pool, uint32_t pool_cap,
+                  uint32_t *d_str_off, uint32_t *d_used, int grid, cudaStream_t stream);
 
 int launch_unit_mc(const SdbDevTable &tab, uint32_t proto, int method_override, const uint8_t *d_bits, int n, int mcbitnum,
                    uint8_t *d_out, int out_cap, int32_t *d_seg, int32_t *d_res, cudaStream_t stream);

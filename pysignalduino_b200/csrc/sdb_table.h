@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define SDB_TBL_MAGIC   0x31424453u   /* "SDB1" */
-#define SDB_TBL_VERSION 9u
+#define SDB_TBL_VERSION 10u
 
 #define SDB_MAX_UNIQ 4     /* distinct values per template (shipped table: <= 4)   */
 #define SDB_MAX_TPL  14    /* template length (longest `start` has 14 pulses)      */
@@ -133,7 +133,9 @@ typedef struct SdbHexProto {
     uint8_t method;                   /* SDB_M_*  */
     uint8_t flags;                    /* SDB_HF_* */
     uint8_t pre_len;
-    uint8_t rsv;
+    uint8_t pid_int;                  /* int(protocol id): 1 = positive, 2 = zero or negative, 0 = int() raises ValueError
+                                         (only read by the as-shipped MC path for method manchester.mcRaw, whose shifted
+                                         arguments turn the id into mcbitnum, manchester.py:120 / :606-611) */
     char    preamble[16];             /* MC payload prefix (manchester.py:131-132), host formatting only */
 } SdbHexProto;
 

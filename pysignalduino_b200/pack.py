@@ -179,13 +179,31 @@ def _pulse_domain_reason(data, patterns: Dict[str, float]) -> Optional[str]:
     return None
 
 
-def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int, strict: bool = False) -> PulseBatch:
+try:                                    # native dict walker (csrc/sdb_fastpack.c, built by build_ext.build_fastpack)
+    from . import _fastpack
+except ImportError:                     # not built: the Python packer below does the same, ~30x slower
+    _fastpack = None
+
+
+def pack_pulse(msgs: Sequence[Dict[str, Any]], kind: int, strict: bool = False, native: bool = True) -> PulseBatch:
     """Pack MS (kind 0) or MU (kind 1) parser dicts.
 
-    One pass of plain-Python bookkeeping per message (dict lookups, list appends); every array operation — the digit
-    look-up, nibble packing, record fields — runs once over the whole batch.  A message outside the packed domain becomes
-    an SDB_MSG_DOMAIN record (status "DomainError" for that message only); ``strict`` raises instead."""
+    The native packer (``_fastpack.pack_pulse``) walks the dicts in C; it declines (returns None) on anything it cannot
+    reproduce exactly — non-str values, non-ASCII text, pulse values outside the canonical integer syntax — and the Python
+    packer below then handles the whole batch: one pass of plain-Python bookkeeping per message (dict lookups, list
+    appends), every array operation once over the whole batch.  A message outside the packed domain becomes an
+    SDB_MSG_DOMAIN record (status "DomainError" for that message only); ``strict`` raises instead."""
     n = len(msgs)
+    if native and _fastpack is not None and n:
+        rec = np.zeros(n, dtype=PULSE_DTYPE)
+        clock = np.zeros(n, dtype=np.float64)
+        got = _fastpack.pack_pulse(msgs if type(msgs) is list else list(msgs), kind, rec, clock)
+        if got is not None:
+            pool_bytes, rssi, domain = got
+            if strict and domain:
+                i = min(domain)
+                raise DomainError(f"message {i}: {domain[i]}")
+            return PulseBatch(kind, rec, np.frombuffer(pool_bytes, dtype=np.uint8), rssi, clock, domain)
     rssi: List[Any] = []
     pats: List[int] = []            # 8 values per message
     meta: List[int] = []            # dlen, npat, cp, pat_ids, flags per message

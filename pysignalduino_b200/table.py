@@ -30,7 +30,7 @@ except ImportError:  # pragma: no cover
     import sre_constants as sre_c  # type: ignore
 
 TBL_MAGIC = 0x31424453  # "SDB1"
-TBL_VERSION = 9
+TBL_VERSION = 10
 
 MAX_UNIQ = 4
 MAX_TPL = 14
@@ -99,7 +99,7 @@ HEXPROTO_DTYPE = np.dtype(
     [
         ("length_min", "<i4"), ("length_max", "<i4"),
         ("clock_min", "<i4"), ("clock_max", "<i4"),
-        ("method", "u1"), ("flags", "u1"), ("pre_len", "u1"), ("rsv", "u1"),
+        ("method", "u1"), ("flags", "u1"), ("pre_len", "u1"), ("pid_int", "u1"),
         ("preamble", "S16"),
     ]
 )
@@ -532,6 +532,10 @@ def compile_table(protocols: Dict[str, Dict[str, Any]], strict: bool = False) ->
         if meth:
             h["method"] = METHOD_IDS.get(meth.split(".")[-1], M_UNKNOWN)
         h["flags"] = fl
+        try:
+            h["pid_int"] = 1 if int(pid) > 0 else 2    # as shipped, mcRaw receives the id as its mcbitnum (manchester.py:120)
+        except ValueError:
+            h["pid_int"] = 0
         pre = str(pr.get("preamble", "")).encode("latin-1")
         if len(pre) > 16:
             raise NotImplementedError(f"protocol {pid}: preamble too long")

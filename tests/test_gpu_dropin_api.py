@@ -135,38 +135,51 @@ def test_pure_helpers(protocols):
 
 
 def test_demod_host_payloads_equals_decode_then_format(sdp, corpus):
-    """sdb_demod_host_payloads (decode + payload strings, formatted per pipeline stage on the host threads) returns exactly
-    what sdb_demod_host followed by sdb_format_hits returns — multi-stage (pipelined) and single-stage batches."""
+    """sdb_demod_host_payloads (decode + payload strings; MS / MU strings come from the device format kernel, stage by stage)
+    returns exactly what sdb_demod_host followed by the host formatter sdb_format_hits returns — multi-stage (pipelined) and
+    single-stage batches, all four kinds, with and without the bit arena, and reports the pool size it needs."""
     import numpy as np
 
     from pysignalduino_b200 import pack
 
     eng = sdp.engine()
-    for kind, n in ((pack.KIND_MU, 300_000), (pack.KIND_MS, 270_000), (pack.KIND_MU, 1000), (pack.KIND_MC, 5000)):
+    for kind, n in ((pack.KIND_MU, 300_000), (pack.KIND_MS, 270_000), (pack.KIND_MU, 1000), (pack.KIND_MC, 5000), (pack.KIND_MN, 5000)):
         b = corpus.pulse(kind, n) if kind <= 1 else corpus.hexmsgs(kind, n)
         ref = eng.demod_host(b, mc_repaired=True)
         pool_ref, off_ref = eng.format_hits(kind, ref.hits, ref.bits)
-        nh, nw = len(ref.hits), len(ref.bits)
+        pool_ref = np.frombuffer(pool_ref, dtype=np.uint8)
+        nh = len(ref.hits)
         out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
         hits = np.zeros(nh + 8, dtype=pack.HIT_DTYPE)
-        bits = np.zeros(nw + 8, dtype=np.uint32)
         ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
-        pool = np.zeros(len(pool_ref) + 16, dtype=np.uint8)
-        off = np.zeros(len(hits) + 1, dtype=np.uint64)
+        pool = np.zeros(len(pool_ref) + nh + 16, dtype=np.uint8)
+        off = np.zeros(len(hits), dtype=np.uint32)
+        bits = None if kind <= 1 else np.zeros(len(ref.bits) + 8, dtype=np.uint32)
         rc, used = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
                                                 pool, off, mc_repaired=True)
-        assert rc == 0 and int(ctr["hits"][0]) == nh and used == len(pool_ref)
+        assert rc == 0 and int(ctr["hits"][0]) == nh and used == len(pool_ref) + nh          # one NUL per hit
+
         # hit order differs between runs (atomics), so compare per message: the strings of message m in hit order
-        def per_message(o, hh, pl, of):
+        def strings(o, k, get):
             res = {}
             for m in np.nonzero(o["nhits"])[0][:: max(1, n // 3000)]:
-                h0, k = int(o["hit_off"][m]), int(o["nhits"][m])
-                res[int(m)] = [bytes(pl[int(of[i]) : int(of[i + 1])]) for i in range(h0, h0 + k)]
+                h0, c = int(o["hit_off"][m]), int(o["nhits"][m])
+                res[int(m)] = [get(i) for i in range(h0, h0 + c)]
             return res
-        got = per_message(out, hits, pool, off)
-        exp = per_message(ref.out, ref.hits, np.frombuffer(pool_ref, dtype=np.uint8), off_ref)
+
+        def nul_string(i):
+            a = int(off[i])
+            e = a
+            while pool[e]:
+                e += 1
+            return bytes(pool[a:e])
+
+        got = strings(out, kind, nul_string)
+        exp = strings(ref.out, kind, lambda i: bytes(pool_ref[int(off_ref[i]) : int(off_ref[i + 1])]))
         assert got == exp and len(got) > 100
         small = np.zeros(8, dtype=np.uint8)
         rc, used2 = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
                                                  small, off, mc_repaired=True)
-        assert rc == -3 and used2 == len(pool_ref)              # SDB_E_OVERFLOW reports the size needed
+        assert rc == -3 and used2 == used                       # SDB_E_OVERFLOW reports the size needed
+        res2, pool2, off2 = eng.demod_payloads(b, mc_repaired=True)
+        assert len(res2.hits) == nh and len(pool2) == used

@@ -7,7 +7,7 @@ from tests.common import diff_report, golden_expected, load_golden
 pytestmark = pytest.mark.gpu
 
 FILES = ["reference_vectors.json.gz", "corpus_ms.json.gz", "corpus_mu.json.gz", "fuzz_ms.json.gz", "fuzz_mu.json.gz",
-         "corpus_mn.json.gz", "crafted_mu.json.gz"]
+         "corpus_mn.json.gz", "crafted_mu.json.gz", "edge_ms.json.gz", "edge_mu.json.gz"]
 
 
 def canon(statuses, results):

@@ -5,7 +5,8 @@ from pysignalduino_b200 import pack
 from tests.common import diff_report, golden_expected, load_golden
 
 PULSE = [("reference_vectors.json.gz", None), ("corpus_ms.json.gz", "MS"), ("corpus_mu.json.gz", "MU"),
-         ("fuzz_ms.json.gz", "MS"), ("fuzz_mu.json.gz", "MU"), ("crafted_mu.json.gz", "MU")]
+         ("fuzz_ms.json.gz", "MS"), ("fuzz_mu.json.gz", "MU"), ("crafted_mu.json.gz", "MU"),
+         ("edge_ms.json.gz", "MS"), ("edge_mu.json.gz", "MU")]
 
 
 @pytest.mark.parametrize("name,_typ", PULSE)
@@ -41,6 +42,11 @@ def test_golden_has_raised_and_multi_hit_cases():
     crafted = load_golden("crafted_mu.json.gz")          # > 4 matches per survivor, > 64 per message, empty captures
     assert sum(1 for r in crafted if len(r["results"]) > 64) >= 5
     assert any(r["status"] == "IndexError" for r in crafted)
+    # adversarial sets that reach ACCEPT paths: corpus frames pushed to tolerance edges, duplicate candidates, permuted slots
+    for name in ("edge_ms.json.gz", "edge_mu.json.gz"):
+        edge = load_golden(name)
+        assert sum(1 for r in edge if r["results"]) > 0.2 * len(edge)
+        assert sum(1 for r in edge if not r["results"]) > 0.1 * len(edge)
     mc = load_golden("corpus_mc_strict.json.gz")
     assert all(r["status"] in ("ok", "TypeError") and not r["results"] for r in mc)
     assert any(r["status"] == "TypeError" for r in mc)

@@ -36,5 +36,5 @@ for r in sec["rows"][1:]:
 tot = sum(inst.values())
 print(sec["name"], "total warp inst", tot)
 for k in sorted(inst):
-    if k[0].startswith("sdb_pulse") and lo <= k[1] <= hi:
+    if lo <= k[1] <= hi:
         print(f"{k[0]}:{k[1]:5d} inst {inst[k]:11d} {100*inst[k]/tot:5.1f}%  maxcount {mx[k]:9d} samples {samp[k]}")
