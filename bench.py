@@ -313,6 +313,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the demodulator has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run next to this GPU (NUMA) before any pinned buffer is allocated — the e2e path moves ~2 GB per step
+    # and rank through host memory
+    from pysignalduino_b200.capi import bind_to_gpu_numa
+
+    numa_cpus = None if args.no_numa else bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -440,20 +445,24 @@ def run_ours(args):
             "pool": t_pool.numpy(), "off": t_off.numpy().view(np.uint32), "used": 0,
         })
         h2d += msgs.nbytes + digits.nbytes
-        # result slots + counters + hits + string offsets + strings (MS / MU; counted after the first e2e step) | + bit arena (MC / MN)
-        d2h += 8 * s["n"] + 16 + (16 + 4) * int(c[0]) + (4 * int(c[1]) if s["kind"] >= 2 else 0)
+        # result slots + counters + hits + string offsets (+ the strings, counted after the first e2e step)
+        d2h += 8 * s["n"] + 16 + (16 + 4) * int(c[0])
+
+    e2e_kind_s = [0.0] * len(slots)
 
     def e2e_step(nmsgs=None):
         for i, hs in enumerate(host):
+            t_k = time.perf_counter()
             msgs, digits = hs["msgs"], hs["digits"]
             if nmsgs is not None and nmsgs[i] < len(msgs):
                 msgs = msgs[: nmsgs[i]]
                 digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
-            rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], hs["bits"] if hs["kind"] >= 2 else None,
+            rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], None,
                                                     hs["ctr"], hs["pool"], hs["off"], mc_repaired=True)
             if rc != 0:
                 raise SystemExit("bench.py: e2e arena / payload pool overflow")
             hs["used"] = used
+            e2e_kind_s[i] += time.perf_counter() - t_k
 
     def timed_e2e(nmsgs=None):
         e2e_step(nmsgs)
@@ -466,8 +475,9 @@ def run_ours(args):
 
     t_e2e = timed_e2e()
     e2e_value = world * M * args.steps / t_e2e
+    e2e_per_kind_ms = {sl["name"]: 1e3 * e2e_kind_s[i] / (args.steps + 1) for i, sl in enumerate(slots)}
     payload_bytes = int(sum(hs["used"] for hs in host))
-    d2h += int(sum(hs["used"] for hs in host if hs["kind"] <= 1))          # MS / MU strings come back from the device
+    d2h += payload_bytes                                                   # the strings come back from the device instead of the bit arena
 
     # device-resident and host-buffer runs must agree (same hits, same words)
     for s, hs in zip(slots, host):
@@ -714,14 +724,16 @@ def run_ours(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "payload_bytes_per_step": payload_bytes,
-                "includes": "pinned H2D, decode kernels, the payload string of every hit (preamble + hex + postamble; MS / MU by the device format "
-                            "kernel of each pipeline stage, MC / MN on the host), D2H of result slots / hits / string offsets / strings"},
+                "payload_bytes_per_step": payload_bytes, "host_call_ms_per_kind": e2e_per_kind_ms,
+                "includes": "pinned H2D, decode kernels, the payload string of every hit (preamble + hex + postamble) by the device format kernel "
+                            "of each pipeline stage, D2H of result slots / hits / string offsets / strings"},
         "gpu_launches": args.steps * launches(full),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "per_kernel": per_kernel,
         "hit_histogram": {"protocols_with_hits": int((hist > 0).sum()), "total_hits": int(hist.sum()), "ranks": world,
                           "top": {eng.table.ids[int(i)]: int(hist[int(i)]) for i in top}},
         "api": api, "other_scaling": other,
+        "host": {"cpus": os.cpu_count(), "rank0_affinity_cpus": len(numa_cpus) if numa_cpus else None,
+                 "numa_binding": "rank pinned to its GPU's NVML CPU affinity before pinned buffers are allocated" if numa_cpus else "none"},
         "corpus_gen_s": t_gen, "lines": lines_info,
     }
     emit(line)
@@ -741,6 +753,7 @@ def main():
     ap.add_argument("--port", action="store_true", help="--impl reference: time the C oracle port instead of the Python reference")
     ap.add_argument("--ref-sample", type=int, default=50000, help="cpu_baseline: messages per class for the Python reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity / API legs")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-lines", action="store_true", help="skip the text-line (tokenizer) leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -167,6 +167,16 @@ int sdb_demod_pulse_device(SdbHandle *h, int kind,
                            uint32_t *d_bits, uint32_t bits_cap,
                            SdbCounters *d_counters, void *stream);
 
+/*
+ * Pre-size the handle's scratch (survivor / match records the kernels of one launch group hand each other) for launch
+ * groups of up to n_messages.  Without it the first sdb_demod_pulse_device() call that needs more scratch than any call
+ * before synchronises `stream`, frees and reallocates (it blocks the host and cannot be captured into a CUDA graph); after
+ * it, device calls with n <= n_messages (or any n once 1 048 576 is reserved: larger batches run as several groups) only
+ * enqueue.  All work on ONE handle must be stream-ordered: the scratch and the work counters belong to the handle, so two
+ * calls in flight on different streams would share them — use one handle per stream.
+ */
+int sdb_reserve(SdbHandle *h, uint32_t n_messages);
+
 /* Same for MC / MN (sd_protocols.py:76-155, manchester.py, helpers.py:223-716).
  * mc_repaired: 0 = as shipped (TypeError, SURVEY §8c "strict"), 1 = the two documented one-line repairs. */
 int sdb_demod_hex_device(SdbHandle *h, int kind, int mc_repaired,
@@ -189,9 +199,8 @@ int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
 /*
  * sdb_demod_host plus the payload string of every hit in one call: what SDProtocols.demodulate() returns per hit is a
  * string (preamble + hex / bits + postamble, message_synced.py:224-231, message_unsynced.py:254-274, manchester.py:131-132).
- * MS / MU: a format kernel runs after the decode kernels of every pipeline stage and the strings travel back with the hits
- * under the next stage's kernels; `bits` may be NULL (the bit arena is then not copied back).  MC / MN: formatted on the
- * host.  Hit i's string starts at pool[str_off[i]] and is NUL-terminated (str_off has hits_cap entries; the pool is NOT in
+ * A format kernel runs after the decode kernels of every pipeline stage and the strings travel back with the hits under the
+ * next stage's kernels; `bits` may be NULL (the bit arena is then not copied back).  Hit i's string starts at pool[str_off[i]] and is NUL-terminated (str_off has hits_cap entries; the pool is NOT in
  * hit order).  SDB_E_OVERFLOW when an arena or the pool is too small (counters / *pool_used say how much is needed).
  */
 int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,

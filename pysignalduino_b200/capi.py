@@ -33,7 +33,7 @@ EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
     "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines", "sdb_frame_lines_inplace",
-    "sdb_unit_pattern_exists", "sdb_demod_host_payloads",
+    "sdb_unit_pattern_exists", "sdb_demod_host_payloads", "sdb_reserve",
 ]
 
 
@@ -75,6 +75,8 @@ def load_library() -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     L.sdb_demod_host_payloads.restype = C.c_int
     L.sdb_demod_host_payloads.argtypes = list(L.sdb_demod_host.argtypes) + [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+    L.sdb_reserve.restype = C.c_int
+    L.sdb_reserve.argtypes = [C.c_void_p, C.c_uint32]
     L.sdb_format_hits.restype = C.c_int
     L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.POINTER(C.c_size_t)]
@@ -202,6 +204,32 @@ def frame_chunks(raw, chunk_bytes: int = 256 << 20):
             line_base += len(typ)
 
 
+def bind_to_gpu_numa(device: int = 0):
+    """Pin the calling process to the CPU cores next to CUDA device ``device`` (NVML's ideal CPU affinity) BEFORE it allocates
+    pinned host buffers: pinned pages are placed on the NUMA node of the thread that first touches them, and a rank whose
+    buffers sit on the other socket pushes every H2D / D2H byte over the inter-socket link.  With one process per GPU on a
+    multi-socket host this is what keeps the end-to-end path scaling.  Returns the CPU list used (None if NVML or the
+    affinity call is unavailable — the call is then a no-op)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:                      # no NVML / not permitted: keep the inherited affinity
+        return None
+
+
 class Result:
     """Raw result arrays of one batch call."""
 
@@ -236,6 +264,12 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def reserve(self, n_messages: int) -> None:
+        """Pre-size the scratch so that later device-pointer calls only enqueue work (sdb_reserve)."""
+        rc = self.lib.sdb_reserve(self.h, n_messages)
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_reserve")
 
     def _err(self, rc: int, what: str) -> SdbError:
         return SdbError(f"{what} failed ({rc}): {(self.lib.sdb_last_error(self.h) or b'').decode()}")

@@ -173,8 +173,26 @@ extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
     if (kind != SDB_KIND_MS && kind != SDB_KIND_MU) return set_err(h, SDB_E_ARG, "sdb_demod_pulse_device: kind must be MS or MU");
     if (n && (!d_msgs || !d_digits || !d_out || !d_counters)) return set_err(h, SDB_E_ARG, "sdb_demod_pulse_device: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
     return enqueue_pulse(h, kind, d_msgs, d_digits, n, 0, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, st);
+}
+
+/* Scratch for launch groups of up to n_messages (the survivor / match records the kernels of one group hand each other).
+ * After this call sdb_demod_pulse_device() with n <= n_messages per launch group only enqueues work. */
+extern "C" int sdb_reserve(SdbHandle *h, uint32_t n_messages)
+{
+    if (!h) return SDB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    uint32_t chunk = n_messages < SDB_MU_CHUNK ? ((n_messages + 1023u) & ~1023u) : SDB_MU_CHUNK;
+    if (chunk > h->mu_chunk) {
+        CK(cudaDeviceSynchronize());
+        if (h->d_mu_scratch) CK(cudaFree(h->d_mu_scratch));
+        h->d_mu_scratch = nullptr; h->mu_chunk = 0;
+        CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_ms > h->tab.n_mu ? h->tab.n_ms : h->tab.n_mu, chunk)));
+        h->mu_chunk = chunk;
+    }
+    return SDB_OK;
 }
 
 /* Enqueue the kernels for messages [0, n) at d_msgs whose batch indices start at msg_base; counters are NOT reset. */
@@ -211,6 +229,7 @@ extern "C" int sdb_demod_hex_device(SdbHandle *h, int kind, int mc_repaired,
     if (kind != SDB_KIND_MC && kind != SDB_KIND_MN) return set_err(h, SDB_E_ARG, "sdb_demod_hex_device: kind must be MC or MN");
     if (n && (!d_msgs || !d_digits || !d_out || !d_counters)) return set_err(h, SDB_E_ARG, "sdb_demod_hex_device: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(d_counters, 0, sizeof(SdbCounters), st));
     int grid = h->grid_hex;
     uint32_t need = (n + SDB_HEX_THREADS - 1) / SDB_HEX_THREADS;
@@ -296,8 +315,8 @@ static int enqueue_format(SdbHandle *h, int kind, uint32_t hits_cap, uint32_t bi
 {
     const SdbPulseProto *rows = kind == SDB_KIND_MS ? h->tab.ms : h->tab.mu;
     const uint16_t *map = h->d_rowmap + (kind == SDB_KIND_MS ? 0 : h->tab.nproto);
-    int rc = sdb::launch_format(h->d_hits, h->d_bits, rows, map, h->tab.nproto, h->d_fmt, h->d_ctr, hits_cap, bits_cap, h->d_chars,
-                                sink->pool_cap, h->d_stroff, h->d_fmt + 2, h->sm_count * 8, st);
+    int rc = sdb::launch_format(kind, h->d_hits, h->d_bits, rows, map, h->tab.hex, h->tab.nproto, h->d_fmt, h->d_ctr, hits_cap, bits_cap,
+                                h->d_chars, sink->pool_cap, h->d_stroff, h->d_fmt + 2, h->sm_count * 8, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "format kernel launch", static_cast<cudaError_t>(rc));
     CK(cudaMemcpyAsync(&h->h_used[k], h->d_fmt + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return SDB_OK;
@@ -382,7 +401,7 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
             rc = sdb_demod_hex_device(h, kind, mc_repaired, static_cast<const SdbHexMsg *>(h->d_msgs), h->d_digits, n, h->d_out,
                                       h->d_hits, hits_cap, h->d_bits, bits_cap, h->d_ctr, st);
         if (rc != SDB_OK) return rc;
-        if (sink && pulse && (rc = enqueue_format(h, kind, hits_cap, bits_cap, sink, 0, st))) return rc;
+        if (sink && (rc = enqueue_format(h, kind, hits_cap, bits_cap, sink, 0, st))) return rc;
         CK(cudaMemcpyAsync(counters, h->d_ctr, sizeof(SdbCounters), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out, h->d_out, sizeof(SdbMsgOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -390,7 +409,7 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
     if (counters->hits > hits_cap || counters->words > bits_cap) return set_err(h, SDB_E_OVERFLOW, "hit / bit arena too small");
     if (counters->hits && hits) CK(cudaMemcpyAsync(hits, h->d_hits, sizeof(SdbHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
     if (counters->words && bits) CK(cudaMemcpyAsync(bits, h->d_bits, sizeof(uint32_t) * (size_t)counters->words, cudaMemcpyDeviceToHost, st));
-    if (sink && pulse) {
+    if (sink) {
         sink->used = h->h_used[0];
         if (sink->used <= sink->pool_cap) {
             if (counters->hits) CK(cudaMemcpyAsync(sink->str_off, h->d_stroff, sizeof(uint32_t) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
@@ -485,24 +504,6 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
 /* Payload strings of the hits: preamble + hex / bits + postamble.  Two passes over the hits (string lengths -> offsets ->
  * characters), each split over the host threads for large batches: 27 M hits per 10 M-message mixed corpus would take
  * seconds on one core, and the reference side of the comparison (its CPU path) produces these strings too. */
-static inline int hbit(const uint32_t *w, uint32_t i) { return (w[i >> 5] >> (i & 31)) & 1; }
-static const uint8_t kRev4[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
-
-/* hex digit j of nb bits (LSB-first words), right-aligned nibbles as helpers.py:28-64 builds them */
-static inline int hex_digit_at(const uint32_t *w, int nb, int nd, int j)
-{
-    const int b0 = nb - 4 * (nd - j);
-    if (b0 >= 0) {                                    /* message bits b0 .. b0+3, the first one is the digit's MSB */
-        const int sh = b0 & 31;
-        uint32_t x = w[b0 >> 5] >> sh;
-        if (sh > 28) x |= w[(b0 >> 5) + 1] << (32 - sh);      /* b0 + 3 < nb: that word exists */
-        return kRev4[x & 0xF];
-    }
-    int v = 0;
-    for (int k = 0; k < 4; k++) { const int bi = b0 + k; v = (v << 1) | (bi >= 0 ? hbit(w, (uint32_t)bi) : 0); }
-    return v;
-}
-
 namespace {
 struct Fmt {
     const SdbTblHeader *hd;
@@ -514,59 +515,18 @@ struct Fmt {
     uint32_t nhits;
     const uint32_t *bits;
 
-    /* characters of hit i appended at dst (dst == nullptr: count only); returns the count, or (size_t)-1 for a bad record */
+    /* characters of hit i appended at dst (dst == nullptr: count only); returns the count, or (size_t)-1 for a bad record.
+     * sdb_fmt.h holds the formatting itself: the same code the device formatter runs. */
     size_t one(uint32_t i, char *dst) const
     {
-        size_t n = 0;
-        auto put = [&](char c) { if (dst) dst[n] = c; n++; };
-        auto put_hex = [&](const uint32_t *w, uint32_t nb, bool strip) {
-            const int nd = (int)((nb + 3) >> 2);
-            int j = 0;
-            if (strip) while (j < nd && hex_digit_at(w, (int)nb, nd, j) == 0) j++;
-            if (!dst) { n += (size_t)(nd - j); return; }
-            for (; j < nd; j++) dst[n++] = "0123456789ABCDEF"[hex_digit_at(w, (int)nb, nd, j)];
-        };
         const SdbHit &ht = hits[i];
         if (ht.proto >= hd->nproto) return (size_t)-1;
-        const uint32_t *w = bits + ht.bits_off;
         if (pulse) {
             const SdbPulseProto *pp = row[ht.proto];
             if (!pp) return (size_t)-1;
-            return sdb_fmt_pulse(pp, ht, w, dst);         /* sdb_fmt.h: the same code the device formatter runs */
+            return sdb_fmt_pulse(pp, ht, bits + ht.bits_off, dst);
         }
-        /* MC: preamble + hex, or preamble + repr(list) for TFA (manchester.py:131-132, :713-717)
-         * MN: the converter's own string (helpers.py:223-716), no preamble (sd_protocols.py:151-155) */
-        const SdbHexProto &p = hx[ht.proto];
-        if (kind == SDB_KIND_MC) {
-            if (ht.flags & SDB_HIT_LIST) {
-                if (ht.aux != 0) return 0;                /* the first element of a list carries the whole string */
-                for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
-                put('[');
-                for (uint32_t e = i; e < nhits && hits[e].msg == ht.msg && (hits[e].flags & SDB_HIT_LIST) && hits[e].aux == e - i; e++) {
-                    if (e > i) { put(','); put(' '); }
-                    put('\'');
-                    put_hex(bits + hits[e].bits_off, hits[e].nbits, false);
-                    put('\'');
-                }
-                put(']');
-            } else {
-                for (int k = 0; k < p.pre_len; k++) put(p.preamble[k]);
-                if (ht.flags & SDB_HIT_HAS_F) { put('N'); put('o'); put('n'); put('e'); }      /* f"{preamble}{None}" (as-shipped mcRaw) */
-                else put_hex(w, ht.nbits, false);
-            }
-        } else if (ht.flags & SDB_HIT_FIELDS) {
-            char num[96];
-            int k;
-            if (ht.aux == SDB_M_PCA301)                    /* MN hits carry the converter that produced them in aux */
-                k = snprintf(num, sizeof num, "OK 24 %u %u %u %u %u %u %u %u %u %u %04X", w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], w[9], w[10]);
-            else
-                k = snprintf(num, sizeof num, "OK 9 %u %u %u %u %u", w[0], w[1], w[2], w[3], w[4]);
-            for (int q = 0; q < k; q++) put(num[q]);
-        } else {
-            if (ht.aux == SDB_M_KOPP) { put('k'); put('r'); }
-            put_hex(w, ht.nbits, false);
-        }
-        return n;
+        return sdb_fmt_hexkind(kind, hx, hits, i, nhits, bits, dst);
     }
 };
 
@@ -643,38 +603,6 @@ static uint64_t format_range(const Fmt &F, uint32_t lo, uint32_t hi, uint64_t ba
     return end;
 }
 
-/* NUL-terminated variant with one 32-bit offset per hit (the layout sdb_demod_host_payloads returns) */
-static uint64_t format_range_nul(const Fmt &F, uint32_t n, char *pool, size_t pool_cap, uint32_t *str_off)
-{
-    const unsigned threads = fmt_threads();
-    std::vector<uint64_t> part(threads + 1, 0);
-    std::vector<int> bad(threads, 0);
-    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {
-        uint64_t sum = 0;
-        for (uint32_t i = a; i < b; i++) {
-            const size_t len = F.one(i, nullptr);
-            if (len == (size_t)-1) { bad[t] = 1; continue; }
-            str_off[i] = (uint32_t)len;
-            sum += len + 1;
-        }
-        part[t + 1] = sum;
-    });
-    for (unsigned t = 0; t < threads; t++) if (bad[t]) return UINT64_MAX;
-    for (unsigned t = 0; t < threads; t++) part[t + 1] += part[t];
-    const uint64_t end = part[threads];
-    const bool fits = end <= pool_cap && end < 0xFFFFFFF0ull;
-    parallel_ranges(n, threads, [&](unsigned t, uint32_t a, uint32_t b) {
-        uint64_t at = part[t];
-        for (uint32_t i = a; i < b; i++) {
-            const uint32_t len = str_off[i];
-            if (fits) { if (len) F.one(i, pool + at); pool[at + len] = 0; }
-            str_off[i] = (uint32_t)at;
-            at += (uint64_t)len + 1;
-        }
-    });
-    return end;
-}
-
 extern "C" int sdb_format_hits(const SdbHandle *h, int kind,
                                const SdbHit *hits, uint32_t nhits, const uint32_t *bits,
                                char *pool, size_t pool_cap, uint64_t *str_off, size_t *pool_used)
@@ -700,29 +628,14 @@ extern "C" int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
     if (!h) return SDB_E_ARG;
     if (!str_off || !pool_used || !hits || (pool_cap && !pool)) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
     *pool_used = 0;
-    const bool pulse = kind == SDB_KIND_MS || kind == SDB_KIND_MU;
-    if (pulse) {
-        /* MS / MU: format kernel per stage, strings instead of the bit arena on the wire (bits may be NULL) */
-        PayloadSink sink;
-        sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.str_off = str_off;
-        const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink);
-        *pool_used = sink.used;
-        if (rc != SDB_OK) return rc;
-        if (sink.used > sink.pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
-        return SDB_OK;
-    }
-    /* MC / MN: few hits, list / decimal renderings — formatted on the host from the bit arena */
-    std::vector<uint32_t> tmp_bits;
-    if (!bits) { tmp_bits.resize(bits_cap ? bits_cap : 1); bits = tmp_bits.data(); }
-    int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr);
+    if (kind < SDB_KIND_MS || kind > SDB_KIND_MN) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
+    /* a format kernel per pipeline stage (sdb_format.cu): the strings travel back instead of the bit arena (bits may be NULL) */
+    PayloadSink sink;
+    sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.str_off = str_off;
+    const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink);
+    *pool_used = sink.used;
     if (rc != SDB_OK) return rc;
-    Fmt F;
-    if (fmt_init(F, h, kind) != SDB_OK) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
-    F.hits = hits; F.nhits = counters->hits; F.bits = bits;
-    const uint64_t end = format_range_nul(F, counters->hits, pool, pool_cap, str_off);
-    if (end == UINT64_MAX) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: malformed hit records");
-    *pool_used = (size_t)end;
-    if (end > pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
+    if (sink.used > sink.pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
     return SDB_OK;
 }
 

@@ -1,6 +1,7 @@
 /*
- * sdb_fmt.h — the payload string of one MS / MU hit: preamble + hex / bits + postamble
- * (sd_protocols/message_synced.py:224-231, message_unsynced.py:254-274, helpers.py:28-64).
+ * sdb_fmt.h — the payload string of one hit.  MS / MU: preamble + hex / bits + postamble
+ * (sd_protocols/message_synced.py:224-231, message_unsynced.py:254-274, helpers.py:28-64); MC: preamble + hex, or preamble +
+ * repr(list) for TFA (manchester.py:131-132, :713-717); MN: the converter's own string (helpers.py:223-716).
  * ONE definition for the host formatter (sdb_capi.cu, sdb_format_hits) and the device formatter (sdb_format.cu,
  * format_kernel), so the two cannot drift apart.
  */
@@ -54,5 +55,65 @@ SDB_HD uint32_t sdb_fmt_pulse(const SdbPulseProto *pp, const SdbHit &ht, const u
         n += (uint32_t)(nd - j);
     }
     for (int k = 0; k < pp->post_len; k++) { if (dst) dst[n] = pp->postamble[k]; n++; }
+    return n;
+}
+
+/* plain (unstripped) hex digits of nb bits */
+SDB_HD uint32_t sdb_fmt_hexbits(const uint32_t *w, uint32_t nb, char *dst)
+{
+    const int nd = (int)((nb + 3) >> 2);
+    if (dst) for (int q = 0; q < nd; q++) { const int d = sdb_fmt_hex_digit(w, (int)nb, nd, q); dst[q] = (char)(d < 10 ? '0' + d : 'A' + d - 10); }
+    return (uint32_t)nd;
+}
+
+/* "%u" */
+SDB_HD uint32_t sdb_fmt_u32(uint32_t v, char *dst)
+{
+    char tmp[10];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    if (dst) for (int i = 0; i < k; i++) dst[i] = tmp[k - 1 - i];
+    return (uint32_t)k;
+}
+
+/* Characters of MC / MN hit i (hits of one TFA list are consecutive; the first element carries the whole string, the others
+ * are empty); dst == nullptr: count only. */
+SDB_HD uint32_t sdb_fmt_hexkind(int kind, const SdbHexProto *hx, const SdbHit *hits, uint32_t i, uint32_t nhits, const uint32_t *bits, char *dst)
+{
+    const SdbHit &ht = hits[i];
+    const SdbHexProto &p = hx[ht.proto];
+    const uint32_t *w = bits + ht.bits_off;
+    uint32_t n = 0;
+#define SDB_PUT(c) do { if (dst) dst[n] = (c); n++; } while (0)
+    if (kind == SDB_KIND_MC) {
+        if ((ht.flags & SDB_HIT_LIST) && ht.aux != 0) return 0;
+        for (int k = 0; k < p.pre_len; k++) SDB_PUT(p.preamble[k]);
+        if (ht.flags & SDB_HIT_LIST) {
+            SDB_PUT('[');
+            for (uint32_t e = i; e < nhits && hits[e].msg == ht.msg && (hits[e].flags & SDB_HIT_LIST) && hits[e].aux == e - i; e++) {
+                if (e > i) { SDB_PUT(','); SDB_PUT(' '); }
+                SDB_PUT('\'');
+                n += sdb_fmt_hexbits(bits + hits[e].bits_off, hits[e].nbits, dst ? dst + n : nullptr);
+                SDB_PUT('\'');
+            }
+            SDB_PUT(']');
+        } else if (ht.flags & SDB_HIT_HAS_F) {            /* f"{preamble}{None}" (as-shipped mcRaw) */
+            SDB_PUT('N'); SDB_PUT('o'); SDB_PUT('n'); SDB_PUT('e');
+        } else n += sdb_fmt_hexbits(w, ht.nbits, dst ? dst + n : nullptr);
+    } else if (ht.flags & SDB_HIT_FIELDS) {               /* MN hits carry the converter that produced them in aux */
+        const bool pca = ht.aux == SDB_M_PCA301;          /* "OK 24 %u x10 %04X" (helpers.py:525-579) | "OK 9 %u x5" (:630-716) */
+        SDB_PUT('O'); SDB_PUT('K'); SDB_PUT(' ');
+        if (pca) { SDB_PUT('2'); SDB_PUT('4'); } else SDB_PUT('9');
+        const int nf = pca ? 10 : 5;
+        for (int f = 0; f < nf; f++) { SDB_PUT(' '); n += sdb_fmt_u32(w[f], dst ? dst + n : nullptr); }
+        if (pca) {
+            SDB_PUT(' ');
+            for (int q = 3; q >= 0; q--) { const uint32_t d = (w[10] >> (4 * q)) & 0xFu; SDB_PUT((char)(d < 10 ? '0' + d : 'A' + d - 10)); }
+        }
+    } else {
+        if (ht.aux == SDB_M_KOPP) { SDB_PUT('k'); SDB_PUT('r'); }
+        n += sdb_fmt_hexbits(w, ht.nbits, dst ? dst + n : nullptr);
+    }
+#undef SDB_PUT
     return n;
 }

@@ -1,5 +1,5 @@
 /*
- * sdb_format.cu — payload strings of MS / MU hits, on the device.
+ * sdb_format.cu — payload strings of the hits (all four message kinds), on the device.
  *
  * What SDProtocols.demodulate() hands back per hit is a string: preamble + hex (or bits) + postamble
  * (message_synced.py:224-231, message_unsynced.py:254-274).  Formatting 27 M hits per 10 M-message corpus on the host cost
@@ -24,6 +24,8 @@ namespace sdb {
 #define FMT_STAGE 12288                       /* bytes of shared staging per CTA (typical CTA total: 256 x ~17 = 4.4 KB) */
 
 struct FArgs {
+    int kind;
+    const SdbHexProto *hx;                    /* MC / MN: one row per protocol (preamble) */
     const SdbHit *hits;
     const uint32_t *bits;
     const SdbPulseProto *rows;
@@ -55,9 +57,11 @@ __global__ void __launch_bounds__(FMT_THREADS) format_kernel(FArgs A)
         if (i < h1) {
             ht = A.hits[i];
             if (ht.proto < A.nproto) {
-                pp = &A.rows[A.row_of_proto[ht.proto]];
-                w = A.bits + ht.bits_off;
-                len = sdb_fmt_pulse(pp, ht, w, nullptr) + 1;            /* + NUL */
+                if (A.kind <= SDB_KIND_MU) {
+                    pp = &A.rows[A.row_of_proto[ht.proto]];
+                    w = A.bits + ht.bits_off;
+                    len = sdb_fmt_pulse(pp, ht, w, nullptr) + 1;        /* + NUL */
+                } else len = sdb_fmt_hexkind(A.kind, A.hx, A.hits, i, h1, A.bits, nullptr) + 1;
             }
         }
         /* exclusive scan of the lengths over the CTA */
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(FMT_THREADS) format_kernel(FArgs A)
             const bool staged = total <= FMT_STAGE;
             if (len) {
                 char *dst = staged ? stage + excl : A.pool + base + excl;
-                const uint32_t n = sdb_fmt_pulse(pp, ht, w, dst);
+                const uint32_t n = A.kind <= SDB_KIND_MU ? sdb_fmt_pulse(pp, ht, w, dst) : sdb_fmt_hexkind(A.kind, A.hx, A.hits, i, h1, A.bits, dst);
                 dst[n] = 0;
             }
             if (staged) {
@@ -110,7 +114,8 @@ __global__ void __launch_bounds__(FMT_THREADS) format_kernel(FArgs A)
 /* after the format kernel of a stage: the next stage starts where this one ended */
 __global__ void format_advance_kernel(uint32_t *range) { range[0] = range[1]; }
 
-int launch_format(const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulseProto *rows, const uint16_t *row_of_proto, uint32_t nproto,
+int launch_format(int kind, const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulseProto *rows, const uint16_t *row_of_proto,
+                  const SdbHexProto *hx, uint32_t nproto,
                   uint32_t *d_range, const SdbCounters *d_ctr, uint32_t hits_cap, uint32_t bits_cap, char *d_pool, uint32_t pool_cap,
                   uint32_t *d_str_off, uint32_t *d_used, int grid, cudaStream_t stream)
 {
@@ -118,6 +123,7 @@ int launch_format(const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulsePr
     cudaError_t e = cudaMemcpyAsync(d_range + 1, &d_ctr->hits, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return (int)e;
     FArgs A;
+    A.kind = kind; A.hx = hx;
     A.hits = d_hits; A.bits = d_bits; A.rows = rows; A.row_of_proto = row_of_proto; A.nproto = nproto; A.range = d_range;
     A.pool = d_pool; A.pool_cap = pool_cap; A.str_off = d_str_off; A.used = d_used;
     A.ctr = d_ctr; A.hits_cap = hits_cap; A.bits_cap = bits_cap;

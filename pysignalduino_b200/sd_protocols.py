@@ -9,7 +9,8 @@ packs inputs (pack.py), compiles the protocol table (table.py) and formats strin
 from __future__ import annotations
 
 import re
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from collections.abc import Sequence
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -23,6 +24,75 @@ from .tracked import TrackedDict, Version
 MC_METHODS = {"mcBit2Funkbus": 1, "mcBit2Sainlogic": 2, "mcBit2AS": 3, "mcBit2Hideki": 4, "mcBit2Maverick": 5,
               "mcBit2OSV1": 6, "mcBit2OSV2o3": 7, "mcBit2OSPIR": 8, "mcRaw": 9, "mcBit2TFA": 11, "mcBit2Grothe": 12,
               "mcBit2SomfyRTS": 13}
+
+
+_STATUS_ARRAY = np.array([STATUS_NAMES.get(i, f"status{i}") for i in range(256)], dtype=object)
+
+
+class BatchResults(Sequence):
+    """``results`` of :meth:`SDProtocols.demodulate_batch`: ``results[i]`` is the list of hit dicts of message i, exactly what
+    the reference's ``demodulate()`` returns for it, materialised on access from the raw result arrays (27 M hits per 10 M
+    messages are not turned into Python objects unless somebody looks at them).  Compares equal to the equivalent list."""
+
+    def __init__(self, sdp: "SDProtocols", batch, res: Result, pool: bytes, off: np.ndarray):
+        self._sdp, self._batch, self._res, self._pool, self._off = sdp, batch, res, pool, off
+        self._ids = sdp.engine().table.ids
+        self._clk: Dict[int, float] = {}
+
+    def __len__(self) -> int:
+        return self._batch.n
+
+    def _payload(self, i: int) -> str:
+        a = int(self._off[i])
+        return self._pool[a : self._pool.index(0, a)].decode("latin-1")
+
+    def __getitem__(self, m):
+        if isinstance(m, slice):
+            return [self[i] for i in range(*m.indices(len(self)))]
+        if m < 0:
+            m += len(self)
+        if not 0 <= m < len(self):
+            raise IndexError("message index out of range")
+        res, batch, kind, ids = self._res, self._batch, self._batch.kind, self._ids
+        o = res.out[m]
+        if int(o["status"]) != ST_OK:
+            return []
+        lst: List[Dict[str, Any]] = []
+        h0 = int(o["hit_off"])
+        for i in range(h0, h0 + int(o["nhits"])):
+            h = res.hits[i]
+            fl = int(h["flags"])
+            if (fl & HIT_LIST) and int(h["aux"]) != 0:
+                continue
+            pi = int(h["proto"])
+            payload = self._payload(i)
+            if fl & HIT_MM_HOST:                                      # a modulematch shape the device program cannot express
+                if not re.search(str(self._sdp._protocols[ids[pi]].get("modulematch")), payload):       # message_unsynced.py:277-280
+                    continue
+            if kind == pack.KIND_MS:
+                lst.append({"protocol_id": ids[pi], "payload": payload,
+                            "meta": {"bit_length": int(h["nbits"]), "rssi": batch.rssi[m], "clock": float(batch.clock[m])}})   # message_synced.py:239
+            elif kind == pack.KIND_MU:
+                if pi not in self._clk:
+                    self._clk[pi] = float(self._sdp.check_property(ids[pi], "clockabs", 1))
+                lst.append({"protocol_id": ids[pi], "payload": payload,
+                            "meta": {"bit_length": int(h["nbits"]), "rssi": batch.rssi[m], "clock": self._clk[pi]}})          # message_unsynced.py:288
+            elif kind == pack.KIND_MC:
+                pid = batch.protocol_ids[m]
+                lst.append({"protocol_id": str(pid), "payload": payload,
+                            "meta": {"protocol_id": pid, "rssi": None, "freq_afc": None}})                                   # manchester.py:136-140
+            else:
+                meta = {"is_raw": False} if int(h["aux"]) in (18, 19, 20) else {}                                            # helpers.py:578,627,715
+                lst.append({"protocol_id": batch.protocol_ids[m], "payload": payload, "meta": meta})
+        return lst
+
+    def __eq__(self, other):
+        if isinstance(other, (list, tuple, BatchResults)):
+            return len(other) == len(self) and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def __repr__(self) -> str:
+        return f"<BatchResults: {len(self)} messages, {len(self._res.hits)} hits>"
 
 
 class SDProtocols:
@@ -129,7 +199,7 @@ class SDProtocols:
         index = {pid: i for i, pid in enumerate(eng.table.ids)}
         return pack.pack_hex(msgs, kind, index)
 
-    def demodulate_batch(self, msgs: Sequence[Dict[str, Any]], msg_type: str) -> Tuple[List[str], List[List[Dict[str, Any]]]]:
+    def demodulate_batch(self, msgs: Sequence[Dict[str, Any]], msg_type: str, lazy: bool = True):
         """Demodulate many messages of one type.
 
         Returns (statuses, results): statuses[i] is "ok" or the name of the exception the reference
@@ -137,13 +207,19 @@ class SDProtocols:
         reference's demodulate() returns (empty when it raises).  A message the packed domain cannot
         represent (pack.py) gets status "DomainError" and [] — it was NOT decoded; every other message
         of the batch is.
+
+        The dicts are packed natively (csrc/sdb_fastpack.c), decoded and formatted on the device
+        (sdb_demod_host_payloads); ``results`` is a :class:`BatchResults` sequence that builds the per-message
+        lists on access (``lazy=False`` returns plain lists).
         """
         if msg_type not in pack.KIND_BY_NAME:
             self._logging(f"Unknown message type {msg_type}", 3)
             return ["ok"] * len(msgs), [[] for _ in msgs]
         batch = self.pack(msgs, msg_type)
-        res = self.demodulate_packed(batch)
-        return self.format_results(batch, res, msgs)
+        res, pool, off = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
+        statuses = _STATUS_ARRAY[res.out["status"]].tolist()
+        results = BatchResults(self, batch, res, pool.tobytes(), off)
+        return statuses, (results if lazy else list(results))
 
     def format_results(self, batch, res: Result, msgs: Optional[Sequence[Dict[str, Any]]] = None):
         eng = self.engine()
@@ -208,11 +284,11 @@ class SDProtocols:
 
     def _one(self, msg_data: Dict[str, Any], msg_type: str) -> list:
         batch = self.pack([msg_data], msg_type)
-        res = self.demodulate_packed(batch)
+        res, pool, off = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
         st = int(res.out["status"][0])
         if st != ST_OK:
             self._raise_status(st, batch, f"demodulate_{msg_type.lower()}")
-        return self.format_results(batch, res)[1][0]
+        return BatchResults(self, batch, res, pool.tobytes(), off)[0]
 
     def demodulate_ms(self, msg_data: Dict[str, Any], msg_type: str = "MS") -> List[Dict[str, Any]]:
         """message_synced.py:10-243 (invalid input -> [] with a level-3 log line, :21-47)"""
@@ -512,13 +588,10 @@ class SDProtocols:
         if st != ST_OK:
             self._raise_status(st, batch, "_demodulate_mc_data")
         if int(res.out["nhits"][0]) == 0:
-            lead = len(raw_hex) - len(raw_hex.lstrip("0")) if raw_hex.strip("0") else max(len(raw_hex) - 1, 0)
-            bit_len = 4 * (len(raw_hex) - lead)
-            bits = None
-            if (reason & 0xFF) == 11:
-                inv = (self.check_property(pid, "polarity", "") == "invert") ^ toggle
-                bits = self._convert_mc_hex_to_bits(name, raw_hex, inv, len(raw_hex))[1]
-            return (-1, self._mc_reason_text(reason, name, self.get_property(pid, "method"), bit_len, bits), {})
+            # the decoders' messages quote len(bit_data) / bit_data: the string the device walked (inverted, leading zero nibbles dropped)
+            inv = (self.check_property(pid, "polarity", "") == "invert") ^ toggle
+            bits = self._convert_mc_hex_to_bits(name, raw_hex, inv, len(raw_hex))[1] or ""
+            return (-1, self._mc_reason_text(reason, name, self.get_property(pid, "method"), len(bits), bits), {})
         pool, off = eng.format_hits(pack.KIND_MC, res.hits, res.bits)
         dmsg = pool[int(off[0]) : int(off[1])].decode("latin-1")
         return (1, dmsg, {"protocol_id": protocol_id, "rssi": None, "freq_afc": None})        # :134-142

@@ -26,6 +26,17 @@ for kind in (pack.KIND_MS, pack.KIND_MU):
     b = corp.pulse(kind, 30000)
     r = sdp.demodulate_packed(b)
     assert compare_raw(sdp, b, r, *ora.run_pulse_raw(b, nthreads=8)) == ""
+# long messages (D up to 4096 digits: the sdb_long kernels), lines longer than the tokenizer's first pass, the format kernel
+from tests.common import load_golden
+recs = [r for r in load_golden("long_d.json.gz") if r["dlen"] <= pack.MAX_DIGITS]
+for typ in ("MS", "MU"):
+    sel = [r for r in recs if r["type"] == typ]
+    st, res = sdp.demodulate_batch([r["msg"] for r in sel], typ)
+    got = [(a, [[x["protocol_id"], x["payload"], x["meta"]["bit_length"]] for x in lst]) for a, lst in zip(st, res)]
+    assert got == [(r["status"], r["results"]) for r in sel]
+from pysignalduino_b200 import SignalParser
+lines = SignalParser(protocols=sdp).parse_lines([r["line"] for r in recs[:200]])
+assert sum(len(x) for x in lines) > 0
 for kind in (pack.KIND_MC, pack.KIND_MN):
     b = corp.hexmsgs(kind, 30000)
     r = eng.demod_host(b, mc_repaired=True)

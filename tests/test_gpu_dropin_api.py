@@ -134,14 +134,16 @@ def test_pure_helpers(protocols):
     assert protocols.mc2dmc("1010") == "000"
 
 
-def test_demod_host_payloads_equals_decode_then_format(sdp, corpus):
+def test_demod_host_payloads_equals_decode_then_format(sdp):
     """sdb_demod_host_payloads (decode + payload strings; MS / MU strings come from the device format kernel, stage by stage)
     returns exactly what sdb_demod_host followed by the host formatter sdb_format_hits returns — multi-stage (pipelined) and
     single-stage batches, all four kinds, with and without the bit arena, and reports the pool size it needs."""
     import numpy as np
 
+    from corpus.corpus import Corpus
     from pysignalduino_b200 import pack
 
+    corpus = Corpus(sdp.get_protocol_list())
     eng = sdp.engine()
     for kind, n in ((pack.KIND_MU, 300_000), (pack.KIND_MS, 270_000), (pack.KIND_MU, 1000), (pack.KIND_MC, 5000), (pack.KIND_MN, 5000)):
         b = corpus.pulse(kind, n) if kind <= 1 else corpus.hexmsgs(kind, n)
@@ -154,7 +156,7 @@ def test_demod_host_payloads_equals_decode_then_format(sdp, corpus):
         ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
         pool = np.zeros(len(pool_ref) + nh + 16, dtype=np.uint8)
         off = np.zeros(len(hits), dtype=np.uint32)
-        bits = None if kind <= 1 else np.zeros(len(ref.bits) + 8, dtype=np.uint32)
+        bits = None if kind != pack.KIND_MN else np.zeros(len(ref.bits) + 8, dtype=np.uint32)    # the bit arena is optional
         rc, used = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
                                                 pool, off, mc_repaired=True)
         assert rc == 0 and int(ctr["hits"][0]) == nh and used == len(pool_ref) + nh          # one NUL per hit
