@@ -458,7 +458,7 @@ def run_ours(args):
                 msgs = msgs[: nmsgs[i]]
                 digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
             rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], None,
-                                                    hs["ctr"], hs["pool"], hs["off"], mc_repaired=True)
+                                                    hs["ctr"], hs["pool"], hs["off"], mc_repaired=True, bits_cap=len(hs["bits"]))
             if rc != 0:
                 raise SystemExit("bench.py: e2e arena / payload pool overflow")
             hs["used"] = used

@@ -311,15 +311,16 @@ class Engine:
 
     def demod_host_payloads_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, hits: np.ndarray,
                                  bits: Optional[np.ndarray], ctr: np.ndarray, pool: np.ndarray, off: np.ndarray,
-                                 mc_repaired: bool = False):
+                                 mc_repaired: bool = False, bits_cap: int = 0):
         """Decode + payload strings in one pipelined call with caller-owned (ideally pinned) arrays: ``pool`` uint8, ``off``
-        uint32[len(hits)]; hit i's string starts at ``pool[off[i]]`` and is NUL-terminated.  ``bits`` may be None for MS / MU
-        (the bit arena then stays on the device).  Returns (raw code, pool bytes used)."""
+        uint32[len(hits)]; hit i's string starts at ``pool[off[i]]`` and is NUL-terminated.  ``bits`` may be None (the bit
+        arena then stays on the device; ``bits_cap`` sizes it, default 16 words per hit slot).  Returns (raw code, pool bytes
+        used)."""
         used = C.c_size_t(0)
         rc = self.lib.sdb_demod_host_payloads(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
                                               digits.nbytes, len(msgs), out.ctypes.data, hits.ctypes.data, len(hits),
                                               bits.ctypes.data if bits is not None else None,
-                                              len(bits) if bits is not None else max(4096, 4 * len(hits)), ctr.ctypes.data,
+                                              len(bits) if bits is not None else (bits_cap or max(4096, 16 * len(hits))), ctr.ctypes.data,
                                               pool.ctypes.data, pool.nbytes, off.ctypes.data, C.byref(used))
         if rc not in (SDB_OK, SDB_E_OVERFLOW):
             raise self._err(rc, "sdb_demod_host_payloads")
