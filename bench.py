@@ -449,20 +449,35 @@ def run_ours(args):
         d2h += 8 * s["n"] + 16 + (16 + 4) * int(c[0])
 
     e2e_kind_s = [0.0] * len(slots)
+    # One handle (engine) per message kind, driven by its own host thread: the four host calls of a step are in flight together,
+    # so the pipeline head (first H2D) and tail (last D2H) of one kind run under the kernels of another and the small MC / MN
+    # calls disappear behind MS / MU.  ("one handle may be used by one host thread at a time", include/sdb200.h.)
+    from concurrent.futures import ThreadPoolExecutor
+
+    concurrent_kinds = not args.e2e_sequential
+    engines = [eng] + [SDProtocols(device=local, mc_repaired=True).engine() for _ in slots[1:]] if concurrent_kinds else [eng] * len(slots)
+    pool_exec = ThreadPoolExecutor(max_workers=len(slots)) if concurrent_kinds else None
+
+    def e2e_kind(i, nmsgs):
+        hs = host[i]
+        t_k = time.perf_counter()
+        msgs, digits = hs["msgs"], hs["digits"]
+        if nmsgs is not None and nmsgs[i] < len(msgs):
+            msgs = msgs[: nmsgs[i]]
+            digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
+        rc, used = engines[i].demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], None, hs["ctr"], hs["pool"],
+                                                       hs["off"], mc_repaired=True, bits_cap=len(hs["bits"]))
+        if rc != 0:
+            raise SystemExit("bench.py: e2e arena / payload pool overflow")
+        hs["used"] = used
+        e2e_kind_s[i] += time.perf_counter() - t_k
 
     def e2e_step(nmsgs=None):
-        for i, hs in enumerate(host):
-            t_k = time.perf_counter()
-            msgs, digits = hs["msgs"], hs["digits"]
-            if nmsgs is not None and nmsgs[i] < len(msgs):
-                msgs = msgs[: nmsgs[i]]
-                digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
-            rc, used = eng.demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], None,
-                                                    hs["ctr"], hs["pool"], hs["off"], mc_repaired=True, bits_cap=len(hs["bits"]))
-            if rc != 0:
-                raise SystemExit("bench.py: e2e arena / payload pool overflow")
-            hs["used"] = used
-            e2e_kind_s[i] += time.perf_counter() - t_k
+        if pool_exec is None:
+            for i in range(len(host)):
+                e2e_kind(i, nmsgs)
+        else:
+            list(pool_exec.map(lambda i: e2e_kind(i, nmsgs), range(len(host))))
 
     def timed_e2e(nmsgs=None):
         e2e_step(nmsgs)
@@ -725,6 +740,7 @@ def run_ours(args):
         "dtype": "int32", "data": "synthetic", "config": config_dict(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "payload_bytes_per_step": payload_bytes, "host_call_ms_per_kind": e2e_per_kind_ms,
+                "host_threads": len(slots) if concurrent_kinds else 1,
                 "includes": "pinned H2D, decode kernels, the payload string of every hit (preamble + hex + postamble) by the device format kernel "
                             "of each pipeline stage, D2H of result slots / hits / string offsets / strings"},
         "gpu_launches": args.steps * launches(full),
@@ -753,6 +769,7 @@ def main():
     ap.add_argument("--port", action="store_true", help="--impl reference: time the C oracle port instead of the Python reference")
     ap.add_argument("--ref-sample", type=int, default=50000, help="cpu_baseline: messages per class for the Python reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity / API legs")
+    ap.add_argument("--e2e-sequential", action="store_true", help="e2e: issue the four kinds one after the other from one thread")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-lines", action="store_true", help="skip the text-line (tokenizer) leg")
     args = ap.parse_args()

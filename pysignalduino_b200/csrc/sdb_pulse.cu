@@ -332,6 +332,8 @@ __device__ __forceinline__ bool target_present(WarpSm &sm, uint64_t tg, int L, i
     return true;
 }
 
+__constant__ uint32_t k_inv16[9] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u};   /* ceil(2^16 / d) */
+
 /*
  * General pattern_exists (pattern_utils.py:34-136): some distinct value has several candidate
  * slots, so the candidates are ordered by gap rank (then slot) and the cartesian product is
@@ -376,8 +378,10 @@ __device__ __noinline__ bool resolve_general(const SdbKeyTpl *__restrict__ k, in
 #pragma unroll
         for (int u = SDB_MAX_UNIQ - 1; u >= 0; u--) {
             if (u < K) {
-                int ch = rem % cnt[u];
-                rem /= cnt[u];
+                /* rem / cnt[u] without an integer division: cnt <= 8, rem < 8^4, so (rem * ceil(2^16 / cnt)) >> 16 is exact */
+                const int q = (int)(((uint32_t)rem * k_inv16[IDX(cnt[u], 9)]) >> 16);
+                const int ch = rem - q * cnt[u];
+                rem = q;
                 slot[u] = (lists[u] >> (4 * ch)) & 0xF;
             }
         }
@@ -569,13 +573,20 @@ __device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, i
     __syncwarp();
 }
 
+/* nb rounded up to a multiple of paddingbits (1, 4 or 8 in the shipped table: no integer division) */
+__device__ __forceinline__ int pad_up(int nb, int pad)
+{
+    return (pad & (pad - 1)) == 0 ? (nb + pad - 1) & ~(pad - 1) : (nb + pad - 1) / pad * pad;
+}
+
 /* post-demodulation on lane 0 (rare: ~10 of 129 protocols, frames <= ~150 bits) */
 __device__ __noinline__ void run_postdemod(int method, int nb)
 {
     WarpSm &sm = SM();
+    for (int w = lane_id(); w < BIT_WORDS; w += 32) sm.tmp[IDX(w, BIT_WORDS)] = 0;
+    __syncwarp();
     if (lane_id() == 0) {
         int no = 0;
-        for (int w = 0; w < BIT_WORDS; w++) sm.tmp[IDX(w, BIT_WORDS)] = 0;
         sm.pd_rc = postdemod(method, sm.val, nb, sm.tmp, &no);
         sm.pd_no = no;
     }
@@ -603,7 +614,7 @@ __device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp
         if ((flags & SDB_PF_HAS_LIR_MAX) && nb > pp->lir_max) return SDB_ST_OK;
     }
     const int pad = pp->padbits;
-    if (MS) nb = (nb + pad - 1) / pad * pad;      /* message_synced.py:198-200: pad BEFORE postDemod (appended bits are 0 already) */
+    if (MS) nb = pad_up(nb, pad);                 /* message_synced.py:198-200: pad BEFORE postDemod (appended bits are 0 already) */
 
     if (pp->postdemod) {
         if (has_f) {
@@ -624,7 +635,7 @@ __device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp
             __syncwarp();
         }
     }
-    if (!MS) nb = (nb + pad - 1) / pad * pad;     /* message_unsynced.py:257-259: pad AFTER postDemod */
+    if (!MS) nb = pad_up(nb, pad);                /* message_unsynced.py:257-259: pad AFTER postDemod */
 
     bool mm_host = false;
     if (MS) {
@@ -916,8 +927,12 @@ __device__ __noinline__ int mu_emit_match(const KArgs &A, const SdbPulseProto *p
         if (lane == 0) { sm.val[IDX(b0 >> 5, BIT_WORDS)] = vw; sm.fpl[IDX(b0 >> 5, BIT_WORDS)] = fw; }
     }
     __syncwarp();
-    for (int wq = lane; wq < BIT_WORDS; wq += 32)
-        if (wq >= ((n + 31) >> 5)) { sm.val[IDX(wq, BIT_WORDS)] = 0; sm.fpl[IDX(wq, BIT_WORDS)] = 0; }
+    {
+        /* only the words padding can reach need clearing (pad <= 64 bits): the ballots above wrote every word below them, the
+         * consumers read (nb_padded + 31) / 32 words */
+        const int wq = ((n + 31) >> 5) + lane;
+        if (lane < 4 && wq < BIT_WORDS) { sm.val[IDX(wq, BIT_WORDS)] = 0; sm.fpl[IDX(wq, BIT_WORDS)] = 0; }
+    }
     __syncwarp();
     if (lane == 0) {
         if (tail == 0) sm.val[IDX(n >> 5, BIT_WORDS)] |= 1u << (n & 31);
@@ -1296,7 +1311,7 @@ __device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int
     for (int i = lane; i < BIT_WORDS; i += 32) { sm.val[IDX(i, BIT_WORDS)] = 0; sm.fpl[IDX(i, BIT_WORDS)] = 0; }
     __syncwarp();
     int nb = 0;
-    const int nchunks = (dlen - ms + w - 1) / w;
+    const int nchunks = (dlen - ms + w - 1) >> (w == 1 ? 0 : (w == 2 ? 1 : 2));      /* w is 1, 2 or 4 (table.py) */
     for (int b0 = 0; b0 < nchunks; b0 += 32) {
         int c = b0 + lane;
         int cls = 4;                               /* 0 '1', 1 '0', 2 'F', 3 skip, 4 stop, 5 none */

@@ -29,7 +29,10 @@ size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots hand
 #define SDB_MU_CHUNK 1048576u
 #endif
 /* SDB_MU_CHUNK: messages per launch group of the device-resident calls (bounds the survivor scratch: chunk * n_mu * 16 B) */
-#define SDB_PIPE_CHUNK 262144u  /* messages per pipeline stage of the host-buffer calls (H2D / kernels / D2H overlap) */
+#ifndef SDB_PIPE_CHUNK
+#define SDB_PIPE_CHUNK 262144u
+#endif
+/* SDB_PIPE_CHUNK: messages per pipeline stage of the host-buffer calls (H2D / kernels / D2H overlap) */
 
 int launch_hex(int kind, int mc_repaired, const SdbDevTable &tab, const SdbHexMsg *d_msgs, const uint8_t *d_digits,
                uint32_t n, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
