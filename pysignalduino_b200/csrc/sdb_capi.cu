@@ -136,10 +136,10 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     h->tab.hex = reinterpret_cast<const SdbHexProto *>(b + hd->off_hex);
     h->tab.n_ms = hd->n_ms; h->tab.n_mu = hd->n_mu; h->tab.n_clk = hd->n_clk; h->tab.nproto = hd->nproto;
     /* persistent grids: every SM filled with as many CTAs as fit */
-    h->grid_ms = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MS);
-    h->grid_mu = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MU);
+    h->grid_ms = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MS, h->tab);
+    h->grid_mu = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MU, h->tab);
     h->grid_hex = h->sm_count * 8;
-    h->grid_long = h->sm_count * sdb_long::long_blocks_per_sm();
+    h->grid_long = h->sm_count * sdb_long::long_blocks_per_sm(h->tab);
 #undef CKC
     *out = h;
     return SDB_OK;

@@ -233,6 +233,29 @@ struct __align__(16) WarpSm {
 __shared__ WarpSm g_sm[WARPS];
 #define SM() (g_sm[threadIdx.x >> 5])
 
+/* CTA-shared copies of what every lane of the resolve kernels reads all the time (dynamic shared memory, filled once per CTA):
+ * the (clock, interval) pairs and the hot fields of the protocol rows.  The full 248-byte rows stay in global memory for the
+ * rare paths (several candidates, long starts); with each lane on a different row those reads were the main source of
+ * long-scoreboard stalls (profiles/README.md, round 2). */
+struct HotKey {                       /* 12 bytes */
+    uint8_t  len, nuniq;
+    uint16_t vidx[2];                 /* candidate-mask rows of the first two distinct values */
+    uint16_t rsv;
+    uint32_t uidx;
+};
+struct HotRow {                       /* 52 bytes */
+    HotKey   key[4];
+    uint8_t  width, clk_idx;
+    int16_t  regex_min;
+};
+extern __shared__ __align__(16) uint8_t g_dyn[];
+#define HOT_VALS() (reinterpret_cast<const SdbValRow *>(g_dyn))
+#define HOT_ROWS(nvals) (reinterpret_cast<const HotRow *>(g_dyn + (((nvals) * sizeof(SdbValRow) + 15) & ~(size_t)15)))
+__host__ __device__ __forceinline__ size_t hot_bytes(uint32_t nvals, uint32_t nrows)
+{
+    return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (size_t)nrows * sizeof(HotRow) + 16;
+}
+
 /* ---- small helpers ------------------------------------------------------------------- */
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -1110,14 +1133,14 @@ __device__ __forceinline__ int tkey_min8(const int k[8])
     int m = min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
     return m;
 }
-__device__ __forceinline__ bool tres(const SdbKeyTpl *__restrict__ k, int clk_idx, const WarpSm &sm, int from,
+__device__ __forceinline__ bool tres(const HotKey &hk, const SdbKeyTpl *__restrict__ k, int clk_idx, const WarpSm &sm, int from,
                                      uint32_t &code, int &pos)
 {
-    const int L = k->len, K = k->nuniq;
-    const uint32_t uidx = k->uidx, ids = sm.pat_ids;
+    const int L = hk.len, K = hk.nuniq;
+    const uint32_t uidx = hk.uidx, ids = sm.pat_ids;
     /* candidate slots of the (<= 2) distinct values (:73-76): looked up in the per-message mask table */
-    const uint32_t ca = sm.M[IDX(k->vidx[0], SDB_MAX_VALS)];
-    const uint32_t cb = K > 1 ? sm.M[IDX(k->vidx[1], SDB_MAX_VALS)] : 0u;
+    const uint32_t ca = sm.M[IDX(hk.vidx[0], SDB_MAX_VALS)];
+    const uint32_t cb = K > 1 ? sm.M[IDX(hk.vidx[1], SDB_MAX_VALS)] : 0u;
     if (!ca || (K > 1 && !cb)) return false;                  /* :78-80 */
     if (!(ca & (ca - 1)) && !(cb & (cb - 1))) {
         /* the common case: one candidate per value -> a single combination, no ordering needed */
@@ -1220,23 +1243,23 @@ __device__ __noinline__ bool tpre(const SdbKeyTpl *__restrict__ k, const WarpSm 
  * Returns 0 dead, 1 resolved (codes = start | one<<8 | zero<<16 | float<<24, s0f = s0 | hasf<<16),
  * 2 = needs the warp-level path (for a long start: after one / zero passed a pre-screen on the whole D).
  * after_start: the warp has resolved a long start meanwhile (D' begins at s0_in); one / zero / float follow here. */
-__device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
+__device__ __forceinline__ int thread_resolve_mu(const HotRow &hr, const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
                                                  uint32_t &codes, uint32_t &s0f, bool after_start, int s0_in)
 {
-    const int width = pp->width;
-    if (width > 2 || (width == 1 && pp->key[0].len > 2)) return 2;   /* 4-digit symbols: warp-level path for every key */
-    const int clk_idx = pp->clk_idx;
-    const bool long_start = !after_start && pp->key[0].len > 2;   /* needs a warp-wide search: only pre-screen one / zero here */
+    const int width = hr.width;
+    if (width > 2 || (width == 1 && hr.key[0].len > 2)) return 2;   /* 4-digit symbols: warp-level path for every key */
+    const int clk_idx = hr.clk_idx;
+    const bool long_start = !after_start && hr.key[0].len > 2;   /* needs a warp-wide search: only pre-screen one / zero here */
     if (long_start && !tpre(&pp->key[0], sm)) return 0;
     uint32_t acc = 0, hasf = 0;
     int s0 = after_start ? s0_in : 0;
 #pragma unroll 1
     for (int kk = (long_start || after_start) ? 1 : 0; kk < 4; kk++) {   /* start (:67-88), then one / zero / float (:99-141) */
-        const SdbKeyTpl *k = &pp->key[kk];
-        if (!k->len) continue;
+        const HotKey &hk = hr.key[kk];
+        if (!hk.len) continue;
         uint32_t code = 0;
         int p = 0;
-        if (!tres(k, clk_idx, sm, kk == 0 ? 0 : s0, code, p)) {
+        if (!tres(hk, &pp->key[kk], clk_idx, sm, kk == 0 ? 0 : s0, code, p)) {
             if (kk == 3) break;                               /* float is optional (:138) */
             return 0;
         }
@@ -1249,10 +1272,10 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
     if (width == 2) {
         const uint32_t c1 = (acc >> 8) & 0xFF, c0 = (acc >> 16) & 0xFF, cf = acc >> 24;
         uint32_t cnt = sm.cnt2[IDX((c1 & 15) * 10 + (c1 >> 4), 100)];
-        if (pp->key[2].len && c0 != c1) cnt += sm.cnt2[IDX((c0 & 15) * 10 + (c0 >> 4), 100)];
+        if (hr.key[2].len && c0 != c1) cnt += sm.cnt2[IDX((c0 & 15) * 10 + (c0 >> 4), 100)];
         if (hasf && cf != c1 && cf != c0) cnt += sm.cnt2[IDX((cf & 15) * 10 + (cf >> 4), 100)];
         const int best = max((int)(cnt & 0xFFFF), (int)(cnt >> 16));
-        if (best < (int)pp->regex_min) return 0;
+        if (best < (int)hr.regex_min) return 0;
     }
     codes = acc;
     s0f = (uint32_t)s0 | (hasf << 16);
@@ -1263,25 +1286,25 @@ __device__ __forceinline__ int thread_resolve_mu(const SdbPulseProto *__restrict
 /* Thread-level resolution of one MS protocol (2-digit symbols, sync of <= 2 pulses): message_synced.py:109-163.
  * Returns 0 dead, 1 resolved (codes = sync | one<<8 | zero<<16 | float<<24, msf = message_start | hasf<<16),
  * 2 = needs the warp-level path.  Every pattern_exists call of MS searches the whole D (from = 0). */
-__device__ __forceinline__ int thread_resolve_ms(const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
+__device__ __forceinline__ int thread_resolve_ms(const HotRow &hr, const SdbPulseProto *__restrict__ pp, const WarpSm &sm,
                                                  uint32_t &codes, uint32_t &msf)
 {
-    if (pp->width != 2 || pp->key[0].len > 2) return 2;
+    if (hr.width != 2 || hr.key[0].len > 2) return 2;
     uint32_t acc = 0, hasf = 0;
     int spos = 0;
 #pragma unroll 1
     for (int kk = 0; kk < 4; kk++) {                          /* sync, one, zero, float (:109) */
-        const SdbKeyTpl *k = &pp->key[kk];
-        if (!k->len) continue;
+        const HotKey &hk = hr.key[kk];
+        if (!hk.len) continue;
         uint32_t code = 0;
         int p = 0;
-        if (!tres(k, 0, sm, 0, code, p)) {
+        if (!tres(hk, &pp->key[kk], 0, sm, 0, code, p)) {
             if (kk == 3) break;                               /* :160-163 float may be missing */
             return 0;
         }
         if (kk == 0) {                                        /* :140-156 */
-            spos = p + k->len;
-            if ((int)pp->regex_min * 2 > sm.dlen - spos) return 0;
+            spos = p + hk.len;
+            if ((int)hr.regex_min * 2 > sm.dlen - spos) return 0;
         }
         if (kk == 3) hasf = 1;
         acc |= code << (8 * kk);
@@ -1511,7 +1534,7 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
     uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
     for (int v = v0 + lane; v < v1; v += 32) {
-        const SdbValRow vr = A.tab.vals[v];
+        const SdbValRow vr = HOT_VALS()[v];
         const int4 row = *reinterpret_cast<const int4 *>(&sm.T[IDX(vr.clk_idx, SDB_MAX_CLK)][0]);
         const int lo = vr.lo, hi = vr.hi;
         int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
@@ -1549,6 +1572,26 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
     const int lane = lane_id();
     const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
     const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
+
+    /* once per CTA: the pairs and the hot protocol fields into shared memory */
+    {
+        SdbValRow *sv = reinterpret_cast<SdbValRow *>(g_dyn);
+        for (uint32_t v = threadIdx.x; v < A.tab.n_vals; v += blockDim.x) sv[v] = A.tab.vals[v];
+        HotRow *hrw = const_cast<HotRow *>(HOT_ROWS(A.tab.n_vals));
+        for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
+            const SdbPulseProto *pr = &rows[r];
+            HotRow h;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                h.key[kk].len = pr->key[kk].len; h.key[kk].nuniq = pr->key[kk].nuniq; h.key[kk].uidx = pr->key[kk].uidx;
+                h.key[kk].vidx[0] = pr->key[kk].vidx[0]; h.key[kk].vidx[1] = pr->key[kk].vidx[1]; h.key[kk].rsv = 0;
+            }
+            h.width = pr->width; h.clk_idx = (uint8_t)pr->clk_idx; h.regex_min = pr->regex_min;
+            hrw[r] = h;
+        }
+        __syncthreads();
+    }
+    const HotRow *hot = HOT_ROWS(A.tab.n_vals);
 
     uint32_t tk_base = 0, tk_left = 0, mi = 0;
     while (next_message(A, tk_base, tk_left, mi)) {
@@ -1604,7 +1647,7 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
                         if (state == 4) {
                             const SdbPulseProto *pq = &rows[q];
                             uint32_t codes = 0, sf = 0;
-                            state = MS ? thread_resolve_ms(pq, sm, codes, sf) : thread_resolve_mu(pq, sm, codes, sf, pass == 1, s0w);
+                            state = MS ? thread_resolve_ms(hot[q], pq, sm, codes, sf) : thread_resolve_mu(hot[q], pq, sm, codes, sf, pass == 1, s0w);
                             rec.start = pass == 1 ? long_start : (uint64_t)(codes & 0xFF);
                             rec.c1 = (codes >> 8) & 0xFF; rec.c0 = (codes >> 16) & 0xFF; rec.cf = codes >> 24;
                             rec.meta = (uint16_t)((sf & SURV_POS_MASK) | ((sf >> 16) ? SURV_HASF : 0));
@@ -1852,14 +1895,23 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_emit_kernel(KArgs A)
     }
 }
 
-int pulse_blocks_per_sm(int kind)
+/* dynamic shared memory of the resolve kernels (the CTA-shared table copies); opting in is needed beyond 48 KB in total */
+template <bool MS>
+static size_t resolve_dyn_smem(const SdbDevTable &tab)
+{
+    const size_t bytes = hot_bytes(tab.n_vals, MS ? tab.n_ms : tab.n_mu);
+    cudaFuncSetAttribute(resolve_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return bytes;
+}
+
+int pulse_blocks_per_sm(int kind, const SdbDevTable &tab)
 {
     int a = 0, b = 0;
     if (kind == SDB_KIND_MS) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, SDB_PULSE_THREADS, resolve_dyn_smem<true>(tab));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, SDB_PULSE_THREADS, 0);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false>, SDB_PULSE_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false>, SDB_PULSE_THREADS, resolve_dyn_smem<false>(tab));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mu_match_kernel, SDB_PULSE_THREADS, 0);
         int c = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, mu_emit_kernel, SDB_PULSE_THREADS, 0);
@@ -1942,10 +1994,10 @@ int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, co
         cudaError_t e = cudaMemsetAsync(tickets, 0, 16 * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return (int)e;
         if (ms) {
-            A.ticket = tickets + 0; resolve_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 0; resolve_kernel<true><<<g, SDB_PULSE_THREADS, hot_bytes(tab.n_vals, tab.n_ms), stream>>>(A);
             A.ticket = tickets + 1; scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
         } else {
-            A.ticket = tickets + 0; resolve_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = tickets + 0; resolve_kernel<false><<<g, SDB_PULSE_THREADS, hot_bytes(tab.n_vals, tab.n_mu), stream>>>(A);
             A.ticket = tickets + 1; mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
             A.ticket = tickets + 2; mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
             A.ticket = tickets + 3; A.ticket_batch = 256; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
@@ -1973,12 +2025,15 @@ unsigned int debug_violations_long(bool reset)
 #endif
 }
 
-int long_blocks_per_sm()
+int long_blocks_per_sm(const SdbDevTable &tab)
 {
     int a = 0, b = 0, c = 0, d = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, KTHREADS, 0);
+    const size_t dms = hot_bytes(tab.n_vals, tab.n_ms), dmu = hot_bytes(tab.n_vals, tab.n_mu);
+    cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dms);
+    cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dmu);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, KTHREADS, dms);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, KTHREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false>, KTHREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false>, KTHREADS, dmu);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, scan_kernel<false>, KTHREADS, 0);
     int nb = a;
     if (b < nb) nb = b;
@@ -2033,10 +2088,10 @@ int launch_long(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, con
     A.surv = static_cast<SdbSurv *>(surv); A.surv_cnt = surv_cnt; A.surv_stride = surv_stride;
     A.match = nullptr; A.match_cnt = nullptr; A.ticket_batch = 1; A.long_list = long_list; A.long_cnt = long_cnt;
     if (kind == SDB_KIND_MS) {
-        A.ticket = tickets + 0; resolve_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = tickets + 0; resolve_kernel<true><<<grid, KTHREADS, hot_bytes(tab.n_vals, tab.n_ms), stream>>>(A);
         A.ticket = tickets + 1; scan_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
     } else {
-        A.ticket = tickets + 0; resolve_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = tickets + 0; resolve_kernel<false><<<grid, KTHREADS, hot_bytes(tab.n_vals, tab.n_mu), stream>>>(A);
         A.ticket = tickets + 1; scan_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
     }
     return (int)cudaGetLastError();

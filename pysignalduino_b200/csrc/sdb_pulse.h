@@ -18,7 +18,7 @@ namespace sdb {
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
                  SdbCounters *d_ctr, int grid, int grid_long, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream);
-int pulse_blocks_per_sm(int kind);
+int pulse_blocks_per_sm(int kind, const SdbDevTable &tab);
 unsigned int debug_violations(bool reset);   /* bounds-check build only; 0xFFFFFFFF otherwise */
 size_t mu_scratch_bytes(uint32_t n_mu, uint32_t chunk);   /* survivor slots handed from mu_resolve_kernel to mu_scan_kernel */
 
@@ -58,7 +58,7 @@ int launch_unit_postdemod(int method, const uint8_t *d_in, uint32_t n_in, uint8_
 
 /* sdb_pulse_long.cu: the same kernels sized for SDB_FAST_DIGITS < D <= SDB_MAX_DIGITS */
 namespace sdb_long {
-int long_blocks_per_sm();
+int long_blocks_per_sm(const SdbDevTable &tab);
 int launch_unit_pattern(const SdbKeyTpl &tpl, const uint16_t *d_rank, const int16_t *d_tenths, uint32_t pat_ids, int npat,
                         const uint8_t *d_digits, int dlen, int32_t *d_res, cudaStream_t stream);
 unsigned int debug_violations_long(bool reset);
