@@ -251,9 +251,11 @@ struct HotRow {                       /* 52 bytes */
 extern __shared__ __align__(16) uint8_t g_dyn[];
 #define HOT_VALS() (reinterpret_cast<const SdbValRow *>(g_dyn))
 #define HOT_ROWS(nvals) (reinterpret_cast<const HotRow *>(g_dyn + (((nvals) * sizeof(SdbValRow) + 15) & ~(size_t)15)))
+/* then, 16-byte aligned, the MU clocks: n_clk values and n_clk times 10 / clock */
+#define HOT_CLK(nvals, nrows) (reinterpret_cast<const double *>(g_dyn + (((nvals) * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((nrows) * sizeof(HotRow) + 15) & ~(size_t)15)))
 __host__ __device__ __forceinline__ size_t hot_bytes(uint32_t nvals, uint32_t nrows)
 {
-    return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (size_t)nrows * sizeof(HotRow) + 16;
+    return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((size_t)nrows * sizeof(HotRow) + 15) & ~(size_t)15) + 2 * SDB_MAX_CLK * sizeof(double) + 16;
 }
 
 /* ---- small helpers ------------------------------------------------------------------- */
@@ -1521,10 +1523,11 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
     } else {
         /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
         const int ncl = A.tab.n_clk;
+        const double *hclk = HOT_CLK(A.tab.n_vals, A.tab.n_mu);
 #pragma unroll 1
         for (int idx = lane; idx < ncl * 8; idx += 32) {
             int c = idx >> 3, j = idx & 7;
-            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)((j < npat && SLOT_USED(j)) ? tenths_fast(sm.pat[j], __ldg(&A.tab.clk[c]), __ldg(&A.tab.clk[ncl + c])) : -32768);
+            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)((j < npat && SLOT_USED(j)) ? tenths_fast(sm.pat[j], hclk[c], hclk[ncl + c]) : -32768);
         }
         v0 = 0; v1 = (int)A.tab.n_mu_vals;
     }
@@ -1588,6 +1591,10 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
             }
             h.width = pr->width; h.clk_idx = (uint8_t)pr->clk_idx; h.regex_min = pr->regex_min;
             hrw[r] = h;
+        }
+        if (!MS) {
+            double *hc = const_cast<double *>(HOT_CLK(A.tab.n_vals, nrows));
+            for (uint32_t c = threadIdx.x; c < 2 * A.tab.n_clk; c += blockDim.x) hc[c] = A.tab.clk[c];
         }
         __syncthreads();
     }

@@ -81,3 +81,40 @@ def compare_raw(sdp, batch, res, ora_status, ora_hits, ora_pool, check_bits=True
     if pool != ora_pool:
         return "payload bytes differ"
     return ""
+
+
+def compare_payloads(batch, res, pool, off, ora_status, ora_hits, ora_pool) -> str:
+    """The same comparison for a result of ``sdb_demod_host_payloads`` (strings written by the DEVICE format kernel:
+    NUL-terminated, one offset per hit, pool in CTA order): status, protocol, bit length (MS / MU) and payload bytes of every
+    hit against the oracle's arrays; returns '' or a description."""
+    import numpy as np
+
+    out, hits = res.out, res.hits
+    if not np.array_equal(out["status"], ora_status):
+        return f"status differs for {int((out['status'] != ora_status).sum())} messages"
+    nh = out["nhits"].astype(np.int64)
+    total = int(nh.sum())
+    if total != len(hits):
+        return f"sum(nhits)={total} != len(hits)={len(hits)}"
+    within = np.arange(total) - np.repeat(np.cumsum(nh) - nh, nh)
+    order = np.repeat(out["hit_off"].astype(np.int64), nh) + within
+    g = hits[order]
+    o = off[order].astype(np.int64)
+    keep = ~(((g["flags"] & 2) != 0) & (g["aux"] != 0))          # continuation rows of a TFA list carry no string
+    g, o = g[keep], o[keep]
+    if len(g) != len(ora_hits):
+        return f"{len(g)} device hits vs {len(ora_hits)} oracle hits"
+    if not np.array_equal(g["proto"].astype(np.int64), ora_hits["proto"].astype(np.int64)):
+        return "protocol ids differ"
+    if batch.kind <= 1 and not np.array_equal(g["nbits"].astype(np.int64), ora_hits["bit_length"].astype(np.int64)):
+        return "bit_length differs"
+    pool = np.asarray(pool, dtype=np.uint8)
+    nul = np.flatnonzero(pool == 0)
+    lens = nul[np.searchsorted(nul, o)] - o
+    want = ora_hits["payload_len"].astype(np.int64)
+    if not np.array_equal(lens, want):
+        return f"payload lengths differ at {int((lens != want).sum())} hits"
+    idx = np.repeat(o - (np.cumsum(lens) - lens), lens) + np.arange(int(lens.sum()))
+    if pool[idx].tobytes() != ora_pool:
+        return "payload bytes differ"
+    return ""
