@@ -437,16 +437,16 @@ def run_ours(args):
         t_ctr = torch.zeros(16, dtype=torch.uint8).pin_memory()
         c = ctrs[s["name"]]
         t_pool = torch.empty(int(c[0]) * 48 + 4096, dtype=torch.uint8).pin_memory()
-        t_off = torch.empty(4 * s["hits_cap"], dtype=torch.uint8).pin_memory()
+        t_off = torch.empty(pack.PAYHIT_DTYPE.itemsize * s["hits_cap"], dtype=torch.uint8).pin_memory()
         host.append({
             "kind": s["kind"], "keep": (t_msgs, t_dig, t_out, t_hits, t_bits, t_ctr, t_pool, t_off), "msgs": msgs, "digits": digits,
             "out": t_out.numpy().view(pack.MSGOUT_DTYPE), "hits": t_hits.numpy().view(pack.HIT_DTYPE),
             "bits": t_bits.numpy().view(np.uint32), "ctr": t_ctr.numpy().view(pack.COUNTERS_DTYPE),
-            "pool": t_pool.numpy(), "off": t_off.numpy().view(np.uint32), "used": 0,
+            "pool": t_pool.numpy(), "phits": t_off.numpy().view(pack.PAYHIT_DTYPE), "used": 0,
         })
         h2d += msgs.nbytes + digits.nbytes
-        # result slots + counters + hits + string offsets (+ the strings, counted after the first e2e step)
-        d2h += 8 * s["n"] + 16 + (16 + 4) * int(c[0])
+        # result slots + counters + 12-byte payload hit records (+ the strings, counted after the first e2e step)
+        d2h += 8 * s["n"] + 16 + pack.PAYHIT_DTYPE.itemsize * int(c[0])
 
     e2e_kind_s = [0.0] * len(slots)
     # One handle (engine) per message kind, driven by its own host thread: the four host calls of a step are in flight together,
@@ -465,8 +465,8 @@ def run_ours(args):
         if nmsgs is not None and nmsgs[i] < len(msgs):
             msgs = msgs[: nmsgs[i]]
             digits = digits[: int(hs["msgs"]["doff"][nmsgs[i]]) * 16 + 64]
-        rc, used = engines[i].demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["hits"], None, hs["ctr"], hs["pool"],
-                                                       hs["off"], mc_repaired=True, bits_cap=len(hs["bits"]))
+        rc, used = engines[i].demod_host_payloads_into(hs["kind"], msgs, digits, hs["out"], hs["phits"], hs["ctr"], hs["pool"],
+                                                       mc_repaired=True, bits_cap=len(hs["bits"]))
         if rc != 0:
             raise SystemExit("bench.py: e2e arena / payload pool overflow")
         hs["used"] = used
@@ -503,7 +503,7 @@ def run_ours(args):
     nproto = len(eng.table.ids)
     hist = np.zeros(nproto, dtype=np.int64)
     for s, hs in zip(slots, host):
-        hist += np.bincount(hs["hits"]["proto"][: int(hs["ctr"]["hits"][0])].astype(np.int64), minlength=nproto)[:nproto]
+        hist += np.bincount(hs["phits"]["proto"][: int(hs["ctr"]["hits"][0])].astype(np.int64), minlength=nproto)[:nproto]
     th = torch.from_numpy(hist).to(dev)
     if world > 1:
         dist.all_reduce(th, op=dist.ReduceOp.SUM)
@@ -742,7 +742,7 @@ def run_ours(args):
                 "payload_bytes_per_step": payload_bytes, "host_call_ms_per_kind": e2e_per_kind_ms,
                 "host_threads": len(slots) if concurrent_kinds else 1,
                 "includes": "pinned H2D, decode kernels, the payload string of every hit (preamble + hex + postamble) by the device format kernel "
-                            "of each pipeline stage, D2H of result slots / hits / string offsets / strings"},
+                            "of each pipeline stage, D2H of result slots / 12-byte payload hit records / strings"},
         "gpu_launches": args.steps * launches(full),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "per_kernel": per_kernel,
         "hit_histogram": {"protocols_with_hits": int((hist > 0).sum()), "total_hits": int(hist.sum()), "ranks": world,

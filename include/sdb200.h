@@ -126,6 +126,17 @@ typedef struct SdbHit {
     uint8_t  rsv;
 } SdbHit;
 
+/* One hit as sdb_demod_host_payloads returns it, 12 bytes: what a caller needs next to the payload string (the message is
+ * implied by SdbMsgOut.hit_off / nhits, the bits stay on the device). */
+typedef struct SdbPayloadHit {
+    uint32_t str_off;            /* the NUL-terminated payload string starts at pool[str_off]                 */
+    uint16_t proto;              /* as SdbHit                                                                */
+    uint16_t nbits;
+    uint16_t aux;
+    uint8_t  flags;
+    uint8_t  rsv;
+} SdbPayloadHit;
+
 #define SDB_HIT_HAS_F   0x01     /* a second plane of nbits follows: 1 = symbol is 'F' (float)           */
 #define SDB_HIT_LIST    0x02     /* MC TFA: element of the duplicate list (manchester.py:705-717)        */
 #define SDB_HIT_FIELDS  0x04     /* MN: bits hold decoder fields, host renders "OK 9 ..." / "OK 24 ..."  */
@@ -200,14 +211,18 @@ int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
  * sdb_demod_host plus the payload string of every hit in one call: what SDProtocols.demodulate() returns per hit is a
  * string (preamble + hex / bits + postamble, message_synced.py:224-231, message_unsynced.py:254-274, manchester.py:131-132).
  * A format kernel runs after the decode kernels of every pipeline stage and the strings travel back with the hits under the
- * next stage's kernels; `bits` may be NULL (the bit arena is then not copied back).  Hit i's string starts at pool[str_off[i]] and is NUL-terminated (str_off has hits_cap entries; the pool is NOT in
- * hit order).  SDB_E_OVERFLOW when an arena or the pool is too small (counters / *pool_used say how much is needed).
+ * next stage's kernels, as 12-byte SdbPayloadHit records (string offset, protocol, bit length, flags) + the string pool:
+ * 27.5 bytes per hit on the wire instead of 16 (SdbHit) + 4 (offset) + 15.5 (string) — with N ranks on one host the host's
+ * copy bandwidth is what bounds the end-to-end path.  `hits` and `bits` may be NULL (the 16-byte records / the bit arena are
+ * then not copied back; hits_cap / bits_cap still size the device arenas).  phits has hits_cap entries; hit i's string
+ * starts at pool[phits[i].str_off] and is NUL-terminated (the pool is NOT in hit order).  SDB_E_OVERFLOW when an arena or
+ * the pool is too small (counters / *pool_used say how much is needed).
  */
 int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
                             const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                             SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                             uint32_t *bits, uint32_t bits_cap, SdbCounters *counters,
-                            char *pool, size_t pool_cap, uint32_t *str_off, size_t *pool_used);
+                            char *pool, size_t pool_cap, SdbPayloadHit *phits, size_t *pool_used);
 
 /*
  * Host-side result formatting (the payload string of every hit:

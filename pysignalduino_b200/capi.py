@@ -309,25 +309,29 @@ class Engine:
             raise self._err(rc, "sdb_demod_host")
         return rc
 
-    def demod_host_payloads_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, hits: np.ndarray,
-                                 bits: Optional[np.ndarray], ctr: np.ndarray, pool: np.ndarray, off: np.ndarray,
-                                 mc_repaired: bool = False, bits_cap: int = 0):
-        """Decode + payload strings in one pipelined call with caller-owned (ideally pinned) arrays: ``pool`` uint8, ``off``
-        uint32[len(hits)]; hit i's string starts at ``pool[off[i]]`` and is NUL-terminated.  ``bits`` may be None (the bit
-        arena then stays on the device; ``bits_cap`` sizes it, default 16 words per hit slot).  Returns (raw code, pool bytes
-        used)."""
+    def demod_host_payloads_into(self, kind: int, msgs: np.ndarray, digits: np.ndarray, out: np.ndarray, phits: np.ndarray,
+                                 ctr: np.ndarray, pool: np.ndarray, mc_repaired: bool = False, bits_cap: int = 0,
+                                 hits: Optional[np.ndarray] = None, bits: Optional[np.ndarray] = None):
+        """Decode + payload strings in one pipelined call with caller-owned (ideally pinned) arrays: ``phits`` is a
+        ``pack.PAYHIT_DTYPE`` array (12 bytes per hit: string offset, protocol, bit length, flags), ``pool`` uint8; hit i's
+        string starts at ``pool[phits[i]["off"]]`` and is NUL-terminated.  The 16-byte ``hits`` records and the ``bits``
+        arena are optional extras (None: they stay on the device; ``bits_cap`` sizes the device arena, default 16 words per
+        hit slot).  Returns (raw code, pool bytes used)."""
         used = C.c_size_t(0)
+        if hits is not None and len(hits) < len(phits):
+            raise ValueError("hits must have at least len(phits) entries")
         rc = self.lib.sdb_demod_host_payloads(self.h, kind, 1 if mc_repaired else 0, msgs.ctypes.data, digits.ctypes.data,
-                                              digits.nbytes, len(msgs), out.ctypes.data, hits.ctypes.data, len(hits),
+                                              digits.nbytes, len(msgs), out.ctypes.data,
+                                              hits.ctypes.data if hits is not None else None, len(phits),
                                               bits.ctypes.data if bits is not None else None,
-                                              len(bits) if bits is not None else (bits_cap or max(4096, 16 * len(hits))), ctr.ctypes.data,
-                                              pool.ctypes.data, pool.nbytes, off.ctypes.data, C.byref(used))
+                                              len(bits) if bits is not None else (bits_cap or max(4096, 16 * len(phits))), ctr.ctypes.data,
+                                              pool.ctypes.data, pool.nbytes, phits.ctypes.data, C.byref(used))
         if rc not in (SDB_OK, SDB_E_OVERFLOW):
             raise self._err(rc, "sdb_demod_host_payloads")
         return rc, used.value
 
     def demod_payloads(self, batch, mc_repaired: bool = False):
-        """Convenience form: -> (Result without bits for MS / MU, pool bytes, offsets uint32[nhits])."""
+        """Convenience form: -> (Result whose ``hits`` are PAYHIT_DTYPE records and whose ``bits`` are empty, pool bytes)."""
         n = batch.n
         kind = batch.kind
         msgs = np.ascontiguousarray(batch.msgs)
@@ -336,18 +340,16 @@ class Engine:
         ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
         hits_cap, bits_cap, pool_cap = max(1024, 4 * n), max(4096, 16 * n), max(4096, 96 * n)
         while True:
-            hits = np.empty(hits_cap, dtype=pack.HIT_DTYPE)
-            bits = np.empty(bits_cap, dtype=np.uint32)
+            phits = np.empty(hits_cap, dtype=pack.PAYHIT_DTYPE)
             pool = np.empty(pool_cap, dtype=np.uint8)
-            off = np.empty(hits_cap, dtype=np.uint32)
-            rc, used = self.demod_host_payloads_into(kind, msgs, digits, out, hits, bits, ctr, pool, off, mc_repaired=mc_repaired)
+            rc, used = self.demod_host_payloads_into(kind, msgs, digits, out, phits, ctr, pool, mc_repaired=mc_repaired, bits_cap=bits_cap)
             if rc == SDB_E_OVERFLOW:
                 hits_cap = max(hits_cap, int(ctr["hits"][0]) + 16)
                 bits_cap = max(bits_cap, int(ctr["words"][0]) + 16)
                 pool_cap = max(pool_cap, used + 64)
                 continue
             nh = int(ctr["hits"][0])
-            return Result(kind, out, hits[:nh], bits[: int(ctr["words"][0])], ctr[0]), pool[:used], off[:nh]
+            return Result(kind, out, phits[:nh], np.zeros(0, dtype=np.uint32), ctr[0]), pool[:used]
 
     # ---- text lines (tokenizer kernel + demodulation) ---------------------------------------
     def demod_lines(self, kind: int, text: np.ndarray, line_off: np.ndarray, line_len: np.ndarray,

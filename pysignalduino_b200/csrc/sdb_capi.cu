@@ -49,7 +49,7 @@ struct SdbHandle {
     uint32_t snap_cap = 0;
     uint16_t *d_rowmap = nullptr;       /* [nproto] MS rows, then [nproto] MU rows: table-order protocol index -> row (format kernel) */
     char *d_chars = nullptr;    size_t cap_chars = 0;     /* device payload pool of sdb_demod_host_payloads */
-    uint32_t *d_stroff = nullptr; size_t cap_stroff = 0;
+    SdbPayloadHit *d_phits = nullptr; size_t cap_phits = 0;
     uint32_t *d_fmt = nullptr;          /* [0] first hit not formatted yet, [1] scratch, [2] pool bytes handed out */
 };
 
@@ -151,7 +151,7 @@ extern "C" void sdb_destroy(SdbHandle *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch); cudaFree(h->d_text); cudaFree(h->d_lines);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
-    cudaFree(h->d_rowmap); cudaFree(h->d_chars); cudaFree(h->d_stroff); cudaFree(h->d_fmt);
+    cudaFree(h->d_rowmap); cudaFree(h->d_chars); cudaFree(h->d_phits); cudaFree(h->d_fmt);
     if (h->h_used) cudaFreeHost(h->h_used);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
@@ -282,7 +282,7 @@ struct ArenaDrain { uint32_t hits = 0, words = 0, chars = 0; };
  * kernels and copied back with the hits, under the next stage's kernels */
 struct PayloadSink {
     char *pool = nullptr; uint32_t pool_cap = 0;
-    uint32_t *str_off = nullptr;
+    SdbPayloadHit *phits = nullptr;
     uint32_t used = 0;
 };
 static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, uint32_t hits_cap, uint32_t *bits, uint32_t bits_cap,
@@ -300,7 +300,7 @@ static int drain_chunk(SdbHandle *h, uint32_t k, ArenaDrain &d, SdbHit *hits, ui
         sink->used = used;
         if (used <= sink->pool_cap) {
             if (c.hits > d.hits)
-                CK(cudaMemcpyAsync(sink->str_off + d.hits, h->d_stroff + d.hits, sizeof(uint32_t) * (size_t)(c.hits - d.hits), cudaMemcpyDeviceToHost, h->d2h_stream));
+                CK(cudaMemcpyAsync(sink->phits + d.hits, h->d_phits + d.hits, sizeof(SdbPayloadHit) * (size_t)(c.hits - d.hits), cudaMemcpyDeviceToHost, h->d2h_stream));
             if (used > d.chars)
                 CK(cudaMemcpyAsync(sink->pool + d.chars, h->d_chars + d.chars, (size_t)(used - d.chars), cudaMemcpyDeviceToHost, h->d2h_stream));
             d.chars = used;
@@ -316,7 +316,7 @@ static int enqueue_format(SdbHandle *h, int kind, uint32_t hits_cap, uint32_t bi
     const SdbPulseProto *rows = kind == SDB_KIND_MS ? h->tab.ms : h->tab.mu;
     const uint16_t *map = h->d_rowmap + (kind == SDB_KIND_MS ? 0 : h->tab.nproto);
     int rc = sdb::launch_format(kind, h->d_hits, h->d_bits, rows, map, h->tab.hex, h->tab.nproto, h->d_fmt, h->d_ctr, hits_cap, bits_cap,
-                                h->d_chars, sink->pool_cap, h->d_stroff, h->d_fmt + 2, h->sm_count * 8, st);
+                                h->d_chars, sink->pool_cap, h->d_phits, h->d_fmt + 2, h->sm_count * 8, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "format kernel launch", static_cast<cudaError_t>(rc));
     CK(cudaMemcpyAsync(&h->h_used[k], h->d_fmt + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return SDB_OK;
@@ -344,7 +344,7 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
     cudaStream_t st = h->stream;
     if (sink) {                                               /* payload mode (MS / MU): device pool + one offset per hit */
         if ((rc = grow(h, h->d_chars, h->cap_chars, (size_t)sink->pool_cap + 16))) return rc;
-        if ((rc = grow(h, h->d_stroff, h->cap_stroff, sizeof(uint32_t) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
+        if ((rc = grow(h, h->d_phits, h->cap_phits, sizeof(SdbPayloadHit) * (size_t)(hits_cap ? hits_cap : 1)))) return rc;
         if ((rc = pipeline_prepare(h, 1))) return rc;
         CK(cudaMemsetAsync(h->d_fmt, 0, 4 * sizeof(uint32_t), st));
     }
@@ -412,7 +412,7 @@ static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
     if (sink) {
         sink->used = h->h_used[0];
         if (sink->used <= sink->pool_cap) {
-            if (counters->hits) CK(cudaMemcpyAsync(sink->str_off, h->d_stroff, sizeof(uint32_t) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
+            if (counters->hits) CK(cudaMemcpyAsync(sink->phits, h->d_phits, sizeof(SdbPayloadHit) * (size_t)counters->hits, cudaMemcpyDeviceToHost, st));
             if (sink->used) CK(cudaMemcpyAsync(sink->pool, h->d_chars, sink->used, cudaMemcpyDeviceToHost, st));
         }
     }
@@ -623,15 +623,15 @@ extern "C" int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
                                        const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                                        SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                                        uint32_t *bits, uint32_t bits_cap, SdbCounters *counters,
-                                       char *pool, size_t pool_cap, uint32_t *str_off, size_t *pool_used)
+                                       char *pool, size_t pool_cap, SdbPayloadHit *phits, size_t *pool_used)
 {
     if (!h) return SDB_E_ARG;
-    if (!str_off || !pool_used || !hits || (pool_cap && !pool)) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
+    if (!phits || !pool_used || (pool_cap && !pool)) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: null pointer");
     *pool_used = 0;
     if (kind < SDB_KIND_MS || kind > SDB_KIND_MN) return set_err(h, SDB_E_ARG, "sdb_demod_host_payloads: bad kind");
     /* a format kernel per pipeline stage (sdb_format.cu): the strings travel back instead of the bit arena (bits may be NULL) */
     PayloadSink sink;
-    sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.str_off = str_off;
+    sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.phits = phits;
     const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink);
     *pool_used = sink.used;
     if (rc != SDB_OK) return rc;

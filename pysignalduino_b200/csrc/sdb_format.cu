@@ -8,8 +8,8 @@
  *
  * One thread per hit; a CTA of 256 hits lays its strings out contiguously (block-wide exclusive scan of the lengths + one
  * atomicAdd on the pool counter per CTA), stages them in shared memory when they fit and writes them out coalesced.
- * Every string is followed by a NUL; str_off[i] is where hit i's string starts.  The pool order follows the CTA order of
- * the atomics, not the hit order — callers index through str_off.
+ * Every string is followed by a NUL; phits[i] (12 bytes: string offset, protocol, bit length, flags) is what travels back
+ * per hit.  The pool order follows the CTA order of the atomics, not the hit order — callers index through phits[i].str_off.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,7 +36,7 @@ struct FArgs {
     uint32_t hits_cap, bits_cap;
     char *pool;
     uint32_t pool_cap;
-    uint32_t *str_off;
+    SdbPayloadHit *phits;
     uint32_t *used;                           /* pool bytes handed out so far (may exceed pool_cap: overflow) */
 };
 
@@ -78,7 +78,11 @@ __global__ void __launch_bounds__(FMT_THREADS) format_kernel(FArgs A)
         __syncthreads();
         const uint32_t base = base_sh;
         const bool fits = base + total <= A.pool_cap && base + total >= base;
-        if (i < h1) A.str_off[i] = base + excl;
+        if (i < h1) {
+            SdbPayloadHit ph;
+            ph.str_off = base + excl; ph.proto = ht.proto; ph.nbits = ht.nbits; ph.aux = ht.aux; ph.flags = ht.flags; ph.rsv = 0;
+            A.phits[i] = ph;
+        }
         if (fits && total) {
             const bool staged = total <= FMT_STAGE;
             if (len) {
@@ -117,7 +121,7 @@ __global__ void format_advance_kernel(uint32_t *range) { range[0] = range[1]; }
 int launch_format(int kind, const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulseProto *rows, const uint16_t *row_of_proto,
                   const SdbHexProto *hx, uint32_t nproto,
                   uint32_t *d_range, const SdbCounters *d_ctr, uint32_t hits_cap, uint32_t bits_cap, char *d_pool, uint32_t pool_cap,
-                  uint32_t *d_str_off, uint32_t *d_used, int grid, cudaStream_t stream)
+                  SdbPayloadHit *d_phits, uint32_t *d_used, int grid, cudaStream_t stream)
 {
     /* range[1] = the hit counter now (device-side copy, stream-ordered after the decode kernels of this stage) */
     cudaError_t e = cudaMemcpyAsync(d_range + 1, &d_ctr->hits, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
@@ -125,7 +129,7 @@ int launch_format(int kind, const SdbHit *d_hits, const uint32_t *d_bits, const 
     FArgs A;
     A.kind = kind; A.hx = hx;
     A.hits = d_hits; A.bits = d_bits; A.rows = rows; A.row_of_proto = row_of_proto; A.nproto = nproto; A.range = d_range;
-    A.pool = d_pool; A.pool_cap = pool_cap; A.str_off = d_str_off; A.used = d_used;
+    A.pool = d_pool; A.pool_cap = pool_cap; A.phits = d_phits; A.used = d_used;
     A.ctr = d_ctr; A.hits_cap = hits_cap; A.bits_cap = bits_cap;
     format_kernel<<<grid, FMT_THREADS, 0, stream>>>(A);
     format_advance_kernel<<<1, 1, 0, stream>>>(d_range);

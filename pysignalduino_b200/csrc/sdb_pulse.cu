@@ -1902,13 +1902,14 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_emit_kernel(KArgs A)
     }
 }
 
-/* dynamic shared memory of the resolve kernels (the CTA-shared table copies); opting in is needed beyond 48 KB in total */
+/* dynamic shared memory of the resolve kernels (the CTA-shared table copies); opting in is needed beyond 48 KB in total.
+ * The attribute is per FUNCTION (not per handle): it is set to the largest size any table can need, so that handles with
+ * different tables can coexist (a handle created later with a smaller table must not lower the cap of an earlier one). */
 template <bool MS>
 static size_t resolve_dyn_smem(const SdbDevTable &tab)
 {
-    const size_t bytes = hot_bytes(tab.n_vals, MS ? tab.n_ms : tab.n_mu);
-    cudaFuncSetAttribute(resolve_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return bytes;
+    cudaFuncSetAttribute(resolve_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    return hot_bytes(tab.n_vals, MS ? tab.n_ms : tab.n_mu);
 }
 
 int pulse_blocks_per_sm(int kind, const SdbDevTable &tab)
@@ -2036,8 +2037,8 @@ int long_blocks_per_sm(const SdbDevTable &tab)
 {
     int a = 0, b = 0, c = 0, d = 0;
     const size_t dms = hot_bytes(tab.n_vals, tab.n_ms), dmu = hot_bytes(tab.n_vals, tab.n_mu);
-    cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dms);
-    cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dmu);
+    cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, KTHREADS, dms);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, KTHREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false>, KTHREADS, dmu);

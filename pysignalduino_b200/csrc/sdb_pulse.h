@@ -42,11 +42,11 @@ size_t lines_pool_bytes(size_t text_len, uint32_t n);
 int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, const uint32_t *d_len, uint32_t n, uint32_t base,
                     SdbPulseMsg *d_msgs, uint8_t *d_pool, SdbLineInfo *d_info, uint32_t *d_long /* 2 + n words */, int sm_count, cudaStream_t stream);
 
-/* sdb_format.cu: payload strings of the MS / MU hits [range[0], ctr->hits) into a device pool (NUL-terminated, str_off per hit) */
+/* sdb_format.cu: payload strings of the MS / MU hits [range[0], ctr->hits) into a device pool (NUL-terminated, one SdbPayloadHit per hit) */
 int launch_format(int kind, const SdbHit *d_hits, const uint32_t *d_bits, const SdbPulseProto *rows, const uint16_t *row_of_proto,
                   const SdbHexProto *hx, uint32_t nproto,
                   uint32_t *d_range, const SdbCounters *d_ctr, uint32_t hits_cap, uint32_t bits_cap, char *d_pool, uint32_t pool_cap,
-                  uint32_t *d_str_off, uint32_t *d_used, int grid, cudaStream_t stream);
+                  SdbPayloadHit *d_phits, uint32_t *d_used, int grid, cudaStream_t stream);
 
 int launch_unit_mc(const SdbDevTable &tab, uint32_t proto, int method_override, const uint8_t *d_bits, int n, int mcbitnum,
                    uint8_t *d_out, int out_cap, int32_t *d_seg, int32_t *d_res, cudaStream_t stream);

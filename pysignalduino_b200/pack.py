@@ -72,6 +72,9 @@ HIT_DTYPE = np.dtype(
         ("rsv", "u1"),
     ]
 )
+# SdbPayloadHit: what sdb_demod_host_payloads returns per hit (the string lives in the pool at `off`)
+PAYHIT_DTYPE = np.dtype([("off", "<u4"), ("proto", "<u2"), ("nbits", "<u2"), ("aux", "<u2"), ("flags", "u1"), ("rsv", "u1")])
+assert PAYHIT_DTYPE.itemsize == 12
 COUNTERS_DTYPE = np.dtype([("hits", "<u4"), ("words", "<u4"), ("raised", "<u4"), ("domain", "<u4")])
 assert MSGOUT_DTYPE.itemsize == 8 and HIT_DTYPE.itemsize == 16 and COUNTERS_DTYPE.itemsize == 16
 

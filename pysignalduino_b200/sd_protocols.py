@@ -34,8 +34,8 @@ class BatchResults(Sequence):
     the reference's ``demodulate()`` returns for it, materialised on access from the raw result arrays (27 M hits per 10 M
     messages are not turned into Python objects unless somebody looks at them).  Compares equal to the equivalent list."""
 
-    def __init__(self, sdp: "SDProtocols", batch, res: Result, pool: bytes, off: np.ndarray):
-        self._sdp, self._batch, self._res, self._pool, self._off = sdp, batch, res, pool, off
+    def __init__(self, sdp: "SDProtocols", batch, res: Result, pool: bytes):
+        self._sdp, self._batch, self._res, self._pool = sdp, batch, res, pool       # res.hits: pack.PAYHIT_DTYPE records
         self._ids = sdp.engine().table.ids
         self._clk: Dict[int, float] = {}
 
@@ -43,7 +43,7 @@ class BatchResults(Sequence):
         return self._batch.n
 
     def _payload(self, i: int) -> str:
-        a = int(self._off[i])
+        a = int(self._res.hits["off"][i])
         return self._pool[a : self._pool.index(0, a)].decode("latin-1")
 
     def __getitem__(self, m):
@@ -216,9 +216,9 @@ class SDProtocols:
             self._logging(f"Unknown message type {msg_type}", 3)
             return ["ok"] * len(msgs), [[] for _ in msgs]
         batch = self.pack(msgs, msg_type)
-        res, pool, off = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
+        res, pool = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
         statuses = _STATUS_ARRAY[res.out["status"]].tolist()
-        results = BatchResults(self, batch, res, pool.tobytes(), off)
+        results = BatchResults(self, batch, res, pool.tobytes())
         return statuses, (results if lazy else list(results))
 
     def format_results(self, batch, res: Result, msgs: Optional[Sequence[Dict[str, Any]]] = None):
@@ -284,11 +284,11 @@ class SDProtocols:
 
     def _one(self, msg_data: Dict[str, Any], msg_type: str) -> list:
         batch = self.pack([msg_data], msg_type)
-        res, pool, off = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
+        res, pool = self.engine().demod_payloads(batch, mc_repaired=self.mc_repaired)
         st = int(res.out["status"][0])
         if st != ST_OK:
             self._raise_status(st, batch, f"demodulate_{msg_type.lower()}")
-        return BatchResults(self, batch, res, pool.tobytes(), off)[0]
+        return BatchResults(self, batch, res, pool.tobytes())[0]
 
     def demodulate_ms(self, msg_data: Dict[str, Any], msg_type: str = "MS") -> List[Dict[str, Any]]:
         """message_synced.py:10-243 (invalid input -> [] with a level-3 log line, :21-47)"""

@@ -83,9 +83,9 @@ def compare_raw(sdp, batch, res, ora_status, ora_hits, ora_pool, check_bits=True
     return ""
 
 
-def compare_payloads(batch, res, pool, off, ora_status, ora_hits, ora_pool) -> str:
-    """The same comparison for a result of ``sdb_demod_host_payloads`` (strings written by the DEVICE format kernel:
-    NUL-terminated, one offset per hit, pool in CTA order): status, protocol, bit length (MS / MU) and payload bytes of every
+def compare_payloads(batch, res, pool, ora_status, ora_hits, ora_pool) -> str:
+    """The same comparison for a result of ``sdb_demod_host_payloads`` (12-byte SdbPayloadHit records + strings written by the
+    DEVICE format kernel: NUL-terminated, pool in CTA order): status, protocol, bit length (MS / MU) and payload bytes of every
     hit against the oracle's arrays; returns '' or a description."""
     import numpy as np
 
@@ -99,9 +99,9 @@ def compare_payloads(batch, res, pool, off, ora_status, ora_hits, ora_pool) -> s
     within = np.arange(total) - np.repeat(np.cumsum(nh) - nh, nh)
     order = np.repeat(out["hit_off"].astype(np.int64), nh) + within
     g = hits[order]
-    o = off[order].astype(np.int64)
     keep = ~(((g["flags"] & 2) != 0) & (g["aux"] != 0))          # continuation rows of a TFA list carry no string
-    g, o = g[keep], o[keep]
+    g = g[keep]
+    o = g["off"].astype(np.int64)
     if len(g) != len(ora_hits):
         return f"{len(g)} device hits vs {len(ora_hits)} oracle hits"
     if not np.array_equal(g["proto"].astype(np.int64), ora_hits["proto"].astype(np.int64)):

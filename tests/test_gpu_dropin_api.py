@@ -152,14 +152,18 @@ def test_demod_host_payloads_equals_decode_then_format(sdp):
         pool_ref = np.frombuffer(pool_ref, dtype=np.uint8)
         nh = len(ref.hits)
         out = np.zeros(n, dtype=pack.MSGOUT_DTYPE)
-        hits = np.zeros(nh + 8, dtype=pack.HIT_DTYPE)
+        phits = np.zeros(nh + 8, dtype=pack.PAYHIT_DTYPE)
         ctr = np.zeros(1, dtype=pack.COUNTERS_DTYPE)
         pool = np.zeros(len(pool_ref) + nh + 16, dtype=np.uint8)
-        off = np.zeros(len(hits), dtype=np.uint32)
-        bits = None if kind != pack.KIND_MN else np.zeros(len(ref.bits) + 8, dtype=np.uint32)    # the bit arena is optional
-        rc, used = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
-                                                pool, off, mc_repaired=True)
+        # the 16-byte hit records and the bit arena are optional extras
+        hits = np.zeros(nh + 8, dtype=pack.HIT_DTYPE) if kind == pack.KIND_MN else None
+        bits = np.zeros(len(ref.bits) + 8, dtype=np.uint32) if kind == pack.KIND_MN else None
+        args = (kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, phits, ctr)
+        kw = dict(mc_repaired=True, bits_cap=len(ref.bits) + 8, hits=hits, bits=bits)
+        rc, used = eng.demod_host_payloads_into(*args, pool, **kw)
         assert rc == 0 and int(ctr["hits"][0]) == nh and used == len(pool_ref) + nh          # one NUL per hit
+        if hits is not None:
+            assert np.array_equal(hits["proto"][:nh], phits["proto"][:nh]) and np.array_equal(hits["nbits"][:nh], phits["nbits"][:nh])
 
         # hit order differs between runs (atomics), so compare per message: the strings of message m in hit order
         def strings(o, k, get):
@@ -170,7 +174,7 @@ def test_demod_host_payloads_equals_decode_then_format(sdp):
             return res
 
         def nul_string(i):
-            a = int(off[i])
+            a = int(phits["off"][i])
             e = a
             while pool[e]:
                 e += 1
@@ -180,8 +184,25 @@ def test_demod_host_payloads_equals_decode_then_format(sdp):
         exp = strings(ref.out, kind, lambda i: bytes(pool_ref[int(off_ref[i]) : int(off_ref[i + 1])]))
         assert got == exp and len(got) > 100
         small = np.zeros(8, dtype=np.uint8)
-        rc, used2 = eng.demod_host_payloads_into(kind, np.ascontiguousarray(b.msgs), np.ascontiguousarray(b.digits), out, hits, bits, ctr,
-                                                 small, off, mc_repaired=True)
+        rc, used2 = eng.demod_host_payloads_into(*args, small, **kw)
         assert rc == -3 and used2 == used                       # SDB_E_OVERFLOW reports the size needed
-        res2, pool2, off2 = eng.demod_payloads(b, mc_repaired=True)
-        assert len(res2.hits) == nh and len(pool2) == used
+        res2, pool2 = eng.demod_payloads(b, mc_repaired=True)
+        assert len(res2.hits) == nh and len(pool2) == used and res2.hits.dtype == pack.PAYHIT_DTYPE
+
+
+def test_handles_with_different_tables_coexist(sdp):
+    """The resolve kernels keep table copies in dynamic shared memory whose size depends on the table; the opt-in attribute is per
+    kernel function, not per handle: a handle created later with a much smaller table must not break an earlier one."""
+    from corpus.corpus import Corpus
+    from pysignalduino_b200 import pack
+
+    b = Corpus(sdp.get_protocol_list()).pulse(pack.KIND_MU, 2000)
+    before = sdp.demodulate_packed(b)
+    small = SDProtocols(device=0)
+    keep = ["9", "44", "46"]
+    for pid in [p for p in list(small._protocols) if p not in keep]:
+        del small._protocols[pid]
+    msg = parse_line("MU;P0=-28704;P1=450;P2=-1064;P3=1422;CP=1;R=13;D=012121212121212123212121212121212121212123232323232123212321232123232323232323232323232323232323232323232323232323232121212123210121212121212121232121212121212121212121232323232321232123212321232323232323232323232323232323232323232323232323232321212121232101212121212121212321212121212121212121212323232323212321232123212323232323232323232323232323232323232323232323232323212121212321;")
+    assert [r["protocol_id"] for r in small.demodulate(msg, "MU")] == ["9", "9", "9"]
+    after = sdp.demodulate_packed(b)                      # the big table's handle still launches
+    assert int(after.counters["hits"]) == int(before.counters["hits"]) > 0

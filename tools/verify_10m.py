@@ -50,9 +50,9 @@ for (name, kind, _), n in zip(MIX, counts):
             bad.append(f"[{lo}:{hi}] {msg}")
         # the same block through sdb_demod_host_payloads: strings written by the device format kernel
         t0 = time.perf_counter()
-        res2, dpool, doff = sdp.engine().demod_payloads(b, mc_repaired=True)
+        res2, dpool = sdp.engine().demod_payloads(b, mc_repaired=True)
         t_gpu_payload += time.perf_counter() - t0
-        msg = compare_payloads(b, res2, dpool, doff, status, ohits, pool)
+        msg = compare_payloads(b, res2, dpool, status, ohits, pool)
         if msg:
             bad.append(f"[{lo}:{hi}] device-formatted: {msg}")
         hits += len(res.hits)
