@@ -239,6 +239,18 @@ extern "C" int sdb_demod_hex_device(SdbHandle *h, int kind, int mc_repaired,
     return SDB_OK;
 }
 
+/* The pipelined host calls queue asynchronous copies into the caller's buffers on three streams: before an error code goes
+ * back to the caller nothing of that may still be in flight. */
+static int settle(SdbHandle *h, int rc)
+{
+    if (rc != SDB_OK && h) {
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+    }
+    return rc;
+}
+
 template <typename T>
 static int grow(SdbHandle *h, T *&p, size_t &cap, size_t need_bytes)
 {
@@ -426,14 +438,29 @@ extern "C" int sdb_demod_host(SdbHandle *h, int kind, int mc_repaired,
                               uint32_t *bits, uint32_t bits_cap, SdbCounters *counters)
 {
     if (n && (!hits || !bits)) return h ? set_err(h, SDB_E_ARG, "sdb_demod_host: null pointer") : SDB_E_ARG;
-    return demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr);
+    return settle(h, demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, nullptr));
 }
+
+static int demod_lines_impl(SdbHandle *h, int kind,
+                            const uint8_t *text, size_t text_len,
+                            const uint32_t *line_off, const uint32_t *line_len, uint32_t n,
+                            SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                            uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info);
 
 extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
                                     const uint8_t *text, size_t text_len,
                                     const uint32_t *line_off, const uint32_t *line_len, uint32_t n,
                                     SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                                     uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info)
+{
+    return settle(h, demod_lines_impl(h, kind, text, text_len, line_off, line_len, n, out, hits, hits_cap, bits, bits_cap, counters, info));
+}
+
+static int demod_lines_impl(SdbHandle *h, int kind,
+                            const uint8_t *text, size_t text_len,
+                            const uint32_t *line_off, const uint32_t *line_len, uint32_t n,
+                            SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                            uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info)
 {
     if (!h) return SDB_E_ARG;
     if (kind != SDB_KIND_MS && kind != SDB_KIND_MU) return set_err(h, SDB_E_ARG, "sdb_demod_lines_host: kind must be MS or MU");
@@ -632,7 +659,7 @@ extern "C" int sdb_demod_host_payloads(SdbHandle *h, int kind, int mc_repaired,
     /* a format kernel per pipeline stage (sdb_format.cu): the strings travel back instead of the bit arena (bits may be NULL) */
     PayloadSink sink;
     sink.pool = pool; sink.pool_cap = pool_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)pool_cap; sink.phits = phits;
-    const int rc = demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink);
+    const int rc = settle(h, demod_host_impl(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, &sink));
     *pool_used = sink.used;
     if (rc != SDB_OK) return rc;
     if (sink.used > sink.pool_cap) return set_err(h, SDB_E_OVERFLOW, "payload pool too small");
