@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 1
+#define SDB_ABI_VERSION 2      /* 2: SdbMsgOut.reason, SdbCounters.domain, SDB_ST_DOMAIN, payload / reserve / pattern entry points */
 
 /* ---- limits of the packed domain ------------------------------------------------ */
 #define SDB_MAX_SLOTS   8      /* P0..P7: pulse-pattern slots per message (firmware emits <= 8) */

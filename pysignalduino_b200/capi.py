@@ -105,7 +105,7 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_int)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
-    if L.sdb_abi_version() != 1:
+    if L.sdb_abi_version() != 2:
         raise SdbError("libsdb200.so ABI version mismatch")
     _lib = L
     return L
