@@ -20,7 +20,8 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 2      /* 2: SdbMsgOut.reason, SdbCounters.domain, SDB_ST_DOMAIN, payload / reserve / pattern entry points */
+#define SDB_ABI_VERSION 3      /* 2: SdbMsgOut.reason, SdbCounters.domain, SDB_ST_DOMAIN, payload / reserve / pattern entry points;
+                                  3: SDB_ST_SCRATCH + sdb_scratch_short (compact scratch arenas) */
 
 /* ---- limits of the packed domain ------------------------------------------------ */
 #define SDB_MAX_SLOTS   8      /* P0..P7: pulse-pattern slots per message (firmware emits <= 8) */
@@ -35,6 +36,8 @@ extern "C" {
 #define SDB_E_CUDA       -2    /* CUDA runtime error, see sdb_last_error()     */
 #define SDB_E_OVERFLOW   -3    /* hit / bit arena too small: counters say how much is needed */
 #define SDB_E_NOGPU      -4    /* no CUDA device: there is NO CPU fallback     */
+#define SDB_E_SCRATCH    -5    /* messages still flagged SDB_ST_SCRATCH after the scratch was grown 6 times (a user table
+                                  with more than 151 protocols in one class and messages longer than 1024 digits) */
 
 /* ---- message kinds (SDProtocols.demodulate(msg, msg_type), sd_protocols/sd_protocols.py:60-74) */
 #define SDB_KIND_MS 0          /* demodulate_ms, sd_protocols/message_synced.py:10-243   */
@@ -49,6 +52,10 @@ extern "C" {
 #define SDB_ST_VALUEERROR  3   /* message_synced.py:174 range(..., 0) with signal_width == 0        */
 #define SDB_ST_DOMAIN      4   /* NOT a reference outcome: the message is outside the packed domain (SDB_MSG_DOMAIN, or a
                                   malformed record); it was not decoded — no hits, reported per message, never silently wrong */
+#define SDB_ST_SCRATCH     5   /* NOT a reference outcome, device-pointer calls only: the message was not decoded because the
+                                  handle's scratch arenas (sized by AVERAGE survivor counts) were too small for this batch;
+                                  sdb_scratch_short() grows them, then submit the flagged messages again.  The host-buffer
+                                  calls do that themselves and never return this status. */
 
 /*
  * One MS / MU message after host-side packing of the parser dict
@@ -187,6 +194,25 @@ int sdb_demod_pulse_device(SdbHandle *h, int kind,
  * calls in flight on different streams would share them — use one handle per stream.
  */
 int sdb_reserve(SdbHandle *h, uint32_t n_messages);
+
+/*
+ * The scratch holds COMPACT survivor / match records: every warp claims blocks of 256 survivor records (16 B each) / 1024 match
+ * records (4 B each) from per-launch-group arenas and fills them message after message.  The arenas are sized for 18 survivor
+ * and 12 match records per message on average (the benchmark corpus needs 14.6 and 6.7) plus one block per resident warp, and
+ * worst-case slots for 8192 messages per launch group take what did not fit — 0.41 GB per 1 048 576-message group instead of
+ * the 2.2 GB that room for every protocol of every message took.  A launch group that needs more (a batch averaging more than
+ * 18 surviving protocols per message AND more than 8192 messages that did not fit) leaves the excess messages undecoded with
+ * status SDB_ST_SCRATCH.  The host-buffer calls notice, grow the scratch from the recorded need and repeat the call.  After
+ * device-pointer calls, sdb_scratch_short() synchronises the device, stores in *n_short how many messages were flagged since
+ * the last check and grows the budgets (the next call reallocates), so that submitting the flagged messages again succeeds.
+ */
+int sdb_scratch_short(SdbHandle *h, uint32_t *n_short);
+/* Set the budgets (0 = keep the current one): survivor records / MU match records per message on average, messages of the
+ * worst-case region; slack_warps = 0 (automatic) unless a test wants the arenas smaller than one block per resident warp on top
+ * of the budgets.  Synchronises and releases the current block; the next call allocates with the new budgets. */
+int sdb_scratch_budget(SdbHandle *h, uint32_t surv_avg, uint32_t match_avg, uint32_t ovf_max, uint32_t slack_warps);
+/* Bytes of the scratch block as allocated (0 = none yet); cfg = {messages per launch group, surv_avg, match_avg, ovf_max}. */
+size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[4]);
 
 /* Same for MC / MN (sd_protocols.py:76-155, manchester.py, helpers.py:223-716).
  * mc_repaired: 0 = as shipped (TypeError, SURVEY §8c "strict"), 1 = the two documented one-line repairs. */

@@ -21,11 +21,12 @@ LIB_PATH = Path(__file__).resolve().parent / ("libsdb200_chk.so" if CHECKED else
 if os.environ.get("SDB200_LIB"):                       # an experiment variant built with build_ext.py -D... --out=...
     LIB_PATH = Path(os.environ["SDB200_LIB"]).resolve()
 
-SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU = 0, -1, -2, -3, -4
-ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR, ST_DOMAIN = 0, 1, 2, 3, 4
+SDB_OK, SDB_E_ARG, SDB_E_CUDA, SDB_E_OVERFLOW, SDB_E_NOGPU, SDB_E_SCRATCH = 0, -1, -2, -3, -4, -5
+ST_OK, ST_INDEXERROR, ST_TYPEERROR, ST_VALUEERROR, ST_DOMAIN, ST_SCRATCH = 0, 1, 2, 3, 4, 5
 STATUS_EXC = {ST_INDEXERROR: IndexError, ST_TYPEERROR: TypeError, ST_VALUEERROR: ValueError, ST_DOMAIN: pack.DomainError}
 STATUS_NAMES = {ST_OK: "ok", ST_INDEXERROR: "IndexError", ST_TYPEERROR: "TypeError", ST_VALUEERROR: "ValueError",
-                ST_DOMAIN: "DomainError"}    # DomainError: outside the packed domain, NOT decoded (never a reference outcome)
+                ST_DOMAIN: "DomainError",    # DomainError: outside the packed domain, NOT decoded (never a reference outcome)
+                ST_SCRATCH: "ScratchShort"}  # device-pointer calls only: not decoded, scratch too small (Engine.scratch_short())
 
 HIT_HAS_F, HIT_LIST, HIT_FIELDS, HIT_MM_HOST = 0x01, 0x02, 0x04, 0x08
 
@@ -33,7 +34,7 @@ EXPORTS = [
     "sdb_abi_version", "sdb_last_error", "sdb_create", "sdb_destroy",
     "sdb_demod_pulse_device", "sdb_demod_hex_device", "sdb_demod_host",
     "sdb_format_hits", "sdb_unit_postdemod", "sdb_unit_mc", "sdb_debug_violations", "sdb_demod_lines_host", "sdb_format_json", "sdb_frame_lines", "sdb_frame_lines_inplace",
-    "sdb_unit_pattern_exists", "sdb_demod_host_payloads", "sdb_reserve",
+    "sdb_unit_pattern_exists", "sdb_demod_host_payloads", "sdb_reserve", "sdb_scratch_short", "sdb_scratch_budget", "sdb_scratch_info",
 ]
 
 
@@ -77,6 +78,12 @@ def load_library() -> C.CDLL:
     L.sdb_demod_host_payloads.argtypes = list(L.sdb_demod_host.argtypes) + [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
     L.sdb_reserve.restype = C.c_int
     L.sdb_reserve.argtypes = [C.c_void_p, C.c_uint32]
+    L.sdb_scratch_short.restype = C.c_int
+    L.sdb_scratch_short.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    L.sdb_scratch_budget.restype = C.c_int
+    L.sdb_scratch_budget.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.sdb_scratch_info.restype = C.c_size_t
+    L.sdb_scratch_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32 * 4)]
     L.sdb_format_hits.restype = C.c_int
     L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.POINTER(C.c_size_t)]
@@ -105,7 +112,7 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_int)]
     L.sdb_debug_violations.restype = C.c_uint
     L.sdb_debug_violations.argtypes = [C.c_void_p, C.c_int]
-    if L.sdb_abi_version() != 2:
+    if L.sdb_abi_version() != 3:
         raise SdbError("libsdb200.so ABI version mismatch")
     _lib = L
     return L
@@ -270,6 +277,28 @@ class Engine:
         rc = self.lib.sdb_reserve(self.h, n_messages)
         if rc != SDB_OK:
             raise self._err(rc, "sdb_reserve")
+
+    def scratch_short(self) -> int:
+        """After device-pointer calls: synchronise, return how many messages were flagged ST_SCRATCH since the last check
+        (their launch group needed more scratch than the compact arenas hold) and grow the scratch budgets so that
+        submitting those messages again succeeds (sdb_scratch_short).  The host-buffer calls do this themselves."""
+        n = C.c_uint32(0)
+        rc = self.lib.sdb_scratch_short(self.h, C.byref(n))
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_scratch_short")
+        return int(n.value)
+
+    def scratch_budget(self, surv_avg: int = 0, match_avg: int = 0, ovf_max: int = 0, slack_warps: int = 0) -> None:
+        """Budgets the scratch is sized by (0 = keep): survivor / MU match records per message on average, messages of the
+        worst-case overflow region; ``slack_warps`` caps the arena blocks added on top (tests only) (sdb_scratch_budget)."""
+        rc = self.lib.sdb_scratch_budget(self.h, surv_avg, match_avg, ovf_max, slack_warps)
+        if rc != SDB_OK:
+            raise self._err(rc, "sdb_scratch_budget")
+
+    def scratch_info(self) -> dict:
+        cfg = (C.c_uint32 * 4)()
+        nbytes = self.lib.sdb_scratch_info(self.h, C.byref(cfg))
+        return {"bytes": int(nbytes), "chunk": int(cfg[0]), "surv_avg": int(cfg[1]), "match_avg": int(cfg[2]), "ovf_max": int(cfg[3])}
 
     def _err(self, rc: int, what: str) -> SdbError:
         return SdbError(f"{what} failed ({rc}): {(self.lib.sdb_last_error(self.h) or b'').decode()}")

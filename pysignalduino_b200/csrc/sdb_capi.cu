@@ -23,7 +23,7 @@
 struct SdbHandle {
     int device = 0;
     int sm_count = 0;
-    int grid_ms = 0, grid_mu = 0, grid_hex = 0, grid_long = 0;
+    int grid_ms[3] = {0, 0, 0}, grid_mu[3] = {0, 0, 0}, grid_hex = 0, grid_long = 0;   /* MS / MU: resolve, match or scan, emit */
     std::vector<uint8_t> blob;          /* host copy (formatting needs preamble / flags) */
     uint8_t *d_blob = nullptr;
     SdbDevTable tab{};
@@ -38,8 +38,11 @@ struct SdbHandle {
     uint8_t *d_unit = nullptr;          /* unit-op scratch */
     uint8_t *d_text = nullptr;  size_t cap_text = 0;     /* sdb_demod_lines_host: line text */
     uint8_t *d_lines = nullptr; size_t cap_lines = 0;    /* line offsets, lengths, SdbLineInfo */
-    void *d_mu_scratch = nullptr;       /* MU survivor slots (resolve kernel -> scan kernel), allocated on first MU call */
-    uint32_t mu_chunk = 0;
+    void *d_scratch = nullptr;          /* what the pulse kernels of a launch group hand each other (sdb_pulse.h), allocated on the first MS / MU call */
+    SdbScratchCfg scfg{0, 0, 0, 0, 0};     /* ... as allocated */
+    uint32_t want_surv = SDB_SURV_AVG_DEFAULT, want_match = SDB_MATCH_AVG_DEFAULT, want_ovf = SDB_OVF_MAX_DEFAULT;   /* budgets (grown from the recorded need) */
+    uint32_t slack_warps = 0;           /* 0 = one arena block per resident warp on top of the budgets; else that many (tests of the overflow paths) */
+    uint32_t *h_stats = nullptr;        /* pinned copy of the scratch statistics */
     cudaStream_t stream = nullptr;      /* compute + final copies of the host-buffer path */
     cudaStream_t copy_stream = nullptr; /* pipelined H2D */
     cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
@@ -136,8 +139,10 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     h->tab.hex = reinterpret_cast<const SdbHexProto *>(b + hd->off_hex);
     h->tab.n_ms = hd->n_ms; h->tab.n_mu = hd->n_mu; h->tab.n_clk = hd->n_clk; h->tab.nproto = hd->nproto;
     /* persistent grids: every SM filled with as many CTAs as fit */
-    h->grid_ms = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MS, h->tab);
-    h->grid_mu = h->sm_count * sdb::pulse_blocks_per_sm(SDB_KIND_MU, h->tab);
+    sdb::pulse_blocks_per_sm(SDB_KIND_MS, h->tab, h->grid_ms);
+    sdb::pulse_blocks_per_sm(SDB_KIND_MU, h->tab, h->grid_mu);
+    for (int i = 0; i < 3; i++) { h->grid_ms[i] *= h->sm_count; h->grid_mu[i] *= h->sm_count; }
+    CKC(cudaMallocHost(reinterpret_cast<void **>(&h->h_stats), SDB_STAT_WORDS * sizeof(uint32_t)));
     h->grid_hex = h->sm_count * 8;
     h->grid_long = h->sm_count * sdb_long::long_blocks_per_sm(h->tab);
 #undef CKC
@@ -149,10 +154,11 @@ extern "C" void sdb_destroy(SdbHandle *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_mu_scratch); cudaFree(h->d_text); cudaFree(h->d_lines);
+    cudaFree(h->d_blob); cudaFree(h->d_ctr); cudaFree(h->d_unit); cudaFree(h->d_scratch); cudaFree(h->d_text); cudaFree(h->d_lines);
     cudaFree(h->d_msgs); cudaFree(h->d_digits); cudaFree(h->d_out); cudaFree(h->d_hits); cudaFree(h->d_bits);
     cudaFree(h->d_rowmap); cudaFree(h->d_chars); cudaFree(h->d_phits); cudaFree(h->d_fmt);
     if (h->h_used) cudaFreeHost(h->h_used);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_d2h) cudaEventDestroy(e);
@@ -178,21 +184,130 @@ extern "C" int sdb_demod_pulse_device(SdbHandle *h, int kind,
     return enqueue_pulse(h, kind, d_msgs, d_digits, n, 0, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, st);
 }
 
+/* ---- scratch of the pulse kernels (sdb_pulse.h: compact survivor / match arenas sized by average record counts) ---- */
+static uint32_t pulse_stride(const SdbHandle *h) { return h->tab.n_ms > h->tab.n_mu ? h->tab.n_ms : h->tab.n_mu; }
+
+/* (re)allocate when the launch group or one of the budgets outgrew the block; st is synchronised first (the kernels in
+ * flight use the old block) */
+static int ensure_scratch(SdbHandle *h, uint32_t n, cudaStream_t st)
+{
+    const uint32_t chunk0 = n < SDB_MU_CHUNK ? ((n + 1023u) & ~1023u) : SDB_MU_CHUNK;
+    const uint32_t chunk = chunk0 > h->scfg.chunk ? chunk0 : h->scfg.chunk;
+    const uint32_t stride = pulse_stride(h);
+    SdbScratchCfg c;
+    c.chunk = chunk;
+    c.surv_avg = h->want_surv < stride ? h->want_surv : stride;
+    c.match_avg = h->want_match < 64u ? h->want_match : 64u;
+    c.ovf_max = h->want_ovf < chunk ? h->want_ovf : chunk;
+    {
+        /* warps of the largest persistent grid; a launch group of `chunk` messages never starts more than chunk + 8 */
+        int g = h->grid_ms[0];
+        for (int i = 0; i < 3; i++) { if (h->grid_ms[i] > g) g = h->grid_ms[i]; if (h->grid_mu[i] > g) g = h->grid_mu[i]; }
+        const uint32_t w = (uint32_t)g * (SDB_PULSE_THREADS / 32) + (uint32_t)h->grid_long * (SDB_LONG_THREADS / 32);
+        c.warps = w < chunk + 8 ? w : chunk + 8;
+        if (h->slack_warps && h->slack_warps < c.warps) c.warps = h->slack_warps;
+    }
+    if (h->d_scratch && c.chunk <= h->scfg.chunk && c.surv_avg <= h->scfg.surv_avg && c.match_avg <= h->scfg.match_avg &&
+        c.ovf_max <= h->scfg.ovf_max)
+        return SDB_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaDeviceSynchronize());
+    if (h->d_scratch) CK(cudaFree(h->d_scratch));
+    h->d_scratch = nullptr; h->scfg = SdbScratchCfg{0, 0, 0, 0, 0};
+    const size_t bytes = sdb::pulse_scratch_bytes(stride, c);
+    CK(cudaMalloc(&h->d_scratch, bytes));
+    /* counters and statistics start at zero (the lists and arenas need no initialisation) */
+    CK(cudaMemset(static_cast<uint8_t *>(h->d_scratch) + sdb::pulse_scratch_ctl_offset(stride, c), 0, SDB_CTL_WORDS * sizeof(uint32_t)));
+    CK(cudaMemset(static_cast<uint8_t *>(h->d_scratch) + sdb::pulse_scratch_stats_offset(stride, c), 0, SDB_STAT_WORDS * sizeof(uint32_t)));
+    h->scfg = c;
+    return SDB_OK;
+}
+
+/* Read (and reset) the scratch statistics after the work on `st` has finished; grow the budgets from the recorded need so that
+ * the next call — or the repetition of this one, when messages were flagged SDB_ST_SCRATCH — finds room.  *n_short = messages
+ * that were flagged since the last check. */
+static int check_scratch(SdbHandle *h, cudaStream_t st, uint32_t *n_short)
+{
+    *n_short = 0;
+    if (!h->d_scratch) return SDB_OK;
+    const uint32_t stride = pulse_stride(h);
+    uint8_t *stats = static_cast<uint8_t *>(h->d_scratch) + sdb::pulse_scratch_stats_offset(stride, h->scfg);
+    CK(cudaMemcpyAsync(h->h_stats, stats, SDB_STAT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(stats, 0, SDB_STAT_WORDS * sizeof(uint32_t), st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t chunk = h->scfg.chunk ? h->scfg.chunk : 1;
+    const uint64_t need_surv = h->h_stats[SDB_STAT_SURV], need_match = h->h_stats[SDB_STAT_MATCH], need_ovf = h->h_stats[SDB_STAT_OVF];
+    uint32_t caps[2];
+    sdb::pulse_scratch_caps(stride, h->scfg, caps);
+    if (need_surv > caps[0]) {                                  /* the overflow pass had to help: 25 % above the need from now on */
+        const uint64_t per = need_surv - (uint64_t)h->scfg.warps * SDB_SURV_BLOCK;
+        const uint32_t w = (uint32_t)((per + per / 4 + chunk - 1) / chunk);
+        if (w > h->want_surv) h->want_surv = w;
+    }
+    if (need_match > caps[1]) {
+        const uint64_t per = need_match - (uint64_t)h->scfg.warps * SDB_MATCH_BLOCK;
+        const uint32_t w = (uint32_t)((per + per / 4 + chunk - 1) / chunk);
+        if (w > h->want_match) h->want_match = w;
+    }
+    if (need_ovf > h->scfg.ovf_max) {
+        const uint32_t w = (uint32_t)(2 * need_ovf);
+        if (w > h->want_ovf) h->want_ovf = w;
+    }
+    *n_short = h->h_stats[SDB_STAT_SHORT];
+    if (*n_short) h->slack_warps = 0;
+    if (*n_short && h->want_surv <= h->scfg.surv_avg && h->want_ovf <= h->scfg.ovf_max) {
+        /* flagged although the recorded need fits (long messages share the arena): double */
+        h->want_surv = 2 * h->scfg.surv_avg; h->want_ovf = 2 * h->scfg.ovf_max;
+    }
+    return SDB_OK;
+}
+
 /* Scratch for launch groups of up to n_messages (the survivor / match records the kernels of one group hand each other).
  * After this call sdb_demod_pulse_device() with n <= n_messages per launch group only enqueues work. */
 extern "C" int sdb_reserve(SdbHandle *h, uint32_t n_messages)
 {
     if (!h) return SDB_E_ARG;
     CK(cudaSetDevice(h->device));
-    uint32_t chunk = n_messages < SDB_MU_CHUNK ? ((n_messages + 1023u) & ~1023u) : SDB_MU_CHUNK;
-    if (chunk > h->mu_chunk) {
-        CK(cudaDeviceSynchronize());
-        if (h->d_mu_scratch) CK(cudaFree(h->d_mu_scratch));
-        h->d_mu_scratch = nullptr; h->mu_chunk = 0;
-        CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_ms > h->tab.n_mu ? h->tab.n_ms : h->tab.n_mu, chunk)));
-        h->mu_chunk = chunk;
-    }
+    return ensure_scratch(h, n_messages, h->stream);
+}
+
+/* Device-pointer calls cannot repeat themselves: after synchronising, this says how many messages of the calls since the last
+ * check were flagged SDB_ST_SCRATCH (not decoded: the compact scratch arenas were too small for that batch) and grows the
+ * budgets, so that submitting those messages again succeeds.  0 with the shipped table unless a batch averages more than
+ * 18 surviving protocols per message. */
+extern "C" int sdb_scratch_short(SdbHandle *h, uint32_t *n_short)
+{
+    if (!h || !n_short) return SDB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    return check_scratch(h, h->stream, n_short);
+}
+
+/* Set the budgets the scratch is sized by (0 = keep): survivor records and MU match records per message on average, messages
+ * of the worst-case overflow region; slack_warps (0 = automatic: every resident warp) caps the number of arena blocks that are
+ * added on top of the per-message budgets — only the tests of the overflow paths want less than automatic.  The current block
+ * is released; the next call allocates with the new budgets. */
+extern "C" int sdb_scratch_budget(SdbHandle *h, uint32_t surv_avg, uint32_t match_avg, uint32_t ovf_max, uint32_t slack_warps)
+{
+    if (!h) return SDB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    if (surv_avg) h->want_surv = surv_avg;
+    if (match_avg) h->want_match = match_avg;
+    if (ovf_max) h->want_ovf = ovf_max;
+    h->slack_warps = slack_warps;
+    if (h->d_scratch) CK(cudaFree(h->d_scratch));
+    h->d_scratch = nullptr; h->scfg = SdbScratchCfg{0, 0, 0, 0, 0};
     return SDB_OK;
+}
+
+/* bytes of the scratch block as allocated, and its budgets: {chunk, surv_avg, match_avg, ovf_max} */
+extern "C" size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[4])
+{
+    if (!h || !h->d_scratch) { if (cfg) cfg[0] = cfg[1] = cfg[2] = cfg[3] = 0; return 0; }
+    if (cfg) { cfg[0] = h->scfg.chunk; cfg[1] = h->scfg.surv_avg; cfg[2] = h->scfg.match_avg; cfg[3] = h->scfg.ovf_max; }
+    return sdb::pulse_scratch_bytes(pulse_stride(h), h->scfg);
 }
 
 /* Enqueue the kernels for messages [0, n) at d_msgs whose batch indices start at msg_base; counters are NOT reset. */
@@ -200,21 +315,13 @@ static int enqueue_pulse(SdbHandle *h, int kind, const SdbPulseMsg *d_msgs, cons
                          uint32_t msg_base, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap,
                          uint32_t *d_bits, uint32_t bits_cap, SdbCounters *d_counters, cudaStream_t st)
 {
-    int grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
+    const int *grid = kind == SDB_KIND_MS ? h->grid_ms : h->grid_mu;
     if (n) {
-        /* scratch is sized for the worst case (every protocol of every message survives), once per handle */
-        uint32_t chunk = n < SDB_MU_CHUNK ? ((n + 1023u) & ~1023u) : SDB_MU_CHUNK;
-        if (chunk > h->mu_chunk) {
-            CK(cudaSetDevice(h->device));
-            CK(cudaStreamSynchronize(st));
-            if (h->d_mu_scratch) CK(cudaFree(h->d_mu_scratch));
-            h->d_mu_scratch = nullptr; h->mu_chunk = 0;
-            CK(cudaMalloc(&h->d_mu_scratch, sdb::mu_scratch_bytes(h->tab.n_ms > h->tab.n_mu ? h->tab.n_ms : h->tab.n_mu, chunk)));
-            h->mu_chunk = chunk;
-        }
+        int rc = ensure_scratch(h, n, st);
+        if (rc != SDB_OK) return rc;
     }
     int rc = sdb::launch_pulse(kind, h->tab, d_msgs, d_digits, n, d_out, d_hits, hits_cap, d_bits, bits_cap, d_counters, grid,
-                               h->grid_long, h->d_mu_scratch, h->mu_chunk, msg_base, st);
+                               h->grid_long, h->d_scratch, h->scfg, msg_base, st);
     if (rc != 0) return set_err(h, SDB_E_CUDA, "pulse kernel launch", static_cast<cudaError_t>(rc));
     return SDB_OK;
 }
@@ -334,7 +441,30 @@ static int enqueue_format(SdbHandle *h, int kind, uint32_t hits_cap, uint32_t bi
     return SDB_OK;
 }
 
+static int demod_host_once(SdbHandle *h, int kind, int mc_repaired,
+                           const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                           SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                           uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, PayloadSink *sink);
+
+/* The compact scratch arenas are sized by average record counts: a batch that needs more has its excess messages flagged
+ * SDB_ST_SCRATCH by the kernels; the host paths then grow the scratch from the recorded need and run the call again, so that
+ * callers of the host-buffer entry points never see that status. */
+#define SDB_SCRATCH_RETRIES 6
 static int demod_host_impl(SdbHandle *h, int kind, int mc_repaired,
+                           const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
+                           SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
+                           uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, PayloadSink *sink)
+{
+    for (int attempt = 0;; attempt++) {
+        int rc = demod_host_once(h, kind, mc_repaired, msgs, digits, digits_len, n, out, hits, hits_cap, bits, bits_cap, counters, sink);
+        if (rc != SDB_OK || (kind != SDB_KIND_MS && kind != SDB_KIND_MU)) return rc;
+        uint32_t n_short = 0;
+        if ((rc = check_scratch(h, h->stream, &n_short)) != SDB_OK || !n_short) return rc;
+        if (attempt == SDB_SCRATCH_RETRIES) return set_err(h, SDB_E_SCRATCH, "pulse scratch: messages still flagged SDB_ST_SCRATCH after growing it");
+    }
+}
+
+static int demod_host_once(SdbHandle *h, int kind, int mc_repaired,
                            const void *msgs, const uint8_t *digits, size_t digits_len, uint32_t n,
                            SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                            uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, PayloadSink *sink)
@@ -453,7 +583,13 @@ extern "C" int sdb_demod_lines_host(SdbHandle *h, int kind,
                                     SdbMsgOut *out, SdbHit *hits, uint32_t hits_cap,
                                     uint32_t *bits, uint32_t bits_cap, SdbCounters *counters, SdbLineInfo *info)
 {
-    return settle(h, demod_lines_impl(h, kind, text, text_len, line_off, line_len, n, out, hits, hits_cap, bits, bits_cap, counters, info));
+    for (int attempt = 0;; attempt++) {
+        int rc = settle(h, demod_lines_impl(h, kind, text, text_len, line_off, line_len, n, out, hits, hits_cap, bits, bits_cap, counters, info));
+        if (rc != SDB_OK || !h) return rc;
+        uint32_t n_short = 0;
+        if ((rc = check_scratch(h, h->stream, &n_short)) != SDB_OK || !n_short) return rc;       /* (see demod_host_impl) */
+        if (attempt == SDB_SCRATCH_RETRIES) return set_err(h, SDB_E_SCRATCH, "pulse scratch: messages still flagged SDB_ST_SCRATCH after growing it");
+    }
 }
 
 static int demod_lines_impl(SdbHandle *h, int kind,

@@ -59,6 +59,14 @@
 #define KMAXD SDB_FAST_DIGITS
 #define KTHREADS SDB_PULSE_THREADS
 #define KMIN_CTAS SDB_PULSE_MIN_CTAS
+#ifndef SDB_MATCH_CTAS
+#define SDB_MATCH_CTAS SDB_PULSE_MIN_CTAS
+#endif
+#ifndef SDB_EMIT_CTAS
+#define SDB_EMIT_CTAS SDB_PULSE_MIN_CTAS
+#endif
+#define KMATCH_CTAS SDB_MATCH_CTAS    /* per-kernel register caps (65536 / (256 * CTAs)) for the two smaller MU kernels */
+#define KEMIT_CTAS SDB_EMIT_CTAS
 #define POS_BITS 11                   /* p <= 1023, n <= 1024 */
 #endif
 #define POS_MASK ((1u << POS_BITS) - 1u)
@@ -114,52 +122,34 @@ __device__ __forceinline__ int sdb_chk_idx(int i, int n) { if ((unsigned)i >= (u
 #define SDB_CHK(c) do { } while (0)
 #endif
 
-/* One resolved (message x MU protocol) task handed from the resolve kernel to the scan kernel, 16 bytes. */
-struct __align__(16) SdbSurv {
-    uint64_t start;        /* bits 0..55: id string of `start` (nibble-packed), bits 56..63: MU table row */
-    uint16_t c1, c0, cf;   /* id strings of one / zero / float (<= 4 digits) */
-    uint16_t meta;         /* SURV_POS_MASK: s0 (where D' begins), SURV_HASF: float resolved */
-};
-
-struct KArgs {
-    SdbDevTable tab;
-    const SdbPulseMsg *msgs;   /* already offset to the first message of this launch */
-    const uint8_t *digits;
-    uint32_t n;                /* messages of this launch */
-    uint32_t msg_base;         /* batch index of msgs[0] (hit.msg is a batch index) */
-    SdbMsgOut *out;            /* already offset */
-    SdbHit *hits;  uint32_t hits_cap;
-    uint32_t *bits; uint32_t bits_cap;
-    SdbCounters *ctr;
-    SdbSurv *surv;             /* n x surv_stride survivor slots (resolve -> scan) */
-    uint32_t *surv_cnt;        /* survivors per message */
-    uint32_t surv_stride;      /* protocols of this class (47 MS / 129 MU) */
-    uint32_t *match;           /* MU: n x MU_MCAP match records (match kernel -> emit kernel) */
-    uint32_t *match_cnt;       /* MU: records per message, or MU_MARK = left to the fused fallback kernel */
-    uint32_t *ticket;          /* this launch's work counter (zeroed before the chunk): warps draw messages ticket_batch at a time */
-    uint32_t ticket_batch;
-    uint32_t *long_list;       /* messages of this launch with SDB_FAST_DIGITS < dlen <= SDB_MAX_DIGITS (fast resolve -> long kernels) */
-    uint32_t *long_cnt;
-};
+typedef SdbPulseArgs KArgs;
 
 /* Messages differ a lot in cost (dlen 20..1024, 0..129 survivors), so a static message -> warp map leaves a tail at the
  * end of every launch (measured: chunks of 1 M instead of 262 144 messages were 7 % faster).  Warps therefore draw
  * their next messages from a per-launch counter. */
-__device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uint32_t &left, uint32_t &mi)
-{
 #ifdef SDB_PULSE_LONG
-    /* the long kernels draw from the list the fast resolve kernel wrote (complete: stream order) */
-    (void)left;
-    uint32_t b = 0;
-    if ((threadIdx.x & 31) == 0) {
-        b = atomicAdd(A.ticket, 1u);
-        b = b < *A.long_cnt ? A.long_list[b] : 0xFFFFFFFFu;
-    }
-    base = __shfl_sync(0xffffffffu, b, 0);
-    if (base == 0xFFFFFFFFu) return false;
-    mi = base;
-    return true;
+#define KLIST_ALWAYS true
 #else
+#define KLIST_ALWAYS false
+#endif
+/* LIST: the launch draws from a list an earlier kernel of the group wrote (complete: stream order) — the long kernels (messages
+ * of more than SDB_FAST_DIGITS digits) and the overflow pass of the fast resolve kernel; lpos = position in that list. */
+template <bool LIST>
+__device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uint32_t &left, uint32_t &mi, uint32_t &lpos)
+{
+    if (LIST || KLIST_ALWAYS) {
+        (void)left;
+        uint32_t b = 0, v = 0xFFFFFFFFu;
+        if ((threadIdx.x & 31) == 0) {
+            b = atomicAdd(A.ticket, 1u);
+            if (b < min(*A.list_cnt, A.list_max)) v = A.list[b];
+        }
+        base = __shfl_sync(0xffffffffu, v, 0);
+        if (base == 0xFFFFFFFFu) return false;
+        lpos = __shfl_sync(0xffffffffu, b, 0);
+        mi = base;
+        return true;
+    }
     if (!left) {
         uint32_t b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(A.ticket, A.ticket_batch);
@@ -169,8 +159,8 @@ __device__ __forceinline__ bool next_message(const KArgs &A, uint32_t &base, uin
     }
     mi = base++;
     left--;
+    lpos = 0;
     return true;
-#endif
 }
 
 /* A record the packed domain cannot represent (flagged by the packer, or malformed: > 8 slots, an id > 9, D longer than
@@ -202,7 +192,8 @@ struct __align__(16) WarpSm {
             uint32_t first2[100], last2[100]; /* digram ab: first position / last position + 1       */
             uint32_t first1[12], last1[12];   /* digit a                                             */
             uint32_t cnt2[100];               /* digram ab: occurrences at even | odd << 16 positions */
-            int16_t  T[SDB_MAX_CLK][8];       /* MU: tenths per (clock, slot); -32768 = empty slot   */
+            uint16_t T[SDB_MAX_CLK][8];       /* tenths per (clock, slot), biased: T_BIAS + clamp(t, +-T_CLAMP) in 0 .. 0x7FFF so that two
+                                               * of them are range-checked per 32-bit operation; T_EMPTY = empty / unused slot       */
             uint8_t  M[SDB_MAX_VALS];         /* candidate-slot mask per (clock, interval) pair      */
             uint8_t  plist[256];              /* table rows that passed the prefilter, in table order */
             uint32_t dead[SDB_KILL_WORDS];    /* bit r: protocol row r lacks a candidate slot for a mandatory value */
@@ -213,17 +204,19 @@ struct __align__(16) WarpSm {
             uint32_t Sm[MU_NS][MU_BW];        /* bit p: the start string occurs at position p        */
         };
     };
-    int32_t  pat[8];
     uint32_t val[BIT_WORDS];          /* bit plane of the current match (LSB-first)          */
     uint32_t fpl[BIT_WORDS];          /* 'F' plane                                           */
     uint32_t tmp[BIT_WORDS];          /* post-demodulation output                            */
     SdbHit   st_hits[ST_HITS];        /* staged hits of the current message                  */
     uint32_t st_bits[ST_WORDS];
+    int32_t  pat[8];
     int32_t  pd_rc, pd_no;
     /* per-message scalars (so that the out-of-line helpers need few arguments) */
     const uint16_t *rank;
     int32_t  dlen, npat;
     uint32_t pat_ids, msg;
+    uint32_t blk_off, blk_left;       /* resolve / match kernels: the warp's current block of the compact arena (kept here, not
+                                       * in registers: the message loops are at the 64-register cap already)                */
     /* hit sink */
     uint32_t nh, nw;                  /* hits / words produced so far                        */
     uint32_t hbase, wbase;            /* second pass: global bases                           */
@@ -257,6 +250,13 @@ __host__ __device__ __forceinline__ size_t hot_bytes(uint32_t nvals, uint32_t nr
 {
     return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((size_t)nrows * sizeof(HotRow) + 15) & ~(size_t)15) + 2 * SDB_MAX_CLK * sizeof(double) + 16;
 }
+
+/* biased tenths (see WarpSm::T): every accept interval of a compiled table lies well inside +-T_CLAMP (table.py checks) */
+#define T_BIAS 0x4000
+#define T_CLAMP 16000
+#define T_EMPTY 0x7FFFu
+#define T_GET(x) ((int)(x) - T_BIAS)
+__device__ __forceinline__ uint32_t t_biased(int t) { return (uint32_t)(min(max(t, -T_CLAMP), T_CLAMP) + T_BIAS); }
 
 /* ---- small helpers ------------------------------------------------------------------- */
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -297,6 +297,8 @@ __device__ __forceinline__ int tenths(int p, double c)
     return (int)r;
 }
 
+__device__ __noinline__ int tenths_cold(int p, double c) { return tenths(p, c); }   /* the rare exact path of tenths_fast, out of the hot loop */
+
 /* Same value, usually without the division: y' = p * (10/c) differs from the exact 10*RN(p/c) by < 1e-10,
  * so whenever y' is further than 1e-6 from a tie both round to the same integer; only near-ties (and
  * they do occur: p/c = 0.25, 0.35, ...) take the exact path. */
@@ -312,7 +314,7 @@ __device__ __forceinline__ int tenths_fast(int p, double c, double inv10c)
         if (r < -32000.0) r = -32000.0;
         return (int)r;
     }
-    return tenths(p, c);
+    return tenths_cold(p, c);
 }
 
 /* ---- warp-cooperative substring search: first p >= from with D[p:p+L] == tgt, else -1 ------- */
@@ -378,7 +380,7 @@ __device__ __noinline__ bool resolve_general(const SdbKeyTpl *__restrict__ k, in
 #pragma unroll
     for (int u = 0; u < SDB_MAX_UNIQ; u++) cnt[u] = __popc((bal >> (8 * u)) & 0xff);
     int ord = 0;
-#pragma unroll
+#pragma unroll 1
     for (int o = 1; o < 8; o++) {
         int other = __shfl_sync(FULL, key, (lane & ~7) | ((j + o) & 7));
         ord += other < key;
@@ -1173,10 +1175,10 @@ __device__ __forceinline__ bool tres(const HotKey &hk, const SdbKeyTpl *__restri
         const uint16_t *__restrict__ rank = sm.rank;
         const int lo0 = k->lo[0], lo1 = K > 1 ? k->lo[1] : 0;
         const uint32_t ro0 = k->rank_off[0], ro1 = K > 1 ? k->rank_off[1] : 0;
-        const int16_t *trow = sm.T[IDX(clk_idx, SDB_MAX_CLK)];
+        const uint16_t *trow = sm.T[IDX(clk_idx, SDB_MAX_CLK)];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int tj = trow[j];
+            const int tj = T_GET(trow[j]);
             ka[j] = ((ca >> j) & 1) ? (((int)__ldg(&rank[ro0 + (tj - lo0)]) << 3) | j) : TKEY_NONE;
             kb[j] = ((cb >> j) & 1) ? (((int)__ldg(&rank[ro1 + (tj - lo1)]) << 3) | j) : TKEY_NONE;
         }
@@ -1412,35 +1414,47 @@ __device__ __forceinline__ void stage_digits(const KArgs &A, WarpSm &sm, const S
     __syncwarp();
 }
 
+/* one round of the occurrence tables: 32 positions, one writer per distinct key (match_any) */
+__device__ __forceinline__ void occurrence_round(WarpSm &sm, int base, int dlen, int lane)
+{
+    int p = base + lane;
+    uint32_t x = win32(sm.dig, p);
+    int a = x & 0xF, b = (x >> 4) & 0xF;
+    bool va = p < dlen && a <= 9;
+    bool vb = va && (p + 1 < dlen) && b <= 9;
+    uint32_t ga = __match_any_sync(FULL, va ? a : 16 + lane);
+    uint32_t gb = __match_any_sync(FULL, vb ? a * 10 + b : 128 + lane);
+    if (va) {
+        if (lane == __ffs(ga) - 1 && sm.first1[IDX(a, 12)] == NONE32) sm.first1[IDX(a, 12)] = p;
+        if (lane == 31 - __clz(ga)) sm.last1[IDX(a, 12)] = p + 1;
+    }
+    if (vb) {
+        int code = a * 10 + b;
+        if (lane == __ffs(gb) - 1) {
+            if (sm.first2[IDX(code, 100)] == NONE32) sm.first2[IDX(code, 100)] = p;
+            /* base is a multiple of 32, so lane parity == position parity */
+            sm.cnt2[IDX(code, 100)] += (uint32_t)__popc(gb & 0x55555555u) | ((uint32_t)__popc(gb & 0xAAAAAAAAu) << 16);
+        }
+        if (lane == 31 - __clz(gb)) sm.last2[IDX(code, 100)] = p + 1;
+    }
+    __syncwarp();
+}
+
+/* COMPACT: the MU resolve kernel's hot code sits at the edge of the 32 KB instruction cache, so its loops
+ * are not unrolled; the MS kernel (smaller, short messages) keeps the compiler's unrolling. */
+template <bool COMPACT>
 __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const SdbPulseMsg *m, int dlen, uint32_t mi)
 {
     const int lane = lane_id();
     for (int i = lane; i < 100; i += 32) { sm.first2[IDX(i, 100)] = NONE32; sm.last2[IDX(i, 100)] = 0; sm.cnt2[IDX(i, 100)] = 0; }
     if (lane < 12) { sm.first1[IDX(lane, 12)] = NONE32; sm.last1[IDX(lane, 12)] = 0; }
     stage_digits(A, sm, m, dlen, mi);
-    /* occurrence tables, ascending rounds; one writer per distinct key per round (match_any) */
-    for (int base = 0; base < dlen; base += 32) {
-        int p = base + lane;
-        uint32_t x = win32(sm.dig, p);
-        int a = x & 0xF, b = (x >> 4) & 0xF;
-        bool va = p < dlen && a <= 9;
-        bool vb = va && (p + 1 < dlen) && b <= 9;
-        uint32_t ga = __match_any_sync(FULL, va ? a : 16 + lane);
-        uint32_t gb = __match_any_sync(FULL, vb ? a * 10 + b : 128 + lane);
-        if (va) {
-            if (lane == __ffs(ga) - 1 && sm.first1[IDX(a, 12)] == NONE32) sm.first1[IDX(a, 12)] = p;
-            if (lane == 31 - __clz(ga)) sm.last1[IDX(a, 12)] = p + 1;
-        }
-        if (vb) {
-            int code = a * 10 + b;
-            if (lane == __ffs(gb) - 1) {
-                if (sm.first2[IDX(code, 100)] == NONE32) sm.first2[IDX(code, 100)] = p;
-                /* base is a multiple of 32, so lane parity == position parity */
-                sm.cnt2[IDX(code, 100)] += (uint32_t)__popc(gb & 0x55555555u) | ((uint32_t)__popc(gb & 0xAAAAAAAAu) << 16);
-            }
-            if (lane == 31 - __clz(gb)) sm.last2[IDX(code, 100)] = p + 1;
-        }
-        __syncwarp();
+    /* occurrence tables, ascending rounds */
+    if (COMPACT) {
+#pragma unroll 1
+        for (int base = 0; base < dlen; base += 32) occurrence_round(sm, base, dlen, lane);
+    } else {
+        for (int base = 0; base < dlen; base += 32) occurrence_round(sm, base, dlen, lane);
     }
 }
 
@@ -1459,7 +1473,7 @@ __device__ __forceinline__ void stage_message(const KArgs &A, WarpSm &sm, const 
 __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &rec)
 {
     WarpSm &sm = SM();
-    const int t_slot = sm.T[IDX(pp->clk_idx, SDB_MAX_CLK)][lane_id() & 7];
+    const int t_slot = T_GET(sm.T[IDX(pp->clk_idx, SDB_MAX_CLK)][lane_id() & 7]);
     int s0 = 0, dummy;
     uint64_t start_t = 0, t1 = 0, t0 = 0, tf = 0;
     if (pp->key[0].len && !resolve_key(&pp->key[0], t_slot, 0, true, start_t, s0)) return false;      /* :67-88 */
@@ -1477,7 +1491,7 @@ __device__ __noinline__ bool resolve_mu_warp(const SdbPulseProto *pp, SdbSurv &r
 __device__ __noinline__ bool resolve_ms_warp(const SdbPulseProto *pp, SdbSurv &rec)
 {
     WarpSm &sm = SM();
-    const int t_slot = sm.T[IDX(0, SDB_MAX_CLK)][lane_id() & 7];
+    const int t_slot = T_GET(sm.T[IDX(0, SDB_MAX_CLK)][lane_id() & 7]);
     const int w = pp->width;
     uint64_t ts = 0, t1 = 0, t0 = 0, tf = 0;
     int spos = 0, dummy;
@@ -1510,6 +1524,9 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
 #else
 #define SLOT_USED(j) true
 #endif
+    /* the slots that take part, as a bit mask and as a list of slot numbers (one nibble each, ascending) */
+    const bool slot_on = lane < npat && SLOT_USED(lane & 7);
+    const uint32_t usedm = __ballot_sync(FULL, slot_on) & 0xFFu;
     if (MS) {
         const int cp = m->cp;
         if (cp == 0xFF) return false;                                /* message_synced.py:60-62 */
@@ -1517,36 +1534,44 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
         if (pc == 0) return false;                                   /* :65-66 */
         clock_abs = fabs((double)pc);
         /* tenths of the (<= 8) slots, normalised by the message's own clock (:70-72), into row 0 of T */
-        const int t = ((lane & 7) < npat && SLOT_USED(lane & 7)) ? tenths(sm.pat[lane & 7], clock_abs) : -32768;
-        if (lane < 8) sm.T[IDX(0, SDB_MAX_CLK)][lane] = (int16_t)t;
+        if (lane < 8) sm.T[IDX(0, SDB_MAX_CLK)][lane] = (uint16_t)(slot_on ? t_biased(tenths(sm.pat[lane], clock_abs)) : T_EMPTY);
         v0 = (int)A.tab.n_mu_vals; v1 = (int)A.tab.n_vals;          /* the MS intervals follow the MU pairs */
     } else {
-        /* tenths table for every distinct protocol clock (message_unsynced.py:59-64) */
+        /* tenths table for every distinct protocol clock (message_unsynced.py:59-64): one lane per (clock, slot that takes
+         * part) — 4.9 of 8 slots on average — after the rows have been filled with "empty" */
         const int ncl = A.tab.n_clk;
         const double *hclk = HOT_CLK(A.tab.n_vals, A.tab.n_mu);
+        const int nused = __popc(usedm);
+        const uint32_t ulist = __reduce_or_sync(FULL, slot_on ? (uint32_t)lane << (4 * __popc(usedm & ((1u << lane) - 1))) : 0u);
 #pragma unroll 1
-        for (int idx = lane; idx < ncl * 8; idx += 32) {
-            int c = idx >> 3, j = idx & 7;
-            sm.T[IDX(c, SDB_MAX_CLK)][j] = (int16_t)((j < npat && SLOT_USED(j)) ? tenths_fast(sm.pat[j], hclk[c], hclk[ncl + c]) : -32768);
+        for (int c = lane; c < ncl; c += 32)
+            *reinterpret_cast<uint4 *>(&sm.T[IDX(c, SDB_MAX_CLK)][0]) = make_uint4(T_EMPTY * 0x10001u, T_EMPTY * 0x10001u, T_EMPTY * 0x10001u, T_EMPTY * 0x10001u);
+        __syncwarp();
+        const uint32_t inv = k_inv16[IDX(nused, 9)];
+#pragma unroll 1
+        for (int idx = lane; idx < ncl * nused; idx += 32) {
+            const int c = (int)(((uint32_t)idx * inv) >> 16);        /* idx / nused (exact: idx < 8^4, nused <= 8) */
+            const int j = (int)((ulist >> (4 * (idx - c * nused))) & 7u);
+            sm.T[IDX(c, SDB_MAX_CLK)][j] = (uint16_t)t_biased(tenths_fast(sm.pat[j], hclk[c], hclk[ncl + c]));
         }
         v0 = 0; v1 = (int)A.tab.n_mu_vals;
     }
     __syncwarp();
-    /* candidate-slot mask of every distinct (clock, accept interval) pair: one lane per pair; a pair without any
-     * candidate kills every protocol that needs it (pattern_utils.py:78-80) */
+    /* candidate-slot mask of every distinct (clock, accept interval) pair: one lane per pair, two slots per 32-bit operation
+     * (biased 15-bit values: bit 15 of (x | 0x8000) - y says x >= y, and no borrow crosses the halfword boundary); a pair
+     * without any candidate kills every protocol that needs it (pattern_utils.py:78-80) */
     uint4 ka = make_uint4(0, 0, 0, 0), kb = make_uint4(0, 0, 0, 0);
+    const uint32_t H = 0x80008000u;
 #pragma unroll 1
     for (int v = v0 + lane; v < v1; v += 32) {
-        const SdbValRow vr = HOT_VALS()[v];
-        const int4 row = *reinterpret_cast<const int4 *>(&sm.T[IDX(vr.clk_idx, SDB_MAX_CLK)][0]);
-        const int lo = vr.lo, hi = vr.hi;
-        int t0 = (int16_t)(row.x & 0xffff), t1 = row.x >> 16, t2 = (int16_t)(row.y & 0xffff), t3 = row.y >> 16;
-        int t4 = (int16_t)(row.z & 0xffff), t5 = row.z >> 16, t6 = (int16_t)(row.w & 0xffff), t7 = row.w >> 16;
-        uint32_t mk = (uint32_t)(t0 >= lo && t0 <= hi) | ((uint32_t)(t1 >= lo && t1 <= hi) << 1) |
-                      ((uint32_t)(t2 >= lo && t2 <= hi) << 2) | ((uint32_t)(t3 >= lo && t3 <= hi) << 3) |
-                      ((uint32_t)(t4 >= lo && t4 <= hi) << 4) | ((uint32_t)(t5 >= lo && t5 <= hi) << 5) |
-                      ((uint32_t)(t6 >= lo && t6 <= hi) << 6) | ((uint32_t)(t7 >= lo && t7 <= hi) << 7);
-        sm.M[IDX(v, SDB_MAX_VALS)] = (uint8_t)mk;                                       /* empty slots hold -32768 and never qualify */
+        const SdbValRow vr = HOT_VALS()[v];                          /* CTA-shared copy: lo = biased lower bound, hi = biased upper bound | 0x8000 */
+        const uint4 row = *reinterpret_cast<const uint4 *>(&sm.T[IDX(vr.clk_idx, SDB_MAX_CLK)][0]);
+        const uint32_t lo2 = (uint32_t)(uint16_t)vr.lo * 0x10001u, hi2 = (uint32_t)(uint16_t)vr.hi * 0x10001u;
+        const uint32_t m0 = ((row.x | H) - lo2) & (hi2 - row.x) & H, m1 = ((row.y | H) - lo2) & (hi2 - row.y) & H;
+        const uint32_t m2 = ((row.z | H) - lo2) & (hi2 - row.z) & H, m3 = ((row.w | H) - lo2) & (hi2 - row.w) & H;
+        const uint32_t r = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);      /* slot 2i at bit 2i, slot 2i + 1 at bit 16 + 2i */
+        const uint32_t mk = (r | (r >> 15)) & 0xFFu;
+        sm.M[IDX(v, SDB_MAX_VALS)] = (uint8_t)mk;                                       /* empty slots hold T_EMPTY and never qualify */
         if (!mk) {
             const uint4 *kr = reinterpret_cast<const uint4 *>(A.tab.kill + (size_t)v * SDB_KILL_WORDS);
             const uint4 k0 = __ldg(&kr[0]);
@@ -1568,7 +1593,41 @@ __device__ __forceinline__ bool prepare_tables(const KArgs &A, WarpSm &sm, const
     return true;
 }
 
-template <bool MS>
+/* A warp's next block of a compact arena (survivor or match records): `blk` records, or what is left of the arena; false when
+ * that is less than `need`.  Out of line on purpose: it runs once per ~15 messages, and the resolve kernel's hot code sits at
+ * the edge of the instruction cache (a staging + copy epilogue of 250 instructions cost the kernel 18 %). */
+__device__ __noinline__ bool claim_block(uint32_t *ctr, uint32_t cap, uint32_t blk, uint32_t need)
+{
+    WarpSm &sm = SM();
+    const uint32_t want = blk > need ? blk : need;
+    uint32_t o = 0;
+    if (lane_id() == 0) o = atomicAdd(ctr, want);
+    o = __shfl_sync(FULL, o, 0);
+    const uint32_t left = (o <= cap && want <= cap - o) ? want : (o < cap ? cap - o : 0u);     /* the arena's tail: what is left of it, if anything */
+    __syncwarp();
+    if (lane_id() == 0) { sm.blk_off = o; sm.blk_left = left; }
+    __syncwarp();
+    return left >= need;
+}
+#ifndef SDB_PULSE_LONG
+/* no room in the compact arena: the message goes to the overflow pass (worst-case slots); SDB_SURV_SHORT when that is full too */
+__device__ __noinline__ uint32_t overflow_push(uint32_t *ovf_cnt, uint32_t *ovf_list, uint32_t ovf_max, uint32_t mi)
+{
+    uint32_t b = 0;
+    if (lane_id() == 0) {
+        b = atomicAdd(ovf_cnt, 1u);
+        if (b < ovf_max) ovf_list[b] = mi;                            /* the overflow pass writes this message's surv_meta */
+    }
+    b = __shfl_sync(FULL, b, 0);
+    return b < ovf_max ? 0u : SDB_SURV_SHORT;
+}
+#endif
+
+/* OVF = false: the launch group's messages by ticket; survivors go straight into the warp's current block of the compact arena
+ * (claimed SDB_SURV_BLOCK records at a time; a block is abandoned when fewer records are left than protocols passed the
+ * prefilter).  When the arena is exhausted the message is listed for the overflow pass.
+ * OVF = true (fast build only): the overflow pass — list-driven, survivors written into worst-case slots. */
+template <bool MS, bool OVF>
 __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
 {
     WarpSm &sm = SM();
@@ -1579,7 +1638,11 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
     /* once per CTA: the pairs and the hot protocol fields into shared memory */
     {
         SdbValRow *sv = reinterpret_cast<SdbValRow *>(g_dyn);
-        for (uint32_t v = threadIdx.x; v < A.tab.n_vals; v += blockDim.x) sv[v] = A.tab.vals[v];
+        for (uint32_t v = threadIdx.x; v < A.tab.n_vals; v += blockDim.x) {
+            SdbValRow r = A.tab.vals[v];                             /* bounds biased like T (prepare_tables) */
+            r.lo = (int16_t)(r.lo + T_BIAS); r.hi = (int16_t)((r.hi + T_BIAS) | 0x8000);
+            sv[v] = r;
+        }
         HotRow *hrw = const_cast<HotRow *>(HOT_ROWS(A.tab.n_vals));
         for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
             const SdbPulseProto *pr = &rows[r];
@@ -1600,25 +1663,27 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
     }
     const HotRow *hot = HOT_ROWS(A.tab.n_vals);
 
-    uint32_t tk_base = 0, tk_left = 0, mi = 0;
-    while (next_message(A, tk_base, tk_left, mi)) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0, lpos = 0;
+    if (lane == 0) { sm.blk_off = 0; sm.blk_left = 0; }              /* this warp's block of the compact survivor arena */
+    __syncwarp();
+    while (next_message<OVF>(A, tk_base, tk_left, mi, lpos)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         const int dlen = m->dlen;
         uint32_t nsurv = 0;
+        uint32_t off = OVF ? A.ovf_base + lpos * A.surv_stride : 0u, cnt = 0;
         /* records outside the packed domain (ids > 9, > 8 slots, D too long) yield no hits instead of undefined lookups */
         const bool ids_ok = m->npat <= SDB_MAX_SLOTS &&
                             !__any_sync(FULL, lane < m->npat && ((m->pat_ids >> (4 * (lane & 7))) & 0xF) > 9);
         const bool decodable = (m->flags & SDB_MSG_VALID) && !(m->flags & SDB_MSG_DOMAIN) && dlen > 0 && dlen <= SDB_MAX_DIGITS && ids_ok;
 #ifndef SDB_PULSE_LONG
         if (decodable && dlen > KMAXD) {               /* too long for this kernel's staging: the long kernels take it */
-            if (lane == 0) A.long_list[atomicAdd(A.long_cnt, 1u)] = mi;
+            if (lane == 0) A.long_list[atomicAdd(SDB_CTL(A, SDB_CTL_LONG_CNT), 1u)] = mi;
         } else
 #endif
         if (decodable) {
-            stage_message(A, sm, m, dlen, mi);
+            stage_message<!MS>(A, sm, m, dlen, mi);
             double clock_abs = 0.0;
             if (prepare_tables<MS>(A, sm, m, clock_abs)) {
-                SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
                 /* pass 1 (lane = protocol): keep the protocols whose mandatory values all have a candidate slot
                  * (pattern_utils.py:78-80; MS also the 30 % clock gate, message_synced.py:83-88); compact their
                  * row numbers, in table order, into plist */
@@ -1639,6 +1704,18 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
                     nalive += __popc(bal);
                 }
                 __syncwarp();
+                if (!OVF) {
+                    if (sm.blk_left < nalive && !claim_block(SDB_CTL(A, SDB_CTL_SURV), A.surv_cap, SDB_SURV_BLOCK, nalive)) {
+#ifndef SDB_PULSE_LONG
+                        cnt = overflow_push(SDB_CTL(A, SDB_CTL_OVF_CNT), A.ovf_list, A.ovf_max, mi);
+#else
+                        cnt = SDB_SURV_SHORT;                          /* the host grows the arena and runs the call again */
+#endif
+                        nalive = 0;
+                    }
+                    off = sm.blk_off;
+                }
+                SdbSurv *const slots = A.surv + off;
                 /* pass 2 (lane = surviving protocol): exact template resolution */
 #pragma unroll 1
                 for (uint32_t q0 = 0; q0 < nalive; q0 += 32) {
@@ -1671,7 +1748,7 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
                             if (!MS && pb->width == 2) {
                                 uint64_t st = 0;
                                 int sp = 0;
-                                const int t_slot = sm.T[IDX(pb->clk_idx, SDB_MAX_CLK)][lane & 7];
+                                const int t_slot = T_GET(sm.T[IDX(pb->clk_idx, SDB_MAX_CLK)][lane & 7]);
                                 const bool ok = resolve_key(&pb->key[0], t_slot, 0, true, st, sp);     /* :67-88 */
                                 if (lane == b) { state = ok ? 4 : 0; long_start = st; s0w = sp; }
                             } else {
@@ -1685,14 +1762,18 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
                     const uint32_t alive = __ballot_sync(FULL, state == 1);
                     if (state == 1) {                                 /* protocol-table order is the slot order */
                         rec.start |= (uint64_t)q << 56;
-                        SDB_CHK(nsurv + __popc(alive & ((1u << lane) - 1)) < A.surv_stride);
                         slots[nsurv + __popc(alive & ((1u << lane) - 1))] = rec;
                     }
                     nsurv += __popc(alive);
                 }
+                if (!OVF && nsurv) {
+                    __syncwarp();
+                    if (lane == 0) { sm.blk_off += nsurv; sm.blk_left -= nsurv; }
+                }
+                if (nalive) cnt = nsurv;
             }
         }
-        if (lane == 0) A.surv_cnt[mi] = nsurv;
+        if (lane == 0) A.surv_meta[mi] = make_uint2(off, cnt);
         __syncwarp();
     }
 }
@@ -1731,21 +1812,26 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
     WarpSm &sm = SM();
     const int lane = lane_id();
 
-    uint32_t tk_base = 0, tk_left = 0, mi = 0;
-    while (next_message(A, tk_base, tk_left, mi)) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0, lpos = 0;
+    while (next_message<false>(A, tk_base, tk_left, mi, lpos)) {
         const SdbPulseMsg *m = &A.msgs[mi];
         SdbMsgOut mo;
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
 #ifndef SDB_PULSE_LONG
-        if (!MS && A.match_cnt[mi] != MU_MARK) continue;         /* MU: only what the match kernel could not hand over */
+        if (!MS && A.match_meta[mi].y != MU_MARK) continue;      /* MU: only what the match kernel could not hand over */
 #endif
-        const uint32_t nsurv = A.surv_cnt[mi];
-        if (MS && nsurv == 0 && msg_domain(m)) {                 /* (a record outside the domain never has survivors) */
+        const uint2 sv = A.surv_meta[mi];
+        uint32_t nsurv = sv.y;
+        if (nsurv == SDB_SURV_SHORT) {                           /* not resolved: the scratch was too small for this launch group */
+            nsurv = 0;
+            mo.status = SDB_ST_SCRATCH;
+            if (lane == 0) atomicAdd(SDB_CTL(A, SDB_CTL_SHORT), 1u);
+        } else if (MS && nsurv == 0 && msg_domain(m)) {   /* (a record outside the domain never has survivors) */
             mo.status = SDB_ST_DOMAIN;
             if (lane == 0) atomicAdd(&A.ctr->domain, 1u);
         }
         if (nsurv) {
-            const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
+            const SdbSurv *slots = A.surv + sv.x;
             stage_digits(A, sm, m, m->dlen, mi);
             uint32_t unused = 0;
             int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu<false>(A, slots, nsurv, nullptr, unused);
@@ -1787,32 +1873,46 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
 }
 
 #ifndef SDB_PULSE_LONG
-/* MU, kernel 2 of 3: every survivor's regex matches -> match records (message_unsynced.py:146-217) */
-__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_match_kernel(KArgs A)
+/* MU, kernel 2 of 3: every survivor's regex matches -> match records (message_unsynced.py:146-217), written into the warp's
+ * current block of the compact match arena; when that arena is exhausted the message is left to the fused fallback kernel like
+ * one with more than MU_MCAP matches. */
+__global__ void __launch_bounds__(KTHREADS, KMATCH_CTAS) mu_match_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
 
-    uint32_t tk_base = 0, tk_left = 0, mi = 0;
-    while (next_message(A, tk_base, tk_left, mi)) {
+    uint32_t tk_base = 0, tk_left = 0, mi = 0, lpos = 0;
+    if (lane == 0) { sm.blk_off = 0; sm.blk_left = 0; }              /* this warp's block of the compact match arena */
+    __syncwarp();
+    while (next_message<false>(A, tk_base, tk_left, mi, lpos)) {
         const SdbPulseMsg *m = &A.msgs[mi];
-        const uint32_t nsurv = A.surv_cnt[mi];
-        uint32_t nrec = 0;
+        const uint2 sv = A.surv_meta[mi];
+        const bool scratch_short = sv.y == SDB_SURV_SHORT;
+        const uint32_t nsurv = scratch_short ? 0u : sv.y;
+        uint32_t nrec = 0, moff = 0;
         int status = SDB_ST_OK;
         if (nsurv) {
             stage_digits(A, sm, m, m->dlen, mi);
-            status = scan_survivors_mu<true>(A, A.surv + (size_t)mi * A.surv_stride, nsurv, A.match + (size_t)mi * MU_MCAP, nrec);
+            if (sm.blk_left < MU_MCAP && !claim_block(SDB_CTL(A, SDB_CTL_MATCH), A.match_cap, SDB_MATCH_BLOCK, MU_MCAP))
+                status = SDB_ST_MU_OVERFLOW;                          /* match arena exhausted: the fused fallback kernel takes the message */
+            else {
+                moff = sm.blk_off;
+                status = scan_survivors_mu<true>(A, A.surv + sv.x, nsurv, A.match + moff, nrec);
+                __syncwarp();
+                if (status == SDB_ST_OK && lane == 0) { sm.blk_off = moff + nrec; sm.blk_left -= nrec; }
+            }
             __syncwarp();
         }
         if (lane == 0) {
-            if (status == SDB_ST_MU_OVERFLOW) A.match_cnt[mi] = MU_MARK;
+            if (status == SDB_ST_MU_OVERFLOW) A.match_meta[mi] = make_uint2(0u, MU_MARK);
             else {
                 const bool raised = status != SDB_ST_OK;
-                A.match_cnt[mi] = raised ? 0u : nrec;
+                A.match_meta[mi] = make_uint2(moff, raised ? 0u : nrec);
                 if (raised || nrec == 0) {                       /* nothing left to do for the emit kernel */
                     SdbMsgOut mo;
                     mo.hit_off = 0; mo.nhits = 0; mo.status = (uint8_t)status; mo.reason = 0;
-                    if (nsurv == 0 && msg_domain(m)) { mo.status = SDB_ST_DOMAIN; atomicAdd(&A.ctr->domain, 1u); }
+                    if (scratch_short) { mo.status = SDB_ST_SCRATCH; atomicAdd(SDB_CTL(A, SDB_CTL_SHORT), 1u); }
+                    else if (nsurv == 0 && msg_domain(m)) { mo.status = SDB_ST_DOMAIN; atomicAdd(&A.ctr->domain, 1u); }
                     A.out[mi] = mo;
                     if (raised) atomicAdd(&A.ctr->raised, 1u);   /* exception: earlier hits are lost */
                 }
@@ -1853,18 +1953,19 @@ __device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slot
 }
 
 /* MU, kernel 3 of 3: match records -> hits (message_unsynced.py:220-290) */
-__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_emit_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KEMIT_CTAS) mu_emit_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
 
-    uint32_t tk_base = 0, tk_left = 0, mi = 0;
-    while (next_message(A, tk_base, tk_left, mi)) {
-        const uint32_t nrec = A.match_cnt[mi];
+    uint32_t tk_base = 0, tk_left = 0, mi = 0, lpos = 0;
+    while (next_message<false>(A, tk_base, tk_left, mi, lpos)) {
+        const uint2 mm = A.match_meta[mi];
+        const uint32_t nrec = mm.y;
         if (nrec == 0 || nrec == MU_MARK) continue;
         const SdbPulseMsg *m = &A.msgs[mi];
-        const SdbSurv *slots = A.surv + (size_t)mi * A.surv_stride;
-        const uint32_t *recs = A.match + (size_t)mi * MU_MCAP;
+        const SdbSurv *slots = A.surv + A.surv_meta[mi].x;
+        const uint32_t *recs = A.match + mm.x;
         SdbMsgOut mo;
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
         stage_digits(A, sm, m, m->dlen, mi);
@@ -1908,33 +2009,74 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) mu_emit_kernel(KArgs A)
 template <bool MS>
 static size_t resolve_dyn_smem(const SdbDevTable &tab)
 {
-    cudaFuncSetAttribute(resolve_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    cudaFuncSetAttribute(resolve_kernel<MS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    cudaFuncSetAttribute(resolve_kernel<MS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
     return hot_bytes(tab.n_vals, MS ? tab.n_ms : tab.n_mu);
 }
 
-int pulse_blocks_per_sm(int kind, const SdbDevTable &tab)
+/* resident CTAs per SM of the resolve, match / scan and emit kernels (each launch is a persistent grid of its own size) */
+void pulse_blocks_per_sm(int kind, const SdbDevTable &tab, int per_sm[3])
 {
-    int a = 0, b = 0;
+    int a = 0, b = 0, c = 0;
     if (kind == SDB_KIND_MS) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, SDB_PULSE_THREADS, resolve_dyn_smem<true>(tab));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true, false>, SDB_PULSE_THREADS, resolve_dyn_smem<true>(tab));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, SDB_PULSE_THREADS, 0);
+        c = b;
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false>, SDB_PULSE_THREADS, resolve_dyn_smem<false>(tab));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<false, false>, SDB_PULSE_THREADS, resolve_dyn_smem<false>(tab));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mu_match_kernel, SDB_PULSE_THREADS, 0);
-        int c = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, mu_emit_kernel, SDB_PULSE_THREADS, 0);
-        if (c < b) b = c;
     }
-    int nb = a < b ? a : b;
-    return nb > 0 ? nb : 1;
+    per_sm[0] = a > 0 ? a : 1; per_sm[1] = b > 0 ? b : 1; per_sm[2] = c > 0 ? c : 1;
 }
 
-size_t mu_scratch_bytes(uint32_t stride, uint32_t chunk)
+/* ---- scratch layout (one block per handle; SdbScratchCfg in sdb_pulse.h) ---- */
+struct ScratchLayout {
+    size_t surv, surv_meta, match, match_meta, ctl, stats, long_list, ovf_list, total;
+    uint32_t surv_cap, match_cap;
+};
+static ScratchLayout scratch_layout(uint32_t stride, const SdbScratchCfg &c)
 {
-    return (size_t)chunk * stride * sizeof(SdbSurv) + (size_t)chunk * sizeof(uint32_t)        /* survivor slots + counts */
-           + (size_t)chunk * MU_MCAP * sizeof(uint32_t) + (size_t)chunk * sizeof(uint32_t)    /* MU match records + counts */
-           + 64                                                                               /* 16 work counters */
-           + (size_t)chunk * sizeof(uint32_t);                                                /* list of long messages */
+    ScratchLayout L;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const uint64_t scap = (uint64_t)c.chunk * c.surv_avg + (uint64_t)c.warps * SDB_SURV_BLOCK,
+                   mcap = (uint64_t)c.chunk * c.match_avg + (uint64_t)c.warps * SDB_MATCH_BLOCK;
+    L.surv_cap = scap > 0xF0000000ull ? 0xF0000000u : (uint32_t)scap;
+    L.match_cap = mcap > 0xF0000000ull ? 0xF0000000u : (uint32_t)mcap;
+    size_t o = 0;
+    L.surv = o;       o = up(o + ((size_t)L.surv_cap + (size_t)c.ovf_max * stride) * sizeof(SdbSurv));
+    L.surv_meta = o;  o = up(o + (size_t)c.chunk * sizeof(uint2));
+    L.match = o;      o = up(o + (size_t)L.match_cap * sizeof(uint32_t));
+    L.match_meta = o; o = up(o + (size_t)c.chunk * sizeof(uint2));
+    L.ctl = o;        o = up(o + SDB_CTL_WORDS * sizeof(uint32_t));
+    L.stats = o;      o = up(o + SDB_STAT_WORDS * sizeof(uint32_t));
+    L.long_list = o;  o = up(o + (size_t)c.chunk * sizeof(uint32_t));
+    L.ovf_list = o;   o = up(o + (size_t)c.ovf_max * sizeof(uint32_t));
+    L.total = o;
+    return L;
+}
+size_t pulse_scratch_bytes(uint32_t stride, const SdbScratchCfg &cfg) { return scratch_layout(stride, cfg).total; }
+size_t pulse_scratch_stats_offset(uint32_t stride, const SdbScratchCfg &cfg) { return scratch_layout(stride, cfg).stats; }
+size_t pulse_scratch_ctl_offset(uint32_t stride, const SdbScratchCfg &cfg) { return scratch_layout(stride, cfg).ctl; }
+void pulse_scratch_caps(uint32_t stride, const SdbScratchCfg &cfg, uint32_t caps[2])
+{
+    const ScratchLayout L = scratch_layout(stride, cfg);
+    caps[0] = L.surv_cap; caps[1] = L.match_cap;
+}
+
+/* between launch groups: fold the group's allocation counters into the persistent statistics (what the host sizes the
+ * scratch from) and zero the work / allocation counters for the next group */
+__global__ void fold_ctl_kernel(uint32_t *ctl, uint32_t *stats)
+{
+    const int t = threadIdx.x;
+    if (t == 0) {
+        stats[SDB_STAT_SURV] = max(stats[SDB_STAT_SURV], ctl[SDB_CTL_SURV * SDB_CTL_STRIDE]);
+        stats[SDB_STAT_MATCH] = max(stats[SDB_STAT_MATCH], ctl[SDB_CTL_MATCH * SDB_CTL_STRIDE]);
+        stats[SDB_STAT_OVF] = max(stats[SDB_STAT_OVF], ctl[SDB_CTL_OVF_CNT * SDB_CTL_STRIDE]);
+        stats[SDB_STAT_SHORT] += ctl[SDB_CTL_SHORT * SDB_CTL_STRIDE];
+    }
+    __syncwarp();
+    if (t < SDB_CTL_COUNTERS) ctl[t * SDB_CTL_STRIDE] = 0;
 }
 
 /* unit op: one postDemo_* call on one bit list (bytes 0/1), executed by the device function above */
@@ -1974,47 +2116,65 @@ unsigned int debug_violations(bool reset)
 
 int launch_pulse(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
                  SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                 SdbCounters *d_ctr, int grid, int grid_long, void *mu_scratch, uint32_t mu_chunk, uint32_t msg_base0, cudaStream_t stream)
+                 SdbCounters *d_ctr, const int grid[3], int grid_long, void *scratch, const SdbScratchCfg &cfg, uint32_t msg_base0, cudaStream_t stream)
 {
-    KArgs A;
-    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base0; A.out = d_out;
-    A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
-    A.surv = nullptr; A.surv_cnt = nullptr; A.surv_stride = 0; A.ticket = nullptr; A.ticket_batch = 1;
     if (n == 0) return 0;
-    const uint32_t wpc = SDB_PULSE_THREADS / 32;
-    if (!mu_scratch || !mu_chunk) return (int)cudaErrorInvalidValue;
+    if (!scratch || !cfg.chunk) return (int)cudaErrorInvalidValue;
     const bool ms = kind == SDB_KIND_MS;
     const uint32_t stride = tab.n_ms > tab.n_mu ? tab.n_ms : tab.n_mu;       /* scratch is sized for the larger class */
-    A.surv = static_cast<SdbSurv *>(mu_scratch);
-    A.surv_cnt = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(mu_scratch) + (size_t)mu_chunk * stride * sizeof(SdbSurv));
+    const ScratchLayout L = scratch_layout(stride, cfg);
+    uint8_t *sb = static_cast<uint8_t *>(scratch);
+    KArgs A;
+    A.tab = tab; A.digits = d_digits; A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
+    A.surv = reinterpret_cast<SdbSurv *>(sb + L.surv); A.surv_cap = L.surv_cap; A.ovf_base = L.surv_cap; A.ovf_max = cfg.ovf_max;
     A.surv_stride = ms ? tab.n_ms : tab.n_mu;
-    A.match = A.surv_cnt + mu_chunk;
-    A.match_cnt = A.match + (size_t)mu_chunk * MU_MCAP;
-    uint32_t *tickets = A.match_cnt + mu_chunk;                    /* 16 work counters, zeroed per chunk: [0..3] fast kernels, [4..5] long kernels, [6] long-list length */
-    A.long_list = tickets + 16;
-    A.long_cnt = tickets + 6;
-    for (uint32_t off = 0; off < n; off += mu_chunk) {
+    A.surv_meta = reinterpret_cast<uint2 *>(sb + L.surv_meta);
+    A.match = reinterpret_cast<uint32_t *>(sb + L.match); A.match_cap = L.match_cap;
+    A.match_meta = reinterpret_cast<uint2 *>(sb + L.match_meta);
+    A.ctl = reinterpret_cast<uint32_t *>(sb + L.ctl);
+    uint32_t *stats = reinterpret_cast<uint32_t *>(sb + L.stats);
+    A.long_list = reinterpret_cast<uint32_t *>(sb + L.long_list);
+    A.ovf_list = reinterpret_cast<uint32_t *>(sb + L.ovf_list);
+    A.list = nullptr; A.list_cnt = nullptr; A.list_max = 0;
+    const uint32_t wpc = SDB_PULSE_THREADS / 32;
+    const size_t dyn = hot_bytes(tab.n_vals, ms ? tab.n_ms : tab.n_mu);
+    for (uint32_t off = 0; off < n; off += cfg.chunk) {
         A.msgs = d_msgs + off; A.out = d_out + off; A.msg_base = msg_base0 + off;
-        A.n = n - off < mu_chunk ? n - off : mu_chunk;
-        uint32_t need = (A.n + wpc - 1) / wpc;
-        int g = need < (uint32_t)grid ? (int)need : grid;
+        A.n = n - off < cfg.chunk ? n - off : cfg.chunk;
+        const uint32_t need = (A.n + wpc - 1) / wpc;
+        int g[3];
+        for (int i = 0; i < 3; i++) g[i] = need < (uint32_t)grid[i] ? (int)need : grid[i];
         A.ticket_batch = ms ? 4 * SDB_TICKET_BATCH : SDB_TICKET_BATCH;   /* MS messages are ~10x cheaper; the fallback kernel skips nearly everything: 256 */
-        cudaError_t e = cudaMemsetAsync(tickets, 0, 16 * sizeof(uint32_t), stream);
-        if (e != cudaSuccess) return (int)e;
+        fold_ctl_kernel<<<1, 32, 0, stream>>>(A.ctl, stats);
+        A.list = nullptr; A.list_cnt = nullptr; A.list_max = 0;
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 0;
+        if (ms) resolve_kernel<true, false><<<g[0], SDB_PULSE_THREADS, dyn, stream>>>(A);
+        else resolve_kernel<false, false><<<g[0], SDB_PULSE_THREADS, dyn, stream>>>(A);
+        /* overflow pass: the messages whose survivors did not fit the compact arena (usually none: the grid exits at once) */
+        A.list = A.ovf_list; A.list_cnt = SDB_CTL(A, SDB_CTL_OVF_CNT); A.list_max = cfg.ovf_max;
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 6;
+        {
+            const uint32_t need_o = (cfg.ovf_max + wpc - 1) / wpc;
+            const int go = need_o < (uint32_t)g[0] ? (int)need_o : g[0];
+            if (ms) resolve_kernel<true, true><<<go, SDB_PULSE_THREADS, dyn, stream>>>(A);
+            else resolve_kernel<false, true><<<go, SDB_PULSE_THREADS, dyn, stream>>>(A);
+        }
+        A.list = nullptr; A.list_cnt = nullptr; A.list_max = 0;
         if (ms) {
-            A.ticket = tickets + 0; resolve_kernel<true><<<g, SDB_PULSE_THREADS, hot_bytes(tab.n_vals, tab.n_ms), stream>>>(A);
-            A.ticket = tickets + 1; scan_kernel<true><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = A.ctl + SDB_CTL_STRIDE * 1; scan_kernel<true><<<g[1], SDB_PULSE_THREADS, 0, stream>>>(A);
         } else {
-            A.ticket = tickets + 0; resolve_kernel<false><<<g, SDB_PULSE_THREADS, hot_bytes(tab.n_vals, tab.n_mu), stream>>>(A);
-            A.ticket = tickets + 1; mu_match_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            A.ticket = tickets + 2; mu_emit_kernel<<<g, SDB_PULSE_THREADS, 0, stream>>>(A);
-            A.ticket = tickets + 3; A.ticket_batch = 256; scan_kernel<false><<<g, SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
+            A.ticket = A.ctl + SDB_CTL_STRIDE * 1; mu_match_kernel<<<g[1], SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = A.ctl + SDB_CTL_STRIDE * 2; mu_emit_kernel<<<g[2], SDB_PULSE_THREADS, 0, stream>>>(A);
+            A.ticket = A.ctl + SDB_CTL_STRIDE * 3; A.ticket_batch = 256;
+            scan_kernel<false><<<g[0] < g[1] ? g[0] : g[1], SDB_PULSE_THREADS, 0, stream>>>(A);     /* fused fallback: messages with > MU_MCAP matches only */
         }
         /* messages with more than SDB_FAST_DIGITS digits (listed by the resolve kernel above; usually none) */
-        e = (cudaError_t)sdb_long::launch_long(kind, tab, A.msgs, d_digits, A.n, A.msg_base, A.out, d_hits, hits_cap, d_bits, bits_cap, d_ctr,
-                                               A.surv, A.surv_cnt, A.surv_stride, A.long_list, A.long_cnt, tickets + 4, grid_long, stream);
+        A.ticket_batch = 1;
+        A.list = A.long_list; A.list_cnt = SDB_CTL(A, SDB_CTL_LONG_CNT); A.list_max = A.n;
+        cudaError_t e = (cudaError_t)sdb_long::launch_long(kind, A, grid_long, stream);
         if (e != cudaSuccess) return (int)e;
     }
+    fold_ctl_kernel<<<1, 32, 0, stream>>>(A.ctl, stats);
     return (int)cudaGetLastError();
 }
 
@@ -2037,11 +2197,11 @@ int long_blocks_per_sm(const SdbDevTable &tab)
 {
     int a = 0, b = 0, c = 0, d = 0;
     const size_t dms = hot_bytes(tab.n_vals, tab.n_ms), dmu = hot_bytes(tab.n_vals, tab.n_mu);
-    cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
-    cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true>, KTHREADS, dms);
+    cudaFuncSetAttribute(resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    cudaFuncSetAttribute(resolve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_bytes(SDB_MAX_VALS, 255));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, resolve_kernel<true, false>, KTHREADS, dms);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, scan_kernel<true>, KTHREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false>, KTHREADS, dmu);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, resolve_kernel<false, false>, KTHREADS, dmu);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, scan_kernel<false>, KTHREADS, 0);
     int nb = a;
     if (b < nb) nb = b;
@@ -2066,7 +2226,7 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) unit_pattern_kernel(SdbKe
     if (lane == 0) { m.doff = 0; m.dlen = (uint16_t)dlen; m.npat = (uint8_t)npat; m.cp = 0xFF; m.pat_ids = pat_ids; m.flags = SDB_MSG_VALID; }
     if (lane < 8) m.pat[lane] = 0;
     __syncwarp();
-    stage_message(A, sm, &m, dlen, 0);
+    stage_message<true>(A, sm, &m, dlen, 0);
     const int t_slot = tenths[lane & 7];
     uint64_t tgt = 0;
     int pos = 0;
@@ -2084,23 +2244,18 @@ int launch_unit_pattern(const SdbKeyTpl &tpl, const uint16_t *d_rank, const int1
 }
 
 /* The messages the fast resolve kernel listed (SDB_FAST_DIGITS < dlen <= SDB_MAX_DIGITS): resolve + fused scan, sized for
- * the long staging buffers.  Arguments are the fast launch's own (same chunk, same scratch); tickets = two zeroed counters. */
-int launch_long(int kind, const SdbDevTable &tab, const SdbPulseMsg *d_msgs, const uint8_t *d_digits, uint32_t n,
-                uint32_t msg_base, SdbMsgOut *d_out, SdbHit *d_hits, uint32_t hits_cap, uint32_t *d_bits, uint32_t bits_cap,
-                SdbCounters *d_ctr, void *surv, uint32_t *surv_cnt, uint32_t surv_stride, uint32_t *long_list, uint32_t *long_cnt,
-                uint32_t *tickets, int grid, cudaStream_t stream)
+ * the long staging buffers.  A0 = the fast launch group's own arguments with `list` set to the long list; survivors are
+ * claimed from the same compact arena, after the fast kernels' (which are done with theirs: stream order). */
+int launch_long(int kind, const SdbPulseArgs &A0, int grid, cudaStream_t stream)
 {
-    KArgs A;
-    A.tab = tab; A.msgs = d_msgs; A.digits = d_digits; A.n = n; A.msg_base = msg_base; A.out = d_out;
-    A.hits = d_hits; A.hits_cap = hits_cap; A.bits = d_bits; A.bits_cap = bits_cap; A.ctr = d_ctr;
-    A.surv = static_cast<SdbSurv *>(surv); A.surv_cnt = surv_cnt; A.surv_stride = surv_stride;
-    A.match = nullptr; A.match_cnt = nullptr; A.ticket_batch = 1; A.long_list = long_list; A.long_cnt = long_cnt;
+    KArgs A = A0;
+    A.ticket_batch = 1;
     if (kind == SDB_KIND_MS) {
-        A.ticket = tickets + 0; resolve_kernel<true><<<grid, KTHREADS, hot_bytes(tab.n_vals, tab.n_ms), stream>>>(A);
-        A.ticket = tickets + 1; scan_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 4; resolve_kernel<true, false><<<grid, KTHREADS, hot_bytes(A.tab.n_vals, A.tab.n_ms), stream>>>(A);
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 5; scan_kernel<true><<<grid, KTHREADS, 0, stream>>>(A);
     } else {
-        A.ticket = tickets + 0; resolve_kernel<false><<<grid, KTHREADS, hot_bytes(tab.n_vals, tab.n_mu), stream>>>(A);
-        A.ticket = tickets + 1; scan_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 4; resolve_kernel<false, false><<<grid, KTHREADS, hot_bytes(A.tab.n_vals, A.tab.n_mu), stream>>>(A);
+        A.ticket = A.ctl + SDB_CTL_STRIDE * 5; scan_kernel<false><<<grid, KTHREADS, 0, stream>>>(A);
     }
     return (int)cudaGetLastError();
 }

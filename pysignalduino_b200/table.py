@@ -336,6 +336,8 @@ def _fill_key(rec, values, pool: _RankPool, what: str):
     rec["uidx"] = uidx
     for u, s in enumerate(uniq):
         lo, hi, off = pool.get(s)
+        if lo < -15000 or hi > 15000:          # the kernels keep tenths as biased 15-bit values (csrc/sdb_pulse.cu: T_BIAS / T_CLAMP)
+            raise NotImplementedError(f"{what}: accept interval [{lo}, {hi}] tenths outside +-15000")
         rec["lo"][u], rec["hi"][u], rec["rank_off"][u] = lo, hi, off
 
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdb_abi_version() == 2
+    assert lib.sdb_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu():
