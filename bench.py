@@ -367,13 +367,14 @@ def run_ours(args):
                                  s["d_hits"].data_ptr(), s["hits_cap"], s["d_bits"].data_ptr(), s["bits_cap"],
                                  s["d_ctr"].data_ptr(), stream)
 
-    # our kernels per step, per SDB_MU_CHUNK = 1048576 resident messages: MS = resolve + scan, MU = resolve + match + emit +
-    # fused fallback, each followed by the two long-message kernels (resolve + scan; they exit at once when no message has
-    # more than 1024 digits); MC and MN one launch each (sdb_pulse.cu launch_pulse)
+    # our kernels per step, per SDB_MU_CHUNK = 1048576 resident messages (sdb_pulse.cu launch_pulse): the counter fold, then
+    # MS = resolve + overflow pass + scan, MU = resolve + overflow pass + match + emit + fused fallback, each followed by the two
+    # long-message kernels (resolve + scan); the overflow pass and the long kernels exit at once when their list is empty.  One
+    # more counter fold ends a call.  MC and MN: one launch each.
     CHUNK = 1048576
 
     def launches(nmsgs):
-        return sum(((4 if s["kind"] == 0 else 6) * ((nm + CHUNK - 1) // CHUNK)) if s["kind"] <= 1 else 1 for s, nm in zip(slots, nmsgs))
+        return sum(((6 if s["kind"] == 0 else 8) * ((nm + CHUNK - 1) // CHUNK) + 1) if s["kind"] <= 1 else 1 for s, nm in zip(slots, nmsgs))
 
     def barrier():
         if world > 1:
@@ -748,6 +749,9 @@ def run_ours(args):
         "hit_histogram": {"protocols_with_hits": int((hist > 0).sum()), "total_hits": int(hist.sum()), "ranks": world,
                           "top": {eng.table.ids[int(i)]: int(hist[int(i)]) for i in top}},
         "api": api, "other_scaling": other,
+        "scratch": dict(flagged_messages=eng.scratch_short(), **eng.scratch_info(),
+                        note="compact survivor / match arenas of the device-resident handle (bytes per launch group of `chunk` messages; "
+                             "round 1: chunk x 129 x 16 B + chunk x 64 x 4 B = 2.2 GB per 1 048 576 messages)"),
         "host": {"cpus": os.cpu_count(), "rank0_affinity_cpus": len(numa_cpus) if numa_cpus else None,
                  "numa_binding": "rank pinned to its GPU's NVML CPU affinity before pinned buffers are allocated" if numa_cpus else "none"},
         "corpus_gen_s": t_gen, "lines": lines_info,

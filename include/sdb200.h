@@ -196,12 +196,12 @@ int sdb_demod_pulse_device(SdbHandle *h, int kind,
 int sdb_reserve(SdbHandle *h, uint32_t n_messages);
 
 /*
- * The scratch holds COMPACT survivor / match records: every warp claims blocks of 256 survivor records (16 B each) / 1024 match
- * records (4 B each) from per-launch-group arenas and fills them message after message.  The arenas are sized for 18 survivor
- * and 12 match records per message on average (the benchmark corpus needs 14.6 and 6.7) plus one block per resident warp, and
- * worst-case slots for 8192 messages per launch group take what did not fit — 0.41 GB per 1 048 576-message group instead of
+ * The scratch holds COMPACT survivor / match records: every warp claims blocks of 256 survivor records (16 B each) / 512 match
+ * records (4 B each) from per-launch-group arenas and fills them message after message.  The arenas are sized for 17 survivor
+ * and 8 match records per message on average (the benchmark corpus needs 14.6 and 6.7) plus one block per resident warp, and
+ * worst-case slots for 4096 messages per launch group take what did not fit — 0.39 GB per 1 048 576-message group instead of
  * the 2.2 GB that room for every protocol of every message took.  A launch group that needs more (a batch averaging more than
- * 18 surviving protocols per message AND more than 8192 messages that did not fit) leaves the excess messages undecoded with
+ * 17 surviving protocols per message AND more than 4096 messages that did not fit) leaves the excess messages undecoded with
  * status SDB_ST_SCRATCH.  The host-buffer calls notice, grow the scratch from the recorded need and repeat the call.  After
  * device-pointer calls, sdb_scratch_short() synchronises the device, stores in *n_short how many messages were flagged since
  * the last check and grows the budgets (the next call reallocates), so that submitting the flagged messages again succeeds.
@@ -211,8 +211,10 @@ int sdb_scratch_short(SdbHandle *h, uint32_t *n_short);
  * worst-case region; slack_warps = 0 (automatic) unless a test wants the arenas smaller than one block per resident warp on top
  * of the budgets.  Synchronises and releases the current block; the next call allocates with the new budgets. */
 int sdb_scratch_budget(SdbHandle *h, uint32_t surv_avg, uint32_t match_avg, uint32_t ovf_max, uint32_t slack_warps);
-/* Bytes of the scratch block as allocated (0 = none yet); cfg = {messages per launch group, surv_avg, match_avg, ovf_max}. */
-size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[4]);
+/* Bytes of the scratch block as allocated (0 = none yet); cfg = {messages per launch group, surv_avg, match_avg, ovf_max, arena
+ * blocks added on top (warps), and the largest values any sdb_scratch_short() / host-buffer call has read back: the
+ * survivor-arena claim of a launch group (records), the match-arena claim, the overflow list}. */
+size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[8]);
 
 /* Same for MC / MN (sd_protocols.py:76-155, manchester.py, helpers.py:223-716).
  * mc_repaired: 0 = as shipped (TypeError, SURVEY §8c "strict"), 1 = the two documented one-line repairs. */

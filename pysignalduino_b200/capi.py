@@ -83,7 +83,7 @@ def load_library() -> C.CDLL:
     L.sdb_scratch_budget.restype = C.c_int
     L.sdb_scratch_budget.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.sdb_scratch_info.restype = C.c_size_t
-    L.sdb_scratch_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32 * 4)]
+    L.sdb_scratch_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32 * 8)]
     L.sdb_format_hits.restype = C.c_int
     L.sdb_format_hits.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p, C.POINTER(C.c_size_t)]
@@ -296,9 +296,12 @@ class Engine:
             raise self._err(rc, "sdb_scratch_budget")
 
     def scratch_info(self) -> dict:
-        cfg = (C.c_uint32 * 4)()
+        """Size and budgets of the scratch block, and the need the last ``scratch_short()`` / host-buffer call read back."""
+        cfg = (C.c_uint32 * 8)()
         nbytes = self.lib.sdb_scratch_info(self.h, C.byref(cfg))
-        return {"bytes": int(nbytes), "chunk": int(cfg[0]), "surv_avg": int(cfg[1]), "match_avg": int(cfg[2]), "ovf_max": int(cfg[3])}
+        return {"bytes": int(nbytes), "chunk": int(cfg[0]), "surv_avg": int(cfg[1]), "match_avg": int(cfg[2]), "ovf_max": int(cfg[3]),
+                "arena_blocks": int(cfg[4]), "need_surv_records": int(cfg[5]), "need_match_records": int(cfg[6]),
+                "need_overflow_messages": int(cfg[7])}
 
     def _err(self, rc: int, what: str) -> SdbError:
         return SdbError(f"{what} failed ({rc}): {(self.lib.sdb_last_error(self.h) or b'').decode()}")

@@ -43,6 +43,7 @@ struct SdbHandle {
     uint32_t want_surv = SDB_SURV_AVG_DEFAULT, want_match = SDB_MATCH_AVG_DEFAULT, want_ovf = SDB_OVF_MAX_DEFAULT;   /* budgets (grown from the recorded need) */
     uint32_t slack_warps = 0;           /* 0 = one arena block per resident warp on top of the budgets; else that many (tests of the overflow paths) */
     uint32_t *h_stats = nullptr;        /* pinned copy of the scratch statistics */
+    uint32_t seen[3] = {0, 0, 0};       /* largest survivor-arena claim / match-arena claim / overflow list any check has read back */
     cudaStream_t stream = nullptr;      /* compute + final copies of the host-buffer path */
     cudaStream_t copy_stream = nullptr; /* pipelined H2D */
     cudaStream_t d2h_stream = nullptr;  /* pipelined D2H of the per-message result slots */
@@ -238,6 +239,9 @@ static int check_scratch(SdbHandle *h, cudaStream_t st, uint32_t *n_short)
     CK(cudaStreamSynchronize(st));
     const uint64_t chunk = h->scfg.chunk ? h->scfg.chunk : 1;
     const uint64_t need_surv = h->h_stats[SDB_STAT_SURV], need_match = h->h_stats[SDB_STAT_MATCH], need_ovf = h->h_stats[SDB_STAT_OVF];
+    if (need_surv > h->seen[0]) h->seen[0] = (uint32_t)need_surv;
+    if (need_match > h->seen[1]) h->seen[1] = (uint32_t)need_match;
+    if (need_ovf > h->seen[2]) h->seen[2] = (uint32_t)need_ovf;
     uint32_t caps[2];
     sdb::pulse_scratch_caps(stride, h->scfg, caps);
     if (need_surv > caps[0]) {                                  /* the overflow pass had to help: 25 % above the need from now on */
@@ -302,11 +306,17 @@ extern "C" int sdb_scratch_budget(SdbHandle *h, uint32_t surv_avg, uint32_t matc
     return SDB_OK;
 }
 
-/* bytes of the scratch block as allocated, and its budgets: {chunk, surv_avg, match_avg, ovf_max} */
-extern "C" size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[4])
+/* bytes of the scratch block as allocated; cfg = {messages per launch group, surv_avg, match_avg, ovf_max, arena blocks on top
+ * (warps), then the largest values any sdb_scratch_short() / host-buffer call has read back: survivor-arena claim of a launch
+ * group (records), match-arena claim, overflow list} */
+extern "C" size_t sdb_scratch_info(const SdbHandle *h, uint32_t cfg[8])
 {
-    if (!h || !h->d_scratch) { if (cfg) cfg[0] = cfg[1] = cfg[2] = cfg[3] = 0; return 0; }
-    if (cfg) { cfg[0] = h->scfg.chunk; cfg[1] = h->scfg.surv_avg; cfg[2] = h->scfg.match_avg; cfg[3] = h->scfg.ovf_max; }
+    if (cfg) for (int i = 0; i < 8; i++) cfg[i] = 0;
+    if (!h || !h->d_scratch) return 0;
+    if (cfg) {
+        cfg[0] = h->scfg.chunk; cfg[1] = h->scfg.surv_avg; cfg[2] = h->scfg.match_avg; cfg[3] = h->scfg.ovf_max; cfg[4] = h->scfg.warps;
+        cfg[5] = h->seen[0]; cfg[6] = h->seen[1]; cfg[7] = h->seen[2];
+    }
     return sdb::pulse_scratch_bytes(pulse_stride(h), h->scfg);
 }
 

@@ -26,9 +26,9 @@ struct SdbScratchCfg {
     uint32_t ovf_max;      /* messages the worst-case overflow region holds          */
     uint32_t warps;        /* warps of the largest persistent grid (one block of each arena per warp on top of the budgets) */
 };
-#define SDB_SURV_AVG_DEFAULT 18u
-#define SDB_MATCH_AVG_DEFAULT 12u
-#define SDB_OVF_MAX_DEFAULT 8192u
+#define SDB_SURV_AVG_DEFAULT 17u
+#define SDB_MATCH_AVG_DEFAULT 8u
+#define SDB_OVF_MAX_DEFAULT 4096u
 /* persistent statistics of a scratch block (device words, read back by the host paths) */
 #define SDB_STAT_SURV 0    /* largest number of survivor records any launch group asked for        */
 #define SDB_STAT_MATCH 1   /* ... of match records                                                 */
@@ -84,7 +84,7 @@ struct SdbPulseArgs {
  * records are left than the next message could need (protocols that passed the prefilter / MU_MCAP).  The arenas hold one
  * block per resident warp on top of the per-message budgets (the blocks in use when a kernel ends). */
 #define SDB_SURV_BLOCK 256u    /* >= protocols per class (<= 255) */
-#define SDB_MATCH_BLOCK 1024u  /* >= MU_MCAP */
+#define SDB_MATCH_BLOCK 512u   /* >= MU_MCAP */
 #define SDB_SURV_SHORT 0xFFFFFFFFu
 
 namespace sdb {
