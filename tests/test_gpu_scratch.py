@@ -96,3 +96,33 @@ def test_device_calls_flag_messages_and_resubmission_succeeds(own, oracle, corpu
     assert not (out2["status"] == ST_SCRATCH).any()
     assert eng.scratch_short() == 0
     assert [int(x) for x in out2["nhits"]] == [len(e[1]) for e in exp]
+
+
+def test_lines_call_grows_the_scratch_and_repeats(own, corpus):
+    """sdb_demod_lines_host (tokenizer + decode kernels) goes through the same growth and repetition: with budgets that flag
+    most messages on the first attempt its results equal those of the roomy default."""
+    kind = pack.KIND_MU
+    n = 5000
+    b = corpus.pulse(kind, n)
+    lines = []
+    for i in range(n):
+        d = pack.unpack_pulse(b, i)
+        if not d.get("data"):
+            d = {"data": "", "P0": "1"}
+        lines.append((";".join(["MU"] + [f"{k}={v}" for k, v in d.items() if k.startswith("P")] + [f"D={d['data']}"]) + ";").encode("ascii"))
+    lens = np.fromiter((len(x) for x in lines), dtype=np.int64, count=n)
+    offs = np.zeros(n, dtype=np.int64)
+    np.cumsum(lens[:-1] + 1, out=offs[1:])
+    text = np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+    eng = own.engine()
+    ref, ref_info = eng.demod_lines(kind, text, offs.astype(np.uint32), lens.astype(np.uint32))
+    eng.scratch_budget(surv_avg=1, match_avg=8, ovf_max=16, slack_warps=1)
+    res, info = eng.demod_lines(kind, text, offs.astype(np.uint32), lens.astype(np.uint32))
+    assert not (res.out["status"] == ST_SCRATCH).any()
+    assert np.array_equal(info["status"], ref_info["status"])
+    assert np.array_equal(res.out["status"], ref.out["status"]) and np.array_equal(res.out["nhits"], ref.out["nhits"])
+    assert int(res.counters["hits"]) == int(ref.counters["hits"]) > 0
+    o1 = np.lexsort((np.arange(len(res.hits)), res.hits["msg"].astype(np.int64)))
+    o2 = np.lexsort((np.arange(len(ref.hits)), ref.hits["msg"].astype(np.int64)))
+    for f in ("msg", "proto", "nbits", "aux", "flags"):
+        assert np.array_equal(res.hits[f][o1], ref.hits[f][o2]), f
