@@ -102,6 +102,13 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) { return *p; }
 #define LD_STREAM(p) ld_stream(p)
 
 #define FULL 0xffffffffu
+/* Functions with exactly ONE call site per kernel are inlined: no code growth, and a call is expensive here (at the 64-register
+ * cap the ABI saves and restores the live registers around it) — emit kernel −24 %, MS scan −9 %, match −3 % (profiles/README.md).
+ * Functions with several call sites stay out of line (instruction-cache footprint); the per-message drivers of the match and
+ * emit kernels have a second, rare call site (re-run writing in place), which goes through an out-of-line wrapper.
+ * The resolve kernels are a local optimum in BOTH directions: inlining tpre / resolve_general / resolve_*_warp costs 3-9 %,
+ * moving prepare_tables / stage_message / thread_resolve_mu out of line costs 9-18 % (measured, profiles/README.md). */
+#define FN_ONE_SITE __device__ __forceinline__
 #define DIG_WORDS (KMAXD / 8 + 4)
 #define BIT_WORDS (KMAXD / 32 + 4)
 #define ST_HITS 24
@@ -518,7 +525,7 @@ __device__ int payload_char(const Payload &P, int i)
     return -1;
 }
 /* modulematch (message_unsynced.py:277-280) as a fixed-offset character-class program */
-__device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmItem *__restrict__ items, int nb, bool has_f)
+FN_ONE_SITE bool modulematch(const SdbPulseProto *pp, const SdbMmItem *__restrict__ items, int nb, bool has_f)
 {
     WarpSm &sm = SM();
     const int flags = pp->flags;
@@ -570,8 +577,12 @@ __device__ __noinline__ bool modulematch(const SdbPulseProto *pp, const SdbMmIte
     return true;
 }
 
+/* emit_hit <- finish_match <- mu_emit_match / scan_ms: each has exactly one call site per kernel (inside the out-of-line
+ * mu_emit_records / scan_survivors_mu / scan_survivors), so inlining the chain costs no code and saves three calls per match */
+#define CHAIN_FN FN_ONE_SITE
+
 /* ---- hit sink: shared-memory staging, or direct global writes on the rare second pass ------ */
-__device__ __noinline__ void emit_hit(const KArgs &A, const SdbPulseProto *pp, int nb, bool has_f, int ordinal, bool mm_host)
+CHAIN_FN void emit_hit(const KArgs &A, const SdbPulseProto *pp, int nb, bool has_f, int ordinal, bool mm_host)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -607,7 +618,7 @@ __device__ __forceinline__ int pad_up(int nb, int pad)
 }
 
 /* post-demodulation on lane 0 (rare: ~10 of 129 protocols, frames <= ~150 bits) */
-__device__ __noinline__ void run_postdemod(int method, int nb)
+FN_ONE_SITE void run_postdemod(int method, int nb)
 {
     WarpSm &sm = SM();
     for (int w = lane_id(); w < BIT_WORDS; w += 32) sm.tmp[IDX(w, BIT_WORDS)] = 0;
@@ -623,7 +634,7 @@ __device__ __noinline__ void run_postdemod(int method, int nb)
 /* Shared tail of an MS / MU match: the bits are in sm.val / sm.fpl (nb of them, zero beyond).
  * Returns SDB_ST_* (non-OK aborts the message). */
 template <bool MS>
-__device__ __noinline__ int finish_match(const KArgs &A, const SdbPulseProto *pp, int nb, int ordinal, bool maybe_f)
+CHAIN_FN int finish_match(const KArgs &A, const SdbPulseProto *pp, int nb, int ordinal, bool maybe_f)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -711,7 +722,7 @@ __device__ __forceinline__ uint32_t eq_nibbles8(uint32_t x, uint32_t c8)
  * the shared bitmaps; the warp only cooperates again to turn a match into bits (ballots), post-demodulate and emit.
  */
 /* warp: bitmap of the positions where a w-digit symbol of {c1, c0, cf} starts -> dst[0 .. nw + 1] */
-__device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint32_t c0, uint32_t cf, int nw)
+FN_ONE_SITE void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint32_t c0, uint32_t cf, int nw)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -804,7 +815,7 @@ __device__ __noinline__ void mu_build_B(uint32_t *dst, int w, uint32_t c1, uint3
 }
 
 /* warp: bitmap of the occurrences of the Ls-digit start string -> dst[0 .. nw + 1] */
-__device__ __noinline__ void mu_build_S(uint32_t *dst, int Ls, uint64_t start_t, int nw)
+FN_ONE_SITE void mu_build_S(uint32_t *dst, int Ls, uint64_t start_t, int nw)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -930,7 +941,7 @@ __device__ __forceinline__ void mu_step(const uint32_t *dig, MuLane &L, int nwB)
 }
 
 /* warp: one match -> bits (:220-228: later keys overwrite earlier ones on identical strings) -> finish_match */
-__device__ __noinline__ int mu_emit_match(const KArgs &A, const SdbPulseProto *pp, uint32_t rec, uint32_t c1, uint32_t c0,
+CHAIN_FN int mu_emit_match(const KArgs &A, const SdbPulseProto *pp, uint32_t rec, uint32_t c1, uint32_t c0,
                                           uint32_t cf, bool hasf, int ordinal)
 {
     WarpSm &sm = SM();
@@ -980,7 +991,7 @@ __device__ __forceinline__ uint64_t mu_sort3_key(uint32_t a, uint32_t b, uint32_
  * nrec counts them (SDB_ST_MU_OVERFLOW when they do not fit); REC = false: every match is emitted on the spot. */
 #define SDB_ST_MU_OVERFLOW 0x7F
 template <bool REC>
-__device__ __noinline__ int scan_survivors_mu(const KArgs &A, const SdbSurv *slots, uint32_t nsurv, uint32_t *recs, uint32_t &nrec)
+FN_ONE_SITE int scan_survivors_mu_impl(const KArgs &A, const SdbSurv *slots, uint32_t nsurv, uint32_t *recs, uint32_t &nrec)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
@@ -1318,11 +1329,11 @@ __device__ __forceinline__ int thread_resolve_ms(const HotRow &hr, const SdbPuls
     return 1;
 }
 
-__device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
+FN_ONE_SITE int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
                                     uint32_t cf, bool hasf);
 
 /* the chunk loop of one resolved (message x MS protocol) task: message_synced.py:171-241 */
-__device__ __noinline__ int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
+FN_ONE_SITE int scan_ms(const KArgs &A, const SdbPulseProto *pp, int ms, uint32_t cs, uint32_t c1, uint32_t c0,
                                     uint32_t cf, bool hasf)
 {
     WarpSm &sm = SM();
@@ -1778,6 +1789,13 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
     }
 }
 
+/* the fused fallback kernel has two call sites (second pass: writing in place): always out of line */
+__device__ __noinline__ int scan_survivors_mu_fused(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
+{
+    uint32_t unused = 0;
+    return scan_survivors_mu_impl<false>(A, slots, nsurv, nullptr, unused);
+}
+
 template <bool MS>
 __device__ __noinline__ int scan_survivors(const KArgs &A, const SdbSurv *slots, uint32_t nsurv)
 {
@@ -1834,7 +1852,7 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
             const SdbSurv *slots = A.surv + sv.x;
             stage_digits(A, sm, m, m->dlen, mi);
             uint32_t unused = 0;
-            int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu<false>(A, slots, nsurv, nullptr, unused);
+            int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu_fused(A, slots, nsurv);
             __syncwarp();
             const uint32_t nh = sm.nh, nw = sm.nw;
             if (status != SDB_ST_OK) {
@@ -1863,7 +1881,7 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
                     __syncwarp();
                     if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
                     __syncwarp();
-                    if (MS) scan_survivors<MS>(A, slots, nsurv); else scan_survivors_mu<false>(A, slots, nsurv, nullptr, unused);
+                    if (MS) scan_survivors<MS>(A, slots, nsurv); else scan_survivors_mu_fused(A, slots, nsurv);
                 }
             }
         }
@@ -1897,7 +1915,7 @@ __global__ void __launch_bounds__(KTHREADS, KMATCH_CTAS) mu_match_kernel(KArgs A
                 status = SDB_ST_MU_OVERFLOW;                          /* match arena exhausted: the fused fallback kernel takes the message */
             else {
                 moff = sm.blk_off;
-                status = scan_survivors_mu<true>(A, A.surv + sv.x, nsurv, A.match + moff, nrec);
+                status = scan_survivors_mu_impl<true>(A, A.surv + sv.x, nsurv, A.match + moff, nrec);
                 __syncwarp();
                 if (status == SDB_ST_OK && lane == 0) { sm.blk_off = moff + nrec; sm.blk_left -= nrec; }
             }
@@ -1923,7 +1941,7 @@ __global__ void __launch_bounds__(KTHREADS, KMATCH_CTAS) mu_match_kernel(KArgs A
 }
 
 /* the records of one message -> bits, post-demodulation, modulematch, staged hits */
-__device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slots, const uint32_t *recs, uint32_t nrec)
+FN_ONE_SITE void mu_emit_records_impl(const KArgs &A, const SdbSurv *slots, const uint32_t *recs, uint32_t nrec)
 {
     const int lane = lane_id();
     int prev = -1, ordinal = 0;
@@ -1952,6 +1970,11 @@ __device__ __noinline__ void mu_emit_records(const KArgs &A, const SdbSurv *slot
     }
 }
 
+__device__ __noinline__ void mu_emit_records_again(const KArgs &A, const SdbSurv *slots, const uint32_t *recs, uint32_t nrec)
+{
+    mu_emit_records_impl(A, slots, recs, nrec);              /* the rare second pass, writing in place */
+}
+
 /* MU, kernel 3 of 3: match records -> hits (message_unsynced.py:220-290) */
 __global__ void __launch_bounds__(KTHREADS, KEMIT_CTAS) mu_emit_kernel(KArgs A)
 {
@@ -1969,7 +1992,7 @@ __global__ void __launch_bounds__(KTHREADS, KEMIT_CTAS) mu_emit_kernel(KArgs A)
         SdbMsgOut mo;
         mo.hit_off = 0; mo.nhits = 0; mo.status = SDB_ST_OK; mo.reason = 0;
         stage_digits(A, sm, m, m->dlen, mi);
-        mu_emit_records(A, slots, recs, nrec);
+        mu_emit_records_impl(A, slots, recs, nrec);
         __syncwarp();
         const uint32_t nh = sm.nh, nw = sm.nw;
         if (nh) {
@@ -1995,7 +2018,7 @@ __global__ void __launch_bounds__(KTHREADS, KEMIT_CTAS) mu_emit_kernel(KArgs A)
                 __syncwarp();
                 if (lane == 0) { sm.nh = 0; sm.nw = 0; sm.direct = 1; sm.overflow = 0; sm.hbase = hb; sm.wbase = wb; }
                 __syncwarp();
-                mu_emit_records(A, slots, recs, nrec);
+                mu_emit_records_again(A, slots, recs, nrec);
             }
         }
         if (lane == 0) A.out[mi] = mo;
