@@ -197,11 +197,12 @@ int sdb_reserve(SdbHandle *h, uint32_t n_messages);
 
 /*
  * The scratch holds COMPACT survivor / match records: every warp claims blocks of 256 survivor records (16 B each) / 512 match
- * records (4 B each) from per-launch-group arenas and fills them message after message.  The arenas are sized for 17 survivor
- * and 8 match records per message on average (the benchmark corpus needs 14.6 and 6.7) plus one block per resident warp, and
- * worst-case slots for 4096 messages per launch group take what did not fit — 0.39 GB per 1 048 576-message group instead of
- * the 2.2 GB that room for every protocol of every message took.  A launch group that needs more (a batch averaging more than
- * 17 surviving protocols per message AND more than 4096 messages that did not fit) leaves the excess messages undecoded with
+ * records (4 B each) from per-launch-group arenas and fills them message after message.  The arenas are sized for 19 survivor
+ * and 8 match records per message on average plus one block per resident warp (the benchmark corpus writes 14.6 and 6.7 per
+ * message and claims 18.4 and 8.6 with the block remainders), and worst-case slots for 4096 messages per launch group take
+ * what did not fit — 0.42 GB per 1 048 576-message group instead of the 2.2 GB that room for every protocol of every message
+ * took.  A launch group that needs more (more than 19 claimed records per message AND more than 4096 messages that did not
+ * fit) leaves the excess messages undecoded with
  * status SDB_ST_SCRATCH.  The host-buffer calls notice, grow the scratch from the recorded need and repeat the call.  After
  * device-pointer calls, sdb_scratch_short() synchronises the device, stores in *n_short how many messages were flagged since
  * the last check and grows the budgets (the next call reallocates), so that submitting the flagged messages again succeeds.

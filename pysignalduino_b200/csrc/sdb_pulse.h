@@ -26,7 +26,7 @@ struct SdbScratchCfg {
     uint32_t ovf_max;      /* messages the worst-case overflow region holds          */
     uint32_t warps;        /* warps of the largest persistent grid (one block of each arena per warp on top of the budgets) */
 };
-#define SDB_SURV_AVG_DEFAULT 17u
+#define SDB_SURV_AVG_DEFAULT 19u
 #define SDB_MATCH_AVG_DEFAULT 8u
 #define SDB_OVF_MAX_DEFAULT 4096u
 /* persistent statistics of a scratch block (device words, read back by the host paths) */
