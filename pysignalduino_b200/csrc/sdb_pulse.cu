@@ -53,6 +53,7 @@
 #define KMAXD SDB_MAX_DIGITS
 #define KTHREADS SDB_LONG_THREADS
 #define KMIN_CTAS 1
+#define KRESOLVE_CTAS 1
 #define POS_BITS 13                   /* p <= 4095, n <= 4096 */
 #else
 #define KNS sdb
@@ -65,6 +66,10 @@
 #ifndef SDB_EMIT_CTAS
 #define SDB_EMIT_CTAS SDB_PULSE_MIN_CTAS
 #endif
+#ifndef SDB_RESOLVE_CTAS
+#define SDB_RESOLVE_CTAS SDB_PULSE_MIN_CTAS
+#endif
+#define KRESOLVE_CTAS SDB_RESOLVE_CTAS
 #define KMATCH_CTAS SDB_MATCH_CTAS    /* per-kernel register caps (65536 / (256 * CTAs)) for the two smaller MU kernels */
 #define KEMIT_CTAS SDB_EMIT_CTAS
 #define POS_BITS 11                   /* p <= 1023, n <= 1024 */
@@ -1639,13 +1644,15 @@ __device__ __noinline__ uint32_t overflow_push(uint32_t *ovf_cnt, uint32_t *ovf_
  * prefilter).  When the arena is exhausted the message is listed for the overflow pass.
  * OVF = true (fast build only): the overflow pass — list-driven, survivors written into worst-case slots. */
 template <bool MS, bool OVF>
-__global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) resolve_kernel(KArgs A)
+__global__ void __launch_bounds__(KTHREADS, KRESOLVE_CTAS) resolve_kernel(KArgs A)
 {
     WarpSm &sm = SM();
     const int lane = lane_id();
     const uint32_t nrows = MS ? A.tab.n_ms : A.tab.n_mu;
     const SdbPulseProto *rows = MS ? A.tab.ms : A.tab.mu;
 
+    /* list-driven launches (overflow pass, long-message kernels) usually find an empty list: leave before the table copies */
+    if ((OVF || KLIST_ALWAYS) && *A.list_cnt == 0) return;
     /* once per CTA: the pairs and the hot protocol fields into shared memory */
     {
         SdbValRow *sv = reinterpret_cast<SdbValRow *>(g_dyn);
