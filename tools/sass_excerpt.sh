@@ -10,7 +10,7 @@ cuobjdump -sass $lib 2>/dev/null | awk '
 /Function :/ { if (name != "") flush(); name=$3; n=0; delete c; next }
 /^[ \t]+\/\*[0-9a-f]+\*\// { n++; ins=$2; sub(/;$/,"",ins); split(ins,a,"."); m=a[1];
   if (ins ~ /^@/) { ins=$3; split(ins,a,"."); m=a[1] }
-  if (m=="VOTE"||m=="MATCH"||m=="REDUX"||m=="SHFL"||m=="LDL"||m=="STL"||m=="ATOMG"||m=="ATOMS"||m=="RED"||m=="POPC"||m=="FLO"||m=="SHF"||m=="LOP3"||m=="DMUL"||m=="DFMA"||m=="DADD"||m=="F2I"||m=="I2F"||m=="MUFU"||m=="BAR"||m=="LDGSTS") c[m]++;
+  if (m=="VOTE"||m=="MATCH"||m=="REDUX"||m=="SHFL"||m=="LDL"||m=="STL"||m=="ATOMG"||m=="ATOMS"||m=="RED"||m=="POPC"||m=="FLO"||m=="SHF"||m=="LOP3"||m=="VIMNMX"||m=="VIMNMX3"||m=="DMUL"||m=="DFMA"||m=="DADD"||m=="F2I"||m=="I2F"||m=="MUFU"||m=="BAR"||m=="LDGSTS") c[m]++;
   if (ins ~ /^LDG.*128/) c["LDG.128"]++; else if (m=="LDG") c["LDG"]++;
   if (ins ~ /^STG.*128/) c["STG.128"]++; else if (m=="STG") c["STG"]++;
   if (ins ~ /^LDS.*128/) c["LDS.128"]++; else if (m=="LDS") c["LDS"]++;
