@@ -1858,7 +1858,6 @@ __global__ void __launch_bounds__(KTHREADS, KMIN_CTAS) scan_kernel(KArgs A)
         if (nsurv) {
             const SdbSurv *slots = A.surv + sv.x;
             stage_digits(A, sm, m, m->dlen, mi);
-            uint32_t unused = 0;
             int status = MS ? scan_survivors<MS>(A, slots, nsurv) : scan_survivors_mu_fused(A, slots, nsurv);
             __syncwarp();
             const uint32_t nh = sm.nh, nw = sm.nw;
