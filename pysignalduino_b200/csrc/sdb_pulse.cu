@@ -256,11 +256,12 @@ struct HotRow {                       /* 52 bytes */
 extern __shared__ __align__(16) uint8_t g_dyn[];
 #define HOT_VALS() (reinterpret_cast<const SdbValRow *>(g_dyn))
 #define HOT_ROWS(nvals) (reinterpret_cast<const HotRow *>(g_dyn + (((nvals) * sizeof(SdbValRow) + 15) & ~(size_t)15)))
-/* then, 16-byte aligned, the MU clocks: n_clk values and n_clk times 10 / clock */
+/* then, 16-byte aligned, doubles: MU the clocks (n_clk values and n_clk times 10 / clock), MS the clock of every protocol row */
 #define HOT_CLK(nvals, nrows) (reinterpret_cast<const double *>(g_dyn + (((nvals) * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((nrows) * sizeof(HotRow) + 15) & ~(size_t)15)))
 __host__ __device__ __forceinline__ size_t hot_bytes(uint32_t nvals, uint32_t nrows)
 {
-    return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((size_t)nrows * sizeof(HotRow) + 15) & ~(size_t)15) + 2 * SDB_MAX_CLK * sizeof(double) + 16;
+    const size_t ndbl = nrows > 2 * SDB_MAX_CLK ? nrows : 2 * SDB_MAX_CLK;       /* MU: clocks and 10 / clock; MS: one clock per protocol row */
+    return ((nvals * sizeof(SdbValRow) + 15) & ~(size_t)15) + (((size_t)nrows * sizeof(HotRow) + 15) & ~(size_t)15) + ndbl * sizeof(double) + 16;
 }
 
 /* biased tenths (see WarpSm::T): every accept interval of a compiled table lies well inside +-T_CLAMP (table.py checks) */
@@ -896,7 +897,7 @@ __device__ __forceinline__ void mu_step(const uint32_t *dig, MuLane &L, int nwB)
             int j = from >> 5;
             uint32_t first = FULL << (from & 31);
             cd = MU_NONE;
-#pragma unroll 1
+#pragma unroll 2
             for (; j <= nwB; j++) {
                 uint32_t cw = cmask & first;
                 first = FULL;
@@ -1673,9 +1674,11 @@ __global__ void __launch_bounds__(KTHREADS, KRESOLVE_CTAS) resolve_kernel(KArgs 
             h.width = pr->width; h.clk_idx = (uint8_t)pr->clk_idx; h.regex_min = pr->regex_min;
             hrw[r] = h;
         }
+        double *hc = const_cast<double *>(HOT_CLK(A.tab.n_vals, nrows));
         if (!MS) {
-            double *hc = const_cast<double *>(HOT_CLK(A.tab.n_vals, nrows));
             for (uint32_t c = threadIdx.x; c < 2 * A.tab.n_clk; c += blockDim.x) hc[c] = A.tab.clk[c];
+        } else {
+            for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) hc[r] = rows[r].clock;     /* for the 30 % clock gate of pass 1 */
         }
         __syncthreads();
     }
@@ -1713,7 +1716,7 @@ __global__ void __launch_bounds__(KTHREADS, KRESOLVE_CTAS) resolve_kernel(KArgs 
                     if (q < nrows) {
                         ok = !((sm.dead[IDX(q >> 5, SDB_KILL_WORDS)] >> (q & 31)) & 1);
                         if (MS && ok) {
-                            const double pclk = rows[q].clock;
+                            const double pclk = HOT_CLK(A.tab.n_vals, nrows)[q];
                             ok = !(pclk > 0.0 && fabs(__dsub_rn(pclk, clock_abs)) > __dmul_rn(clock_abs, 0.3));
                         }
                     }
