@@ -144,7 +144,10 @@ extern "C" int sdb_create(const void *blob, size_t blob_len, int device, SdbHand
     sdb::pulse_blocks_per_sm(SDB_KIND_MU, h->tab, h->grid_mu);
     for (int i = 0; i < 3; i++) { h->grid_ms[i] *= h->sm_count; h->grid_mu[i] *= h->sm_count; }
     CKC(cudaMallocHost(reinterpret_cast<void **>(&h->h_stats), SDB_STAT_WORDS * sizeof(uint32_t)));
-    h->grid_hex = h->sm_count * 8;
+    /* hex kernel: one thread per message, grid-stride; 16 CTAs of 128 threads are resident per SM, and three times that many
+     * CTAs even out the very different message costs (sweep 8 / 16 / 24 / 32 / 48 / 64 CTAs per SM: MC 1.33 / 1.49 / 1.54 / 1.61 /
+     * 1.68 / 1.69 G msg/s, MN 1.79 ... 1.96; tools/hex_sweep.py with SDB_HEX_CTAS) */
+    h->grid_hex = h->sm_count * (getenv("SDB_HEX_CTAS") ? atoi(getenv("SDB_HEX_CTAS")) : 48);
     h->grid_long = h->sm_count * sdb_long::long_blocks_per_sm(h->tab);
 #undef CKC
     *out = h;
