@@ -29,6 +29,7 @@
  * instantiation of the same kernel with a 4.6 KB staging buffer per warp (2 warps per CTA; exits at once when the list is empty).
  */
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../../include/sdb200.h"
@@ -327,7 +328,7 @@ int launch_tokenize(int kind, const uint8_t *d_text, const uint32_t *d_off, cons
     cudaError_t e = cudaMemsetAsync(d_long, 0, 2 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
     uint32_t need = (n + LN_WARPS - 1) / LN_WARPS;
-    uint32_t grid = (uint32_t)sm_count * 8;
+    uint32_t grid = (uint32_t)sm_count * 24;       /* (8 CTAs per SM: 101.9 M lines/s through the whole text path, 24: 103.2 M) */
     if (need < grid) grid = need;
     const uint32_t grid_long = (uint32_t)sm_count * 4;
     if (kind == SDB_KIND_MU) {
